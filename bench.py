@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- Llama-3-8B-shaped 4-bit (gs=64, axis=1) decode tokens/s on B200 through hqq_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one decoded token (bs=1, seq=1) through all 32 blocks + lm_head of a random-init Llama-3-8B-shaped
+stack whose 224 block linears are HQQLinear layers quantised on the GPU by this package (synthetic data, BASELINE.json
+configs[1]).  `value` is tokens/s with the token fed back on the device (inputs resident in HBM); `e2e` is the same loop
+driven from the host through the public API: every step copies the input token from pinned host memory, replays the
+decode graph and reads the produced token back.  For N > 1 the same model is tensor-parallel over N GPUs (column-sharded
+q/k/v/gate/up, row-sharded o/down + one NCCL all-reduce each), i.e. strong scaling.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port of HQQBackend.PYTORCH:
+dequantise -> matmul per linear) on this box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "llama3_8b_4bit_gs64_decode_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_tokens_per_s(budget_s: float = 20.0, n_blocks_sample: int = 1):
+    """HQQBackend.PYTORCH on the host: per linear, dequantise the whole matrix then matmul (quantize.py:880-898), float32
+    compute dtype (the reference's CPU path), through the oracle port.  Bounded sample: `n_blocks_sample` of the 32 blocks
+    (7 linears each) at bs=1; the per-token figure extrapolates x32 and adds the fp32 lm_head GEMV."""
+    import numpy as np
+    from oracle import hqq_oracle as o
+    rng = np.random.RandomState(0)
+    shapes = {"q": (4096, 4096), "k": (1024, 4096), "v": (1024, 4096), "o": (4096, 4096), "gate": (14336, 4096),
+              "up": (14336, 4096), "down": (4096, 14336)}
+    layers = {}
+    for name, (n, k) in shapes.items():
+        R = n * k // 64
+        W_q = rng.randint(0, 256, size=(R // 2, 64)).astype(np.uint8)
+        meta = {"nbits": 4, "group_size": 64, "shape": (n, k), "axis": 1, "packing": "4bit_u8",
+                "scale": (rng.rand(R, 1) * 0.01 + 1e-3).astype(np.float32), "zero": (rng.rand(R, 1) * 15).astype(np.float32)}
+        layers[name] = (W_q, meta, rng.randn(1, k).astype(np.float32))
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        for name in shapes:
+            W_q, meta, x = layers[name]
+            o.linear_forward_f32_fast(x, W_q, meta)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 3:
+            break
+    block_s = (time.perf_counter() - t0) / reps
+    lm = rng.randn(16032, 4096).astype(np.float32)  # 1/8 of the 128256-row fp32 lm_head
+    xv = rng.randn(4096).astype(np.float32)
+    t1 = time.perf_counter()
+    for _ in range(3):
+        lm @ xv
+    lm_s = (time.perf_counter() - t1) / 3 * 8
+    tok_s = 1.0 / (block_s * 32 + lm_s)
+    return tok_s, {"block_s": block_s, "lm_head_s": lm_s,
+                   "sample": f"{reps}x one block (7 HQQ linears, dequantise+matmul, fp32, bs=1) + 1/8 lm_head; x32 blocks extrapolated"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_reference_tokens_per_s(budget_s=6.0)
+        if i >= args.warmup:
+            vals.append(v)
+        if i >= 1 and len(vals) >= 2:
+            break  # bounded: each "step" is ~5-10 s of CPU work
+    value = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Llama-3-8B-shaped decode bs=1 seq=1, 4-bit gs=64 axis=1, HQQBackend.PYTORCH on CPU (oracle port)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def kernel_roofline(model, torch, peaks, reps=3):
+    """Average duration of the fused forward kernel per linear shape, CUDA events on the launching stream, cycling through
+    all layers' weights so every launch streams cold weights (per-shape footprint x layers >> 126 MB L2 for the big ones).
+    achieved = algorithmic bytes of the 224 launches of one step / their summed durations."""
+    from hqq_b200 import ops
+    dev = model.device
+    names = ["q", "k", "v", "o", "gate", "up", "down"]
+    per = {}
+    tot_bytes = tot_ms = 0.0
+    stream = torch.cuda.current_stream(dev)
+    for name in names:
+        layers = [blk[name] for blk in model.blocks]
+        N, K = layers[0].meta["shape"]
+        x = torch.randn(1, K, device=dev).to(model.dtype)
+        outs = torch.empty(1, N, device=dev, dtype=model.dtype)
+        for l in layers:  # warm-up
+            ops.linear_fwd(x, l.W_q, l.meta["scale"], l.meta["zero"], None, N, K, 64, 4, 1, out=outs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(reps):
+            for l in layers:
+                ops.linear_fwd(x, l.W_q, l.meta["scale"], l.meta["zero"], None, N, K, 64, 4, 1, out=outs)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / (reps * len(layers))
+        nbytes = N * K * 0.5 + 2 * (N * K // 64) * 2 + K * 2 + N * 2
+        per[name] = {"N": N, "K": K, "us": ms * 1e3, "GBps": nbytes / ms / 1e6}
+        tot_bytes += nbytes
+        tot_ms += ms
+    achieved = tot_bytes / tot_ms / 1e6
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "kernel": "hqq::linear_small_kernel<half,4,64,1> (224 launches/step)", "peak_source": peaks["source"],
+            "per_shape": per, "note": "event-timed in isolation, back to back over all layers (cold weights)"}
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from hqq_b200 import _lib, harness
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    lib = _lib.load()
+    shape = harness.LLAMA3_8B
+    n_layers = args.layers or shape.n_layers
+    model = harness.DecodeModel(shape, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=args.cache_len, tp=world,
+                                rank=rank, process_group=pg, n_layers=n_layers)
+    lib.hqq_b200_launch_count_reset()
+    model.capture(warmup=3)
+    # launches of OUR kernels in one step = those issued while capturing one step (3 warm-up steps + 1 captured)
+    launches_per_step = int(lib.hqq_b200_launch_count()) // 4
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident loop -------------------------------------------------------------------
+    model.tok.fill_(1); model.pos.zero_()
+    for _ in range(max(args.warmup, 3)):
+        model.decode()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        model.decode()
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+
+    # ---- end-to-end loop through the public API with host buffers ------------------------------
+    h_in = torch.ones(1, dtype=torch.long).pin_memory()
+    h_out = torch.zeros(1, dtype=torch.long).pin_memory()
+    model.pos.zero_()
+    for _ in range(3):
+        model.tok.copy_(h_in, non_blocking=True); model.graph.replay(); h_out.copy_(model.next_tok, non_blocking=True); torch.cuda.synchronize(dev)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        model.tok.copy_(h_in, non_blocking=True)          # H2D: this step's input token
+        model.graph.replay()
+        h_out.copy_(model.next_tok, non_blocking=True)    # D2H: the produced token
+        stream.synchronize()
+        h_in[0] = h_out[0]                                # host-side feedback, as a generation loop would
+    t1.record(stream)
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t.tolist()
+
+    peaks = load_peaks()
+    roof = kernel_roofline(model, torch, peaks) if (rank == 0 and world == 1) else None
+    if rank == 0:
+        scale_layers = shape.n_layers / n_layers
+        value = args.steps / (dev_ms / 1e3)
+        e2e = args.steps / (e2e_ms / 1e3)
+        bytes_tok = model.bytes_per_token() * world  # whole-job bytes (each rank streams 1/world of the blocks + full lm_head)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic",
+                "config": {"workload": f"Llama-3-8B-shaped decode bs=1 seq=1, {n_layers} blocks x 7 HQQLinear 4-bit gs=64 axis=1, fp16 lm_head, "
+                                       f"kv cache {args.cache_len}, CUDA graph; {model.bytes_per_token() / 1e9:.2f} GB streamed per step >> 126 MB L2 (no flush needed)",
+                           "parallelism": f"tp{world}", "layers": n_layers},
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+                "gpu_launches": launches_per_step * args.steps,
+                "step_hbm_GBps": bytes_tok / world / (dev_ms / args.steps) / 1e6}
+        if scale_layers != 1.0:
+            line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
+        if roof is not None:
+            line["roofline"] = roof
+        if world == 1 and not args.no_cpu_baseline:
+            v, info = cpu_reference_tokens_per_s(budget_s=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="hqq_b200", choices=["hqq_b200", "reference"])
+    ap.add_argument("--cache-len", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

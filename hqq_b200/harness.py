@@ -1,0 +1,166 @@
+"""Llama-shaped decode harness -- the caller of HQQLinear.forward used by bench.py.
+
+A random-init Llama-3-8B-*shaped* stack (no checkpoint is needed or loaded): every block linear
+(q,k,v,o,gate,up,down -- the tags of hqq/models/hf/llama.py:12-21) is an ``HQQLinear`` quantised on the GPU by
+this package; embeddings / lm_head / norms stay fp16 like the reference (hqq/models/base.py:43).  One decode
+step = one token through all blocks with a static KV cache, captured once in a CUDA graph (the reference's
+HFGenerator does the same with torch.compile + manual capture, hqq/utils/generation_hf.py:362-469; there is no
+torch.compile here).  The non-linear glue (RMSNorm, RoPE, attention over the cache, SwiGLU) is plain PyTorch:
+it is plumbing around the hot path, not part of it.
+
+Tensor parallel (world_size > 1): q/k/v/gate/up are column-sharded (each rank quantises its own [N/tp, K]
+shard -- slab packing cannot be sliced after the fact), o/down are row-sharded and end in ONE
+all-reduce of the [1, hidden] activation, the only exchange step on the path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+from .core.quantize import BaseQuantizeConfig, HQQLinear
+
+
+@dataclass
+class LlamaShape:
+    hidden: int = 4096
+    inter: int = 14336
+    n_layers: int = 32
+    n_heads: int = 32
+    n_kv_heads: int = 8
+    vocab: int = 128256
+    rope_theta: float = 500000.0
+    rms_eps: float = 1e-5
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.n_heads
+
+
+LLAMA3_8B = LlamaShape()
+LLAMA3_70B = LlamaShape(hidden=8192, inter=28672, n_layers=80, n_heads=64, n_kv_heads=8)
+TINY = LlamaShape(hidden=512, inter=1024, n_layers=2, n_heads=8, n_kv_heads=2, vocab=1024)
+
+
+def shard_dims(shape: LlamaShape, tp: int):
+    """Per-rank sizes of the sharded projections (pure host logic, unit-tested on CPU)."""
+    if shape.n_heads % tp or shape.n_kv_heads % tp or shape.inter % tp:
+        raise ValueError(f"tp={tp} must divide heads ({shape.n_heads}), kv heads ({shape.n_kv_heads}) and inter ({shape.inter})")
+    hd = shape.head_dim
+    return {"q": (shape.n_heads // tp * hd, shape.hidden), "k": (shape.n_kv_heads // tp * hd, shape.hidden),
+            "v": (shape.n_kv_heads // tp * hd, shape.hidden), "o": (shape.hidden, shape.n_heads // tp * hd),
+            "gate": (shape.inter // tp, shape.hidden), "up": (shape.inter // tp, shape.hidden),
+            "down": (shape.hidden, shape.inter // tp)}
+
+
+class DecodeModel:
+    def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
+                 device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
+                 n_layers: int | None = None):
+        self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
+        self.tp, self.rank, self.pg = tp, rank, process_group
+        self.cache_len = cache_len
+        self.n_layers = n_layers if n_layers is not None else shape.n_layers
+        dims = shard_dims(shape, tp)
+        cfg = BaseQuantizeConfig(nbits=nbits, group_size=group_size, axis=1)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed * 1000 + rank)
+        gshared = torch.Generator(device=self.device)
+        gshared.manual_seed(seed)
+
+        def rnd(n, k, gen):
+            return (torch.randn(n, k, device=self.device, generator=gen, dtype=torch.float32) * 0.02).to(dtype)
+
+        self.embed = rnd(shape.vocab, shape.hidden, gshared)
+        self.lm_head = rnd(shape.vocab, shape.hidden, gshared)
+        self.final_norm = torch.ones(shape.hidden, device=self.device, dtype=dtype)
+        self.blocks = []
+        self.quantized_weights = 0
+        for _ in range(self.n_layers):
+            blk = {}
+            for name, (n, k) in dims.items():
+                blk[name] = HQQLinear.from_weights(rnd(n, k, g), None, cfg, compute_dtype=dtype, device=str(self.device))
+                self.quantized_weights += n * k
+            blk["norm1"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)
+            blk["norm2"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)
+            hkv = shape.n_kv_heads // tp
+            blk["k_cache"] = torch.zeros(1, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
+            blk["v_cache"] = torch.zeros(1, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
+            self.blocks.append(blk)
+        hd = shape.head_dim
+        inv = 1.0 / (shape.rope_theta ** (torch.arange(0, hd, 2, device=self.device, dtype=torch.float32) / hd))
+        t = torch.arange(cache_len, device=self.device, dtype=torch.float32)
+        fr = torch.outer(t, inv)
+        self.cos = torch.cat([fr.cos(), fr.cos()], dim=-1).to(dtype)  # [cache_len, hd]
+        self.sin = torch.cat([fr.sin(), fr.sin()], dim=-1).to(dtype)
+        self.arange = torch.arange(cache_len, device=self.device)
+        # static I/O for graph capture
+        self.tok = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.pos = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.next_tok = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.graph = None
+
+    # bytes one decode step must read from HBM: packed weights + meta + fp16 lm_head row-major
+    def bytes_per_token(self, nbits=4, group_size=64) -> float:
+        meta = 2 * 2 / group_size
+        return self.quantized_weights * (nbits / 8 + meta) + self.lm_head.numel() * 2
+
+    def _rope(self, x, cos, sin):
+        hd = x.shape[-1]
+        x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
+        return x * cos + torch.cat((-x2, x1), dim=-1) * sin
+
+    def step(self):
+        """One token: reads self.tok / self.pos, writes self.next_tok and advances self.pos (all on device)."""
+        s = self.shape
+        hd, hq, hkv = s.head_dim, s.n_heads // self.tp, s.n_kv_heads // self.tp
+        h = self.embed.index_select(0, self.tok)  # [1, hidden]
+        cos = self.cos.index_select(0, self.pos).view(1, 1, hd)
+        sin = self.sin.index_select(0, self.pos).view(1, 1, hd)
+        mask = (self.arange <= self.pos).view(1, 1, 1, self.cache_len)
+        for blk in self.blocks:
+            x = F.rms_norm(h, (s.hidden,), blk["norm1"], s.rms_eps)
+            q = blk["q"](x).view(1, hq, hd)
+            k = blk["k"](x).view(1, hkv, hd)
+            v = blk["v"](x).view(1, hkv, hd)
+            q = self._rope(q, cos, sin)
+            k = self._rope(k, cos, sin)
+            blk["k_cache"].index_copy_(2, self.pos, k.view(1, hkv, 1, hd))
+            blk["v_cache"].index_copy_(2, self.pos, v.view(1, hkv, 1, hd))
+            a = F.scaled_dot_product_attention(q.view(1, hq, 1, hd), blk["k_cache"], blk["v_cache"], attn_mask=mask, enable_gqa=True)
+            o = blk["o"](a.reshape(1, hq * hd))
+            if self.tp > 1:
+                torch.distributed.all_reduce(o, group=self.pg)
+            h = h + o
+            x = F.rms_norm(h, (s.hidden,), blk["norm2"], s.rms_eps)
+            y = blk["down"](F.silu(blk["gate"](x)) * blk["up"](x))
+            if self.tp > 1:
+                torch.distributed.all_reduce(y, group=self.pg)
+            h = h + y
+        h = F.rms_norm(h, (s.hidden,), self.final_norm, s.rms_eps)
+        logits = torch.matmul(h, self.lm_head.t())
+        self.next_tok.copy_(torch.argmax(logits, dim=-1))
+        self.pos.add_(1).remainder_(self.cache_len)
+
+    def capture(self, warmup: int = 3):
+        """Warm up on a side stream, then capture one decode step into a CUDA graph."""
+        st = torch.cuda.Stream(device=self.device)
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st), torch.no_grad():
+            for _ in range(warmup):
+                self.step()
+        torch.cuda.current_stream(self.device).wait_stream(st)
+        torch.cuda.synchronize(self.device)
+        self.pos.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.step()
+        return self.graph
+
+    def decode(self, feed_back: bool = True):
+        """Replay one step; with feed_back the produced token becomes the next input (device-side copy)."""
+        self.graph.replay()
+        if feed_back:
+            self.tok.copy_(self.next_tok)

@@ -1,0 +1,177 @@
+"""Tensor-level wrappers over the C ABI: marshal torch tensors (device pointers + current stream)
+into ``libhqq_b200.so`` calls.  PyTorch is used for allocation and stream plumbing only.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import DTYPE_CODE, HQQ_E_UNSUPPORTED, HQQB200Error, check, load, ptr, stream_ptr
+
+FIELDS = {8: 1, 4: 2, 3: 10, 2: 4, 1: 8}
+
+
+def _as_device(t: torch.Tensor, device=None):
+    """Return (tensor on a CUDA device, original device).  CPU tensors are staged onto the GPU:
+    the arithmetic always runs in the CUDA library."""
+    if t.is_cuda:
+        return t, t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("hqq_b200: no CUDA device available; this package has no CPU path")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return t.to(dev), t.device
+
+
+# ----------------------------------------------------------------------------- BitPack
+def pack(W_q: torch.Tensor, nbits: int) -> torch.Tensor:
+    if W_q.dim() != 2:
+        raise ValueError("BitPack.pack expects a 2-D tensor")
+    if W_q.dtype not in DTYPE_CODE:
+        raise TypeError(f"BitPack.pack: unsupported dtype {W_q.dtype}")
+    w, home = _as_device(W_q.contiguous())
+    rows, cols = w.shape
+    if nbits == 3:
+        out = torch.empty((int(math.ceil(rows / 10.0)), cols), dtype=torch.int32, device=w.device)
+    else:
+        f = FIELDS[nbits]
+        if rows % f:
+            raise RuntimeError(f"BitPack.pack_{nbits}bit: {rows} rows cannot be split into {f} equal slabs")
+        out = torch.empty((rows // f, cols), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        check(load().hqq_b200_pack(nbits, ptr(w), DTYPE_CODE[w.dtype], ptr(out), rows, cols, stream_ptr(w.device)))
+    return out if home.type == "cuda" else out.to(home)
+
+
+def unpack(W_q: torch.Tensor, nbits: int, dtype=torch.uint8) -> torch.Tensor:
+    if W_q.dim() != 2:
+        raise ValueError("BitPack.unpack expects a 2-D tensor")
+    want = torch.int32 if nbits == 3 else torch.uint8
+    if W_q.dtype != want:
+        raise TypeError(f"BitPack.unpack_{nbits}bit expects a {want} tensor, got {W_q.dtype}")
+    if dtype not in DTYPE_CODE:
+        raise TypeError(f"BitPack.unpack: unsupported output dtype {dtype}")
+    w, home = _as_device(W_q.contiguous())
+    prow, cols = w.shape
+    out = torch.empty((prow * FIELDS[nbits], cols), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        check(load().hqq_b200_unpack(nbits, ptr(w), ptr(out), DTYPE_CODE[dtype], prow, cols, stream_ptr(w.device)))
+    return out if home.type == "cuda" else out.to(home)
+
+
+# ----------------------------------------------------------------------------- dequantize
+def dequantize(W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, shape, group_size: int, nbits: int,
+               axis: int, dtype: torch.dtype) -> torch.Tensor:
+    """((unpack(W_q) - zero) * scale).reshape(shape) in `dtype` (quantize.py:184-199)."""
+    N, K = int(shape[0]), int(shape[1])
+    w, home = _as_device(W_q)
+    w = w.contiguous()
+    s = scale.to(device=w.device, dtype=dtype).contiguous()
+    z = zero.to(device=w.device, dtype=dtype).contiguous()
+    out = torch.empty((N, K), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        check(load().hqq_b200_dequantize(ptr(w), ptr(s), ptr(z), ptr(out), N, K, int(group_size), int(nbits), int(axis),
+                                         DTYPE_CODE[dtype], stream_ptr(w.device)))
+    return out if home.type == "cuda" else out.to(home)
+
+
+# ----------------------------------------------------------------------------- quantize
+def packed_shape(N: int, K: int, group_size: int, nbits: int, axis: int):
+    total = N * K
+    G = total // group_size
+    R, C = (G, group_size) if axis == 1 else (group_size, G)
+    prow = int(math.ceil(R / 10.0)) if nbits == 3 else R // FIELDS[nbits]
+    return (prow, C), (R, C), G
+
+
+def quantize(W: torch.Tensor, nbits: int, group_size: int, axis: int, round_zero: bool, optimize: bool,
+             lp_norm: float = 0.7, beta: float = 10.0, iters: int = 20, scale_init=None, zero_init=None,
+             max_level=None, want_trace: bool = False):
+    """Fused min/max init + proximal solver + pack on the device of `W` (must be CUDA).
+
+    Returns (W_q packed, scale [G] f32 (dequantisation form), zero [G] f32, trace-or-None) where trace is a
+    dict of device tensors {info int32[4], errors float32[iters]}.
+    """
+    _lib.require_cuda(W, "the weight passed to quantize")
+    if W.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        W = W.float()
+    W = W.contiguous()
+    if W.dim() != 2:
+        W = W.reshape(W.shape[0], -1)
+    N, K = W.shape
+    lib = load()
+    dev = W.device
+    pshape, _, G = packed_shape(N, K, group_size, nbits, axis)
+    ws_bytes = lib.hqq_b200_quantize_workspace_bytes(N, K, group_size, nbits, axis, iters)
+    if ws_bytes == 0:
+        # re-run the checks through the real entry point to get the reference-worded message
+        check(lib.hqq_b200_quantize(None, 0, N, K, group_size, nbits, axis, 0, 0, lp_norm, beta, iters, None, None, None, None,
+                                    None, None, 0, None))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    W_q = torch.empty(pshape, dtype=torch.int32 if nbits == 3 else torch.uint8, device=dev)
+    scale = torch.empty(G, dtype=torch.float32, device=dev)
+    zero = torch.empty(G, dtype=torch.float32, device=dev)
+    info = torch.zeros(4, dtype=torch.int32, device=dev) if want_trace else None
+    errs = torch.zeros(max(iters, 1), dtype=torch.float32, device=dev) if want_trace else None
+    if max_level is None:
+        max_level = (1 << nbits) - 1
+    if scale_init is not None:
+        scale_init = scale_init.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+        zero_init = zero_init.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+    with torch.cuda.device(dev):
+        check(lib.hqq_b200_quantize_ex(ptr(W), DTYPE_CODE[W.dtype], N, K, int(group_size), int(nbits), int(max_level), int(axis),
+                                       int(bool(round_zero)), int(bool(optimize)), float(lp_norm), float(beta), int(iters),
+                                       ptr(scale_init), ptr(zero_init), ptr(W_q), ptr(scale), ptr(zero), ptr(info), ptr(errs),
+                                       ptr(ws), ws_bytes, stream_ptr(dev)))
+    trace = {"info": info, "errors": errs} if want_trace else None
+    return W_q, scale, zero, trace
+
+
+# ----------------------------------------------------------------------------- fused forward
+def linear_route(M: int, N: int, K: int, group_size: int, nbits: int, axis: int, dtype: torch.dtype) -> int:
+    code = DTYPE_CODE.get(dtype, -1)
+    if code < 0 or not isinstance(nbits, int):
+        return 0
+    return load().hqq_b200_linear_fwd_route(M, N, K, int(group_size), int(nbits), int(axis), code)
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    if nbytes == 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, bias, N: int, K: int,
+               group_size: int, nbits: int, axis: int, out: torch.Tensor | None = None) -> torch.Tensor | None:
+    """y = x2d @ dequantize(W_q).T (+ bias) through the fused kernels; returns None when no fused kernel covers
+    the configuration (caller then uses dequantize + matmul)."""
+    dtype = x2d.dtype
+    M = x2d.shape[0]
+    lib = load()
+    code = DTYPE_CODE[dtype]
+    if lib.hqq_b200_linear_fwd_route(M, N, K, int(group_size), int(nbits), int(axis), code) == 0:
+        return None
+    dev = x2d.device
+    y = out if out is not None else torch.empty((M, N), dtype=dtype, device=dev)
+    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, N, K, int(group_size), int(nbits), code)
+    ws = _workspace(ws_bytes, dev)
+    rc = lib.hqq_b200_linear_fwd(ptr(x2d), ptr(W_q), ptr(scale), ptr(zero), ptr(bias), ptr(y), M, N, K, int(group_size),
+                                 int(nbits), int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev))
+    if rc == HQQ_E_UNSUPPORTED:
+        return None
+    check(rc)
+    return y
+
+
+__all__ = ["pack", "unpack", "dequantize", "quantize", "linear_fwd", "linear_route", "packed_shape", "HQQB200Error"]

@@ -1,0 +1,142 @@
+/*
+ * hqq_b200 -- C ABI of the B200 (sm_100a) HQQ quantize-and-infer hot path.
+ *
+ * This is the drop-in boundary: plain pointers (device memory owned by the caller),
+ * sizes and a cudaStream_t passed as void*.  No torch types, no allocation, no host
+ * synchronisation inside any call; every call is safe under CUDA-graph capture.
+ *
+ * Each entry point names the reference (mobiusml/hqq @ e0b1d00) interface it replaces.
+ * All functions return 0 on success, a negative HQQ_E_* code otherwise; the message is
+ * available (thread-local) through hqq_b200_last_error().
+ *
+ * Tensor conventions (identical to the reference):
+ *   W          [N, K] row-major (nn.Linear.weight), any of f32/f16/bf16
+ *   groups     axis=1: W.reshape(-1, gs)  -> R = N*K/gs rows of gs columns, meta [R,1]
+ *              axis=0: W.reshape(gs, -1)  -> gs rows of C = N*K/gs columns,  meta [1,C]
+ *   W_q        the packed tensor produced by BitPack.pack_* on the grouped matrix:
+ *              "slab interleave" along dim 0 -- field f of packed row i holds unpacked row
+ *              i + f*step (hqq/core/bitpack.py:24-28,43-52,69-91,115-128);
+ *              8/4/2/1 bit -> uint8 (1/2/4/8 fields per byte, most significant first),
+ *              3 bit -> int32 (10 fields, bits 29..0, rows zero-padded to a multiple of 10)
+ *   scale,zero one value per group, dequantisation form  W ~= (W_q - zero) * scale
+ */
+#ifndef HQQ_B200_H
+#define HQQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQQ_B200_ABI_VERSION 1
+
+/* element types */
+enum {
+  HQQ_F32 = 0,
+  HQQ_F16 = 1,
+  HQQ_BF16 = 2,
+  HQQ_U8 = 3,
+  HQQ_I32 = 4,
+  HQQ_I64 = 5
+};
+
+/* error codes */
+enum {
+  HQQ_OK = 0,
+  HQQ_E_INVALID = -1,     /* bad argument (shape, dtype, alignment, null pointer)        */
+  HQQ_E_UNSUPPORTED = -2, /* valid request outside what this build implements            */
+  HQQ_E_WORKSPACE = -3,   /* workspace too small                                         */
+  HQQ_E_CUDA = -4         /* CUDA launch/driver error (message carries cudaGetErrorString) */
+};
+
+int hqq_b200_abi_version(void);
+const char* hqq_b200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * BitPack.pack_{8,4,2,1}bit_u8 / pack_3bit_32            hqq/core/bitpack.py:14-15,24-28,43-52,69-91,115-128
+ *   in : [rows, cols] of in_dtype (any HQQ_* type; values are the integer levels)
+ *   out: uint8 [rows*nbits/8, cols]   (nbits 8/4/2/1; rows must be a multiple of 8/nbits)
+ *        int32 [ceil(rows/10), cols]  (nbits 3)
+ * ------------------------------------------------------------------------------------- */
+int hqq_b200_pack(int nbits, const void* in, int in_dtype, void* out,
+                  int64_t rows, int64_t cols, void* stream);
+
+/* BitPack.unpack_* and hqq_aten.unpack_{4,2,1}bit_u8 / unpack_3bit_32
+ *   hqq/core/bitpack.py:18-19,31-38,55-64,95-110,131-144 ; hqq/kernels/hqq_aten_cuda.cpp:59-71
+ *   in : packed [packed_rows, cols] (uint8, or int32 for nbits 3)
+ *   out: out_dtype [packed_rows * fields, cols]  (fields = 8/nbits, or 10 for 3 bit:
+ *        like the reference the 3-bit output keeps the padded rows; callers slice)      */
+int hqq_b200_unpack(int nbits, const void* in, void* out, int out_dtype,
+                    int64_t packed_rows, int64_t cols, void* stream);
+
+/* Quantizer.dequantize and hqq_aten.dequantize (which only handles axis 0)
+ *   hqq/core/quantize.py:184-199 ; hqq/kernels/hqq_aten_cuda.cpp:32-54
+ *   out[N,K] = ((unpack(W_q) as dtype) - zero) * scale, two roundings in `dtype`,
+ *   scale/zero given in `dtype` (as stored in HQQLinear.meta after .cuda()).
+ *   W_q may be the float "view" of the packed bytes (view_as_float): same pointer.   */
+int hqq_b200_dequantize(const void* W_q, const void* scale, const void* zero, void* out,
+                        int64_t N, int64_t K, int group_size, int nbits, int axis,
+                        int dtype, void* stream);
+
+/* Quantizer.quantize incl. Quantizer.optimize_weights (= optimize_weights_proximal_legacy)
+ * and BitPack.pack      hqq/core/quantize.py:76-180 ; hqq/core/optimize.py:96-108,201-255
+ *   W        [N,K] of src_dtype (f32/f16/bf16), device memory
+ *   optimize 0: W_q = round(W*s+z) only ; 1: proximal solver (lp_norm, beta, iters; the
+ *            reference defaults are 0.7, 10.0, 20) with the reference's whole-tensor early stop
+ *   W_q_out  packed as above; scale_out/zero_out float32, one per group (scale is the
+ *            dequantisation scale, i.e. already inverted, quantize.py:154)
+ *   info_out optional int32[4] device: {iterations executed, selected zero slot, 0, 0}
+ *   err_out  optional float[iters] device: whole-tensor mean |W - W_r| per iteration
+ *   workspace: hqq_b200_quantize_workspace_bytes() bytes of device scratch              */
+size_t hqq_b200_quantize_workspace_bytes(int64_t N, int64_t K, int group_size, int nbits,
+                                         int axis, int iters);
+int hqq_b200_quantize(const void* W, int src_dtype, int64_t N, int64_t K,
+                      int group_size, int nbits, int axis, int round_zero, int optimize,
+                      float lp_norm, float beta, int iters,
+                      void* W_q_out, float* scale_out, float* zero_out,
+                      int32_t* info_out, float* err_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Quantizer.optimize_weights seam (hqq/core/quantize.py:38,137-145): same as hqq_b200_quantize but
+ *   inv_scale_init / zero_init  optional float32 [groups]: the caller's initial inverse scale and zero
+ *                               (what optimize_weights_proximal receives as `scale`, `zero`); NULL = min/max init
+ *   max_level                   upper clamp (min_max[1]); lower clamp is 0 as in the reference
+ * With nbits = 8 the output is one level per byte, i.e. the unpacked W_q the seam returns.            */
+int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int64_t K,
+                         int group_size, int nbits, int max_level, int axis, int round_zero, int optimize,
+                         float lp_norm, float beta, int iters,
+                         const float* inv_scale_init, const float* zero_init,
+                         void* W_q_out, float* scale_out, float* zero_out,
+                         int32_t* info_out, float* err_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* HQQLinear.forward under HQQBackend.PYTORCH (forward_pytorch / forward_pytorch_backprop),
+ * i.e. y = x @ dequantize(W_q).T + bias, as ONE fused unpack->dequant->MMA kernel.
+ *   hqq/core/quantize.py:880-898 ; semantic template hqq/kernels/hqq_aten_torch.cpp:79-107
+ *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
+ *   axis must be 1.  Returns HQQ_E_UNSUPPORTED for configurations the fused kernels do
+ *   not cover (the Python layer then runs hqq_b200_dequantize + a library GEMM).
+ *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes (may be 0).                  */
+size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size,
+                                           int nbits, int dtype);
+int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero,
+                        const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                        int group_size, int nbits, int axis, int dtype,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Which fused kernel hqq_b200_linear_fwd would use: 0 none (unsupported), 1 small-M
+ * mma.sync weight-streaming kernel, 2 tcgen05/TMA GEMM.                                 */
+int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits,
+                              int axis, int dtype);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (used by bench.py for its gpu_launches claim).                                        */
+int64_t hqq_b200_launch_count(void);
+void hqq_b200_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HQQ_B200_H */

@@ -302,3 +302,16 @@ def linear_forward(x, W_q, meta, bias=None, compute_dtype="float32"):
     if bias is not None:
         y = round_to(y.astype(np.float64) + round_to(bias, compute_dtype), compute_dtype)
     return y.reshape(tuple(xs.shape[:-1]) + (W_r.shape[0],))
+
+
+def linear_forward_f32_fast(x, W_q, meta, bias=None):
+    """The reference's CPU data flow at float32 (quantize.py:184-199, 880-898) without the float64 bookkeeping of
+    `linear_forward`: unpack the whole matrix, (W - zero) * scale, then one BLAS matmul.  Used only as the timed
+    CPU baseline in bench.py (it does per token exactly the passes over the N x K matrix the reference does)."""
+    W_r = UNPACK[meta["packing"]](W_q).astype(np.float32)
+    W_r -= meta["zero"]
+    W_r *= meta["scale"]
+    y = np.asarray(x, dtype=np.float32) @ W_r.reshape(meta["shape"]).T
+    if bias is not None:
+        y = y + bias
+    return y

@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads, exports every symbol include/hqq_b200.h declares, and validates its
+arguments before touching the GPU (no compute happens in this file)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hqq_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "hqq_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hqq_b200_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from hqq_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/hqq_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes prototype"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version(lib):
+    assert lib.hqq_b200_abi_version() == 1
+
+
+def test_argument_validation_uses_reference_wording(lib):
+    from hqq_b200 import _lib
+    # unsupported bit width
+    rc = lib.hqq_b200_pack(5, None, 0, None, 8, 8, None)
+    assert rc == _lib.HQQ_E_INVALID and "not supported" in _lib.last_error()
+    # ragged slab split (the reference fails on W_q[:step] | W_q[step:])
+    rc = lib.hqq_b200_pack(4, 1, _lib.HQQ_U8, 1, 7, 8, None)
+    assert rc == _lib.HQQ_E_INVALID
+    # group size must divide the tensor (quantize.py:92-100 wording)
+    assert lib.hqq_b200_quantize_workspace_bytes(10, 10, 64, 4, 1, 20) == 0
+    rc = lib.hqq_b200_quantize(None, 0, 10, 10, 64, 4, 1, 0, 1, 0.7, 10.0, 20, None, None, None, None, None, None, 0, None)
+    assert rc == _lib.HQQ_E_INVALID and "group_size should be divisble" in _lib.last_error()
+    rc = lib.hqq_b200_dequantize(1, 1, 1, 1, 64, 64, 64, 4, 2, _lib.HQQ_F16, None)
+    assert rc == _lib.HQQ_E_INVALID and "axis should be either 0 or 1" in _lib.last_error()
+    # workspace size is a pure function of the shape
+    assert lib.hqq_b200_quantize_workspace_bytes(4096, 4096, 64, 4, 1, 20) > 4096 * 4096 // 64 * 4 * 21
+
+
+def test_forward_routing_table(lib):
+    from hqq_b200._lib import HQQ_BF16, HQQ_F16, HQQ_F32
+    r = lib.hqq_b200_linear_fwd_route
+    assert r(1, 4096, 4096, 64, 4, 1, HQQ_F16) == 1      # decode: weight-streaming kernel
+    assert r(32, 14336, 4096, 64, 4, 1, HQQ_BF16) == 1
+    assert r(1, 4096, 4096, 64, 4, 0, HQQ_F16) == 0      # axis 0: dequantize + GEMM
+    assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0
+    assert r(1, 4096, 4096, 64, 3, 1, HQQ_F16) == 0      # 3-bit: not fused (yet)
+    assert r(1, 4096, 4000, 64, 4, 1, HQQ_F16) == 0      # K must be a multiple of 256
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from hqq_b200 import _lib
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load(str(tmp_path / "nope.so"))
