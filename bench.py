@@ -141,40 +141,55 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def kernel_roofline(model, torch, peaks, reps=3):
-    """Average duration of the fused forward kernel per linear shape, CUDA events on the launching stream, cycling through
-    all layers' weights so every launch streams cold weights (per-shape footprint x layers >> 126 MB L2 for the big ones).
-    achieved = algorithmic bytes of the 224 launches of one step / their summed durations."""
+def kernel_roofline(model, torch, peaks, reps=4):
+    """Average duration of the fused forward kernel per linear shape.  All launches of one shape over all layers (x reps)
+    are captured into a CUDA graph so the measurement is not bound by Python launch overhead, replayed, and timed with CUDA
+    events on the launching stream.  Cycling through every layer's weights means each launch streams cold weights
+    (per-shape footprint x 32 layers exceeds the 126 MB L2 for everything but k/v).
+    achieved = algorithmic bytes of the 224 launches of one step / their summed average durations."""
     from hqq_b200 import ops
     dev = model.device
     names = ["q", "k", "v", "o", "gate", "up", "down"]
     per = {}
     tot_bytes = tot_ms = 0.0
-    stream = torch.cuda.current_stream(dev)
     for name in names:
         layers = [blk[name] for blk in model.blocks]
         N, K = layers[0].meta["shape"]
         x = torch.randn(1, K, device=dev).to(model.dtype)
         outs = torch.empty(1, N, device=dev, dtype=model.dtype)
-        for l in layers:  # warm-up
-            ops.linear_fwd(x, l.W_q, l.meta["scale"], l.meta["zero"], None, N, K, 64, 4, 1, out=outs)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        e0.record(stream)
-        for _ in range(reps):
+
+        def run_all():
             for l in layers:
                 ops.linear_fwd(x, l.W_q, l.meta["scale"], l.meta["zero"], None, N, K, 64, 4, 1, out=outs)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run_all()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                run_all()
+        g.replay()
+        torch.cuda.synchronize(dev)
+        stream = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.replay()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / (reps * len(layers))
         nbytes = N * K * 0.5 + 2 * (N * K // 64) * 2 + K * 2 + N * 2
-        per[name] = {"N": N, "K": K, "us": ms * 1e3, "GBps": nbytes / ms / 1e6}
+        per[name] = {"N": N, "K": K, "us": round(ms * 1e3, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         tot_bytes += nbytes
         tot_ms += ms
     achieved = tot_bytes / tot_ms / 1e6
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": None, "kernel": "hqq::linear_small_kernel<half,4,64,1> (224 launches/step)", "peak_source": peaks["source"],
-            "per_shape": per, "note": "event-timed in isolation, back to back over all layers (cold weights)"}
+            "per_shape": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
+            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights)"}
 
 
 def run_gpu(args, rank, world, local_rank):

@@ -1,10 +1,12 @@
-// hqq_b200_linear_fwd: routing between the fused forward kernels.
+// hqq_b200_linear_fwd / hqq_b200_linear_fwd_multi: routing between the fused forward kernels.
 #include "common.cuh"
 
 namespace hqq {
 bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
-int linear_small(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M,
-                 int64_t N, int64_t K, int gs, int nbits, int dtype, cudaStream_t st);
+size_t small_workspace_bytes(int64_t M);
+int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
+                       const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
+                       void* ws, size_t ws_bytes, cudaStream_t st);
 bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int gs, int nbits, int dtype);
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M,
@@ -20,24 +22,47 @@ extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int gr
 }
 
 extern "C" size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int dtype) {
-  if (small_route_ok(M, N, K, group_size, nbits, 1, dtype)) return 0;
+  if (small_route_ok(M, N, K, group_size, nbits, 1, dtype)) return small_workspace_bytes(M);
   if (gemm_route_ok(M, N, K, group_size, nbits, 1, dtype)) return gemm_workspace_bytes(M, N, K, group_size, nbits, dtype);
   return 0;
+}
+
+static int check_common(const void* x, int64_t M, int64_t K, int group_size, int nbits, int axis) {
+  HQQ_REQUIRE(x, HQQ_E_INVALID, "hqq_b200_linear_fwd: null pointer");
+  HQQ_REQUIRE(M > 0 && K > 0 && group_size > 0, HQQ_E_INVALID, "hqq_b200_linear_fwd: bad shape M=%lld K=%lld gs=%d", (long long)M, (long long)K, group_size);
+  HQQ_REQUIRE(valid_nbits(nbits), HQQ_E_INVALID, "nbits=%d not supported.", nbits);
+  HQQ_REQUIRE(axis == 0 || axis == 1, HQQ_E_INVALID, "axis should be either 0 or 1");
+  return HQQ_OK;
 }
 
 extern "C" int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero, const void* bias, void* y,
                                    int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  HQQ_REQUIRE(x && W_q && scale && zero && y, HQQ_E_INVALID, "hqq_b200_linear_fwd: null pointer");
-  HQQ_REQUIRE(M > 0 && N > 0 && K > 0 && group_size > 0, HQQ_E_INVALID, "hqq_b200_linear_fwd: bad shape M=%lld N=%lld K=%lld gs=%d",
-              (long long)M, (long long)N, (long long)K, group_size);
-  HQQ_REQUIRE(valid_nbits(nbits), HQQ_E_INVALID, "nbits=%d not supported.", nbits);
-  HQQ_REQUIRE(axis == 0 || axis == 1, HQQ_E_INVALID, "axis should be either 0 or 1");
+  int rc = check_common(x, M, K, group_size, nbits, axis);
+  if (rc) return rc;
+  HQQ_REQUIRE(W_q && scale && zero && y && N > 0, HQQ_E_INVALID, "hqq_b200_linear_fwd: null pointer or empty matrix");
   cudaStream_t st = (cudaStream_t)stream;
   const int route = hqq_b200_linear_fwd_route(M, N, K, group_size, nbits, axis, dtype);
-  if (route == 1) return linear_small(x, W_q, scale, zero, bias, y, M, N, K, group_size, nbits, dtype, st);
+  if (route == 1) return linear_small_multi(x, 1, &W_q, &scale, &zero, &bias, &y, &N, M, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
   if (route == 2) return linear_gemm(x, W_q, scale, zero, bias, y, M, N, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
   set_error("hqq_b200_linear_fwd: no fused kernel for M=%lld N=%lld K=%lld gs=%d nbits=%d axis=%d dtype=%d", (long long)M, (long long)N,
             (long long)K, group_size, nbits, axis, dtype);
   return HQQ_E_UNSUPPORTED;
+}
+
+extern "C" int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, const void* const* scale,
+                                         const void* const* zero, const void* const* bias, void* const* y, const int64_t* N, int64_t M,
+                                         int64_t K, int group_size, int nbits, int axis, int dtype, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, M, K, group_size, nbits, axis);
+  if (rc) return rc;
+  HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_linear_fwd_multi: 1..4 matrices, non-null arrays");
+  for (int i = 0; i < count; ++i) {
+    if (!small_route_ok(M, N[i], K, group_size, nbits, axis, dtype)) {
+      set_error("hqq_b200_linear_fwd_multi: matrix %d (N=%lld K=%lld gs=%d nbits=%d axis=%d dtype=%d M=%lld) is outside the fused small-M kernel",
+                i, (long long)N[i], (long long)K, group_size, nbits, axis, dtype, (long long)M);
+      return HQQ_E_UNSUPPORTED;
+    }
+  }
+  return linear_small_multi(x, count, W_q, scale, zero, bias, y, N, M, K, group_size, nbits, dtype, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -20,6 +20,7 @@ from dataclasses import dataclass
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .core.quantize import BaseQuantizeConfig, HQQLinear
 
 
@@ -107,6 +108,13 @@ class DecodeModel:
         meta = 2 * 2 / group_size
         return self.quantized_weights * (nbits / 8 + meta) + self.lm_head.numel() * 2
 
+    @staticmethod
+    def _multi(x, layers):
+        outs = ops.linear_fwd_multi(x, layers)
+        if outs is None:
+            outs = [l(x) for l in layers]
+        return outs
+
     def _rope(self, x, cos, sin):
         hd = x.shape[-1]
         x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
@@ -122,9 +130,8 @@ class DecodeModel:
         mask = (self.arange <= self.pos).view(1, 1, 1, self.cache_len)
         for blk in self.blocks:
             x = F.rms_norm(h, (s.hidden,), blk["norm1"], s.rms_eps)
-            q = blk["q"](x).view(1, hq, hd)
-            k = blk["k"](x).view(1, hkv, hd)
-            v = blk["v"](x).view(1, hkv, hd)
+            q, k, v = self._multi(x, (blk["q"], blk["k"], blk["v"]))  # one launch: the three matrices share x
+            q, k, v = q.view(1, hq, hd), k.view(1, hkv, hd), v.view(1, hkv, hd)
             q = self._rope(q, cos, sin)
             k = self._rope(k, cos, sin)
             blk["k_cache"].index_copy_(2, self.pos, k.view(1, hkv, 1, hd))
@@ -135,7 +142,8 @@ class DecodeModel:
                 torch.distributed.all_reduce(o, group=self.pg)
             h = h + o
             x = F.rms_norm(h, (s.hidden,), blk["norm2"], s.rms_eps)
-            y = blk["down"](F.silu(blk["gate"](x)) * blk["up"](x))
+            gate, up = self._multi(x, (blk["gate"], blk["up"]))
+            y = blk["down"](F.silu(gate) * up)
             if self.tp > 1:
                 torch.distributed.all_reduce(y, group=self.pg)
             h = h + y

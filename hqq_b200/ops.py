@@ -142,12 +142,20 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    """Per-device scratch for the fused forward, allocated ONCE at its maximum size (so a captured CUDA graph never
+    holds a stale pointer) and zero-initialised: the stream-K kernel keeps its ready-flags there and leaves them zero
+    on exit, so the buffer is reusable across launches and graph replays.  Launches that share it must be
+    stream-ordered (one decode stream per device); concurrent streams need their own `hqq_b200_linear_fwd` workspace."""
     if nbytes == 0:
         return None
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    key = device.index if device.index is not None else torch.cuda.current_device()
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        size = max(nbytes, load().hqq_b200_linear_fwd_workspace_bytes(32, 4096, 4096, 64, 4, _lib.HQQ_F16))
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("hqq_b200: run one forward outside CUDA-graph capture first (the workspace is allocated lazily)")
+        buf = torch.zeros(size, dtype=torch.uint8, device=device)
+        _ws_cache.setdefault("keepalive", []).append(buf)
         _ws_cache[key] = buf
     return buf
 
@@ -159,8 +167,8 @@ def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: 
     dtype = x2d.dtype
     M = x2d.shape[0]
     lib = load()
-    code = DTYPE_CODE[dtype]
-    if lib.hqq_b200_linear_fwd_route(M, N, K, int(group_size), int(nbits), int(axis), code) == 0:
+    code = DTYPE_CODE.get(dtype, -1)
+    if code < 0 or lib.hqq_b200_linear_fwd_route(M, N, K, int(group_size), int(nbits), int(axis), code) == 0:
         return None
     dev = x2d.device
     y = out if out is not None else torch.empty((M, N), dtype=dtype, device=dev)
@@ -174,4 +182,47 @@ def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: 
     return y
 
 
-__all__ = ["pack", "unpack", "dequantize", "quantize", "linear_fwd", "linear_route", "packed_shape", "HQQB200Error"]
+def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
+    """Several HQQLinear layers consuming the same activation (q/k/v, gate/up) in ONE launch of the small-M kernel.
+    `layers` are HQQLinear objects with identical K / group_size / nbits / axis=1 / compute dtype; returns a list of
+    outputs, or None when the configuration is outside the fused kernel (caller then runs the layers one by one)."""
+    import ctypes
+    lib = load()
+    n = len(layers)
+    if not (1 <= n <= 4):
+        return None
+    m0 = layers[0].meta
+    K = int(m0["shape"][1])
+    gs, axis = m0["group_size"], m0["axis"]
+    packing = m0["packing"]
+    nbits = {"8bit_u8": 8, "4bit_u8": 4, "3bit_32": 3, "2bit_u8": 2, "1bit_u8": 1}.get(packing, 0)
+    dtype = x2d.dtype
+    code = DTYPE_CODE.get(dtype, -1)
+    M = x2d.shape[0]
+    if code < 0 or gs is None or nbits == 0:
+        return None
+    Ns = []
+    for l in layers:
+        m = l.meta
+        if (m["packing"] != packing or m["group_size"] != gs or m["axis"] != axis or int(m["shape"][1]) != K or l.compute_dtype != dtype
+                or "scale" not in m or "zero" not in m):
+            return None
+        N = int(m["shape"][0])
+        if lib.hqq_b200_linear_fwd_route(M, N, K, int(gs), nbits, int(axis), code) != 1:
+            return None
+        Ns.append(N)
+    dev = x2d.device
+    if outs is None:
+        outs = [torch.empty((M, N), dtype=dtype, device=dev) for N in Ns]
+    VP = ctypes.c_void_p * n
+    arr = lambda ts: VP(*[ptr(t) for t in ts])
+    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, Ns[0], K, int(gs), nbits, code)
+    ws = _workspace(ws_bytes, dev)
+    Narr = (ctypes.c_int64 * n)(*Ns)
+    check(lib.hqq_b200_linear_fwd_multi(ptr(x2d), n, arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]),
+                                        arr([l.meta["zero"] for l in layers]), arr([l.bias for l in layers]), arr(outs), Narr,
+                                        M, K, int(gs), nbits, int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev)))
+    return outs
+
+
+__all__ = ["pack", "unpack", "dequantize", "quantize", "linear_fwd", "linear_fwd_multi", "linear_route", "packed_shape", "HQQB200Error"]

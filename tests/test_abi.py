@@ -62,6 +62,9 @@ def test_forward_routing_table(lib):
     assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0
     assert r(1, 4096, 4096, 64, 3, 1, HQQ_F16) == 0      # 3-bit: not fused (yet)
     assert r(1, 4096, 4000, 64, 4, 1, HQQ_F16) == 0      # K must be a multiple of 256
+    assert r(1, 4096, 4096, 128, 2, 1, HQQ_BF16) == 1
+    assert r(1, 4096, 4096, 32, 4, 1, HQQ_F16) == 0      # group sizes other than 64/128: dequantize + GEMM
+    assert r(64, 4096, 4096, 64, 4, 1, HQQ_F16) != 1     # beyond the small-M kernel
 
 
 def test_missing_library_fails_loudly(tmp_path):
