@@ -14,11 +14,11 @@
 // fragments is used on purpose: at M <= 32 the kernel is bound by HBM and instruction issue, and a
 // register-operand MMA avoids the shared-memory round trip a tcgen05 operand would need.
 //
-// Scheduling is stream-K: the (16-row tile) x (256-k unit) space of up to four weight matrices that share the
-// activation (q/k/v, gate/up) is one linear sequence split evenly over all resident warps.  Every warp streams its
-// contiguous slice through a private cp.async ring in shared memory (3 units in flight per warp, no register
-// staging, no block-level barriers).  A tile that is split across warps is finished by the warp holding its first
-// k-chunk, which adds the other warps' partials in ascending warp order: deterministic, no atomics on the data.
+// Scheduling: persistent CTAs walk the 16-row tiles of up to four weight matrices that share the activation (q/k/v,
+// gate/up) round-robin; the 8 warps of a CTA split K of a tile and stream their chunks through private cp.async rings
+// in shared memory (3 x 2 KB in flight per warp, prefetching across tile boundaries), then reduce through shared
+// memory in a fixed order: deterministic, no atomics, no workspace.  Launched with programmatic dependent launch: the
+// weight prefetch starts before the producer of x has finished.
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
@@ -48,9 +48,6 @@ struct SKArgs {
   int Gk;           // groups per output row = K / GS
   int KB;           // 256-k units per row tile = K / 256
   int total_tiles;
-  long long total_units;
-  float* ws_partial;  // [warps][MT][128] split-K partial tiles in fragment layout
-  int* ws_flags;      // [warps] 0 = empty, 1 = partial ready (left zeroed on exit)
 };
 
 template <typename T> struct MT16;
@@ -142,6 +139,14 @@ struct Lanes<__half, NBITS, MAGIC> {
     a2 = and_or(wh, mask_a, OR);
     a3 = and_or(wh, mask_b, OR);
   }
+  // same without the byte shuffle: lanes pair {k0,k2} (a0/a1) and {k1,k3} (a2/a3); the caller permutes x instead
+  __device__ __forceinline__ void extract_np(uint32_t w, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) const {
+    const uint32_t wh = w >> 8;
+    a0 = and_or(w, mask_a, OR);
+    a1 = and_or(w, mask_b, OR);
+    a2 = and_or(wh, mask_a, OR);
+    a3 = and_or(wh, mask_b, OR);
+  }
 };
 
 // bf16, sub-byte fields: only 7 mantissa bits -> shift the field down to bit 0 first
@@ -162,6 +167,13 @@ struct Lanes<__nv_bfloat16, NBITS, MAGIC> {
     a2 = and_or(wp >> (sh_a + 8), M, 0x43004300u);
     a3 = and_or(wp >> (sh_b + 8), M, 0x43004300u);
   }
+  __device__ __forceinline__ void extract_np(uint32_t w, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) const {
+    constexpr uint32_t M = ((1u << NBITS) - 1u) * 0x00010001u;
+    a0 = and_or(w >> sh_a, M, 0x43004300u);
+    a1 = and_or(w >> sh_b, M, 0x43004300u);
+    a2 = and_or(w >> (sh_a + 8), M, 0x43004300u);
+    a3 = and_or(w >> (sh_b + 8), M, 0x43004300u);
+  }
 };
 
 // fp16, 8-bit: whole bytes, two packed rows per thread (rows r and r+8 of the tile)
@@ -179,6 +191,12 @@ struct Lanes<__half, 8, MAGIC> {
     a1 = prmt(wb, HB, 0x4140u);  // row r+8
     a3 = prmt(wb, HB, 0x4342u);
   }
+  __device__ __forceinline__ void extract2_np(uint32_t wa, uint32_t wb, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) const {
+    a0 = prmt(wa, HB, 0x4240u);  // lanes {k0, k2}
+    a2 = prmt(wa, HB, 0x4341u);  // lanes {k1, k3}
+    a1 = prmt(wb, HB, 0x4240u);
+    a3 = prmt(wb, HB, 0x4341u);
+  }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
@@ -194,14 +212,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
 struct SKCfg {
@@ -214,33 +226,42 @@ struct SKCfg {
   static constexpr int ST = (F == 1) ? 2 : 4;    // ring stages
   static constexpr int W_BYTES = ST * NWV * 256 * 16;
   static constexpr int M_BYTES = ST * 4 * 256 * MB;
-  static constexpr int SMEM = W_BYTES + M_BYTES;
+  static constexpr int P_BYTES = 2 * 8 * MT * 128 * 4;  // double-buffered split-K partials, one 16x8 tile per warp
+  static constexpr int SMEM = W_BYTES + M_BYTES + P_BYTES;
+  static constexpr int MIN_CTAS = (SMEM <= 110 * 1024 && MT <= 2) ? 2 : 1;
 };
 
+// Persistent CTAs; CTA b owns the 16-row tiles b, b+grid, b+2*grid, ... of the concatenated tile list of up to four
+// matrices.  Its 8 warps split K of the current tile into 8 contiguous chunks of 256-k units and stream them through
+// per-thread cp.async rings (the ring keeps prefetching across tile boundaries, so HBM requests never drain).  Partials
+// meet in shared memory once per tile (one block barrier, double-buffered) and warp (tile % 8) adds them in warp order:
+// deterministic, no atomics, no global workspace.
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
-__global__ void __launch_bounds__(256, 2) linear_streamk_kernel(const __grid_constant__ SKArgs a) {
+__global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS) linear_small_kernel(const __grid_constant__ SKArgs a) {
   using C = SKCfg<T, NBITS, GS, MT, MAGIC>;
   constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, MB = C::MB, NWV = C::NWV, ST = C::ST;
   using MM = MT16<T>;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint4* wring = reinterpret_cast<uint4*>(smem);   // [ST][NWV][256] one 16-byte slot per thread
-  uint8_t* mring = smem + C::W_BYTES;              // [ST][4][256][MB]
+  uint4* wring = reinterpret_cast<uint4*>(smem);                             // [ST][NWV][256] one 16-byte slot per thread
+  uint8_t* mring = smem + C::W_BYTES;                                        // [ST][4][256][MB]
+  float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);  // [2][8][MT][128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, c = lane & 3;
-  const long long TW = (long long)gridDim.x * 8, gw = (long long)blockIdx.x * 8 + warp;
-  const long long u0 = gw * a.total_units / TW, u1 = (gw + 1) * a.total_units / TW;
-  if (u0 >= u1) return;  // no block-level synchronisation anywhere below: warps are independent
-
   const int p = (F == 1) ? r : (r % P);
   const int fa = (F == 1) ? 0 : (r / P), fb = (F == 1) ? 0 : (F / 2 + r / P);
   Lanes<T, NBITS, MAGIC> lanes;
   lanes.init(8 - NBITS * (fa + 1), 8 - NBITS * (fb + 1));
 
-  // ---- tile lookup: which matrix a global tile belongs to, and this thread's two rows in it ----------------
+  // this warp's k-chunk of every tile (the same for all tiles: all matrices share K)
+  const int kb0 = a.KB * warp / 8, kb1 = a.KB * (warp + 1) / 8;
+  const int upt = kb1 - kb0;  // units per tile for this warp (may be 0 when K < 2048)
+  const int n_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles owned by this CTA
+  if (n_tiles <= 0) return;
+
   struct Tile {
     const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y;
-    int N, prow_a, prow_b, n_a, n_b; bool ok_a, ok_b;
+    int N, step, tile0;
   };
   auto locate = [&](int gt, Tile& t) {
     int pi = 0;
@@ -253,31 +274,29 @@ __global__ void __launch_bounds__(256, 2) linear_streamk_kernel(const __grid_con
     for (int i = 1; i < kMaxProb; ++i)
       if (pi == i) { Wq = a.p[i].Wq; sc = a.p[i].scale; ze = a.p[i].zero; bi = a.p[i].bias; y = a.p[i].y; N = a.p[i].N; step = a.p[i].step; tile0 = a.p[i].tile0; }
     t.Wq = Wq; t.scale = reinterpret_cast<const T*>(sc); t.zero = reinterpret_cast<const T*>(ze);
-    t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.N = N;
-    t.prow_a = (gt - tile0) * P + p;
-    t.prow_b = (F == 1) ? t.prow_a + 8 : t.prow_a;
-    t.ok_a = t.prow_a < step; t.ok_b = t.prow_b < step;
-    t.n_a = fa * step + t.prow_a; t.n_b = fb * step + t.prow_b;
+    t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.N = N; t.step = step; t.tile0 = tile0;
   };
 
-  // ---- issue cursor: where the next cp.async unit comes from -------------------------------------------------
-  int i_gt = (int)(u0 / a.KB), i_kb = (int)(u0 % a.KB);
+  // ---- issue cursor -------------------------------------------------------------------------------------------
+  int i_tile = 0, i_k = 0;  // index into this CTA's tile list / unit within the warp's chunk
   const uint8_t *iw_a, *iw_b;
   const T *is_a, *iz_a, *is_b, *iz_b;
   auto issue_setup = [&]() {
-    Tile t; locate(i_gt, t);
+    Tile t; locate((int)blockIdx.x + i_tile * (int)gridDim.x, t);
+    const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
+    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
     // rows past the ragged edge re-read row 0 (always mapped); their results are never stored
-    const long long ra = t.ok_a ? t.prow_a : 0, rb = t.ok_b ? t.prow_b : 0;
-    const long long na = t.ok_a ? t.n_a : 0, nb = t.ok_b ? t.n_b : 0;
-    iw_a = t.Wq + ra * a.K + (long long)i_kb * 256 + 16 * c;
-    iw_b = t.Wq + rb * a.K + (long long)i_kb * 256 + 16 * c;
-    is_a = t.scale + na * a.Gk + i_kb * GPB; iz_a = t.zero + na * a.Gk + i_kb * GPB;
-    is_b = t.scale + nb * a.Gk + i_kb * GPB; iz_b = t.zero + nb * a.Gk + i_kb * GPB;
+    const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
+    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
+    iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
+    iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
+    is_a = t.scale + na * a.Gk + kb0 * GPB; iz_a = t.zero + na * a.Gk + kb0 * GPB;
+    is_b = t.scale + nb * a.Gk + kb0 * GPB; iz_b = t.zero + nb * a.Gk + kb0 * GPB;
   };
-  issue_setup();
-  long long issued = u0;
+  int to_issue = n_tiles * upt;
+  if (to_issue > 0) issue_setup();
   auto issue = [&](int stage) {
-    if (issued < u1) {
+    if (to_issue > 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
       if (F == 1) {
@@ -288,156 +307,343 @@ __global__ void __launch_bounds__(256, 2) linear_streamk_kernel(const __grid_con
       cp_async_small<MB>(mring + ((stage * 4 + 1) * 256 + tid) * MB, iz_a);
       cp_async_small<MB>(mring + ((stage * 4 + 2) * 256 + tid) * MB, is_b);
       cp_async_small<MB>(mring + ((stage * 4 + 3) * 256 + tid) * MB, iz_b);
-      ++issued;
-      if (++i_kb == a.KB) {
-        i_kb = 0; ++i_gt;
-        if (issued < u1) issue_setup();
+      --to_issue;
+      if (++i_k == upt) {
+        i_k = 0; ++i_tile;
+        if (to_issue > 0) issue_setup();
       } else {
         iw_a += 256; iw_b += 256; is_a += GPB; iz_a += GPB; is_b += GPB; iz_b += GPB;
       }
     }
     cp_async_commit();  // always commit (possibly empty) so the group count per iteration is uniform
   };
+  // Weights and meta never depend on the previous kernel: start streaming them before the programmatic-dependency wait,
+  // so under PDL this prologue overlaps the tail of whatever produced x.
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue(s);
+  pdl_launch_dependents();
+  pdl_wait();
 
-  // ---- consume cursor ----------------------------------------------------------------------------------------
-  int c_gt = (int)(u0 / a.KB), c_kb = (int)(u0 % a.KB);
-  bool new_tile = true;
-  int k_first = 0;
-  Tile ct;
-  const T* xp[MT];
-  float tot[MT][4];
+  const T* xbase[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    // token columns >= M alias the last real token: MMA columns are independent and never stored
+    const int m = min(mt * 8 + r, a.M - 1);
+    xbase[mt] = reinterpret_cast<const T*>(a.x) + (long long)m * a.K + 16 * c;
+  }
+  // activations are software-pipelined one k64 step ahead (they come from L1/L2, 16 consecutive k per thread)
+  uint4 xa[MT], xb[MT];
+  auto load_x = [&](int kb, int us) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint4* q = reinterpret_cast<const uint4*>(xbase[mt] + kb * 256 + us * 64);
+      xa[mt] = __ldg(q);
+      xb[mt] = __ldg(q + 1);
+    }
+  };
+  if (upt > 0) load_x(kb0, 0);
+
   int stage = 0;
+  for (int ti = 0; ti < n_tiles; ++ti) {
+    float tot[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tot[mt][i] = 0.0f;
 
-  for (long long u = u0; u < u1; ++u) {
-    {
-      int is = stage + (ST - 1);
-      if (is >= ST) is -= ST;
-      issue(is);
-    }
-    if (new_tile) {
-      locate(c_gt, ct);
-      k_first = c_kb;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        // token columns >= M alias the last real token: MMA columns are independent and never stored
-        const int m = min(mt * 8 + r, a.M - 1);
-        xp[mt] = reinterpret_cast<const T*>(a.x) + (long long)m * a.K + 16 * c;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tot[mt][i] = 0.0f;
+    for (int ku = 0; ku < upt; ++ku) {
+      {
+        int is = stage + (ST - 1);
+        if (is >= ST) is -= ST;
+        issue(is);
       }
-      new_tile = false;
-    }
-    cp_async_wait<ST - 1>();  // the group of unit u (and everything older) has landed in this thread's slots
+      cp_async_wait<ST - 1>();  // the group of this unit (and everything older) has landed in this thread's slots
 
-    float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
-    {
-      const Vec<T, GPB> v0 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 0) * 256 + tid) * MB);
-      const Vec<T, GPB> v1 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 1) * 256 + tid) * MB);
-      const Vec<T, GPB> v2 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 2) * 256 + tid) * MB);
-      const Vec<T, GPB> v3 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 3) * 256 + tid) * MB);
+      float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
+      {
+        const Vec<T, GPB> v0 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 0) * 256 + tid) * MB);
+        const Vec<T, GPB> v1 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 1) * 256 + tid) * MB);
+        const Vec<T, GPB> v2 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 2) * 256 + tid) * MB);
+        const Vec<T, GPB> v3 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 3) * 256 + tid) * MB);
 #pragma unroll
-      for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(v0.v[i]); zA[i] = to_f32<T>(v1.v[i]); sB[i] = to_f32<T>(v2.v[i]); zB[i] = to_f32<T>(v3.v[i]); }
-    }
-    float Sg[MT][4], Xg[MT][4];
-#pragma unroll
-    for (int us = 0; us < 4; ++us) {
-      // activations for this k64 step: 16 consecutive k per thread, one column (token) per 4-lane group
-      uint4 xa[MT], xb[MT];
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const uint4* q = reinterpret_cast<const uint4*>(xp[mt] + (long long)c_kb * 256 + us * 64);
-        xa[mt] = __ldg(q);
-        xb[mt] = __ldg(q + 1);
+        for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(v0.v[i]); zA[i] = to_f32<T>(v1.v[i]); sB[i] = to_f32<T>(v2.v[i]); zB[i] = to_f32<T>(v3.v[i]); }
       }
-      const uint4 va = wring[(stage * NWV + us) * 256 + tid];
-      uint4 vb = va;
-      if (F == 1) vb = wring[(stage * NWV + 4 + us) * 256 + tid];
-      const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
-      const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+      const int kb = kb0 + ku;
+      const int kb_next = (ku + 1 == upt) ? kb0 : kb + 1;  // x depends on k only: the next tile restarts at kb0
+      float Sg[MT][4], Xg[MT][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t a0, a1, a2, a3;
-        if constexpr (F == 1) lanes.extract2(wa[j], wb[j], a0, a1, a2, a3);
-        else lanes.extract(wa[j], a0, a1, a2, a3);
-        const bool first = ((us * 4 + j) % MPG) == 0;  // first MMA of a group starts from C = 0
+      for (int us = 0; us < 4; ++us) {
+        uint4 ya[MT], yb[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t b0 = (j == 0) ? xa[mt].x : (j == 1) ? xa[mt].z : (j == 2) ? xb[mt].x : xb[mt].z;
-          const uint32_t b1 = (j == 0) ? xa[mt].y : (j == 1) ? xa[mt].w : (j == 2) ? xb[mt].y : xb[mt].w;
-          if (first) {
-            MM::mma0(Sg[mt], a0, a1, a2, a3, b0, b1);
-            MM::mma0(Xg[mt], MM::ONE2, MM::ONE2, MM::ONE2, MM::ONE2, b0, b1);
-          } else {
-            MM::mma(Sg[mt], a0, a1, a2, a3, b0, b1);
-            MM::mma(Xg[mt], MM::ONE2, MM::ONE2, MM::ONE2, MM::ONE2, b0, b1);
-          }
-        }
-        if (((us * 4 + j + 1) % MPG) == 0) {
-          // a quantisation group is complete: tot += s*(Q - z*X), with lane value = OFF + q*V folded in
-          const int gi = (us * 4 + j) / MPG;
-          const float ka = sA[gi] * lanes.invV_a, la = -sA[gi] * (lanes.offV_a + zA[gi]);
-          const float kb = sB[gi] * lanes.invV_b, lb = -sB[gi] * (lanes.offV_b + zB[gi]);
+        for (int mt = 0; mt < MT; ++mt) { ya[mt] = xa[mt]; yb[mt] = xb[mt]; }
+        if (us < 3) load_x(kb, us + 1); else load_x(kb_next, 0);
+        const uint4 va = wring[(stage * NWV + us) * 256 + tid];
+        uint4 vb = va;
+        if (F == 1) vb = wring[(stage * NWV + 4 + us) * 256 + tid];
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t a0, a1, a2, a3;
+          if constexpr (F == 1) lanes.extract2(wa[j], wb[j], a0, a1, a2, a3);
+          else lanes.extract(wa[j], a0, a1, a2, a3);
+          const bool first = ((us * 4 + j) % MPG) == 0;  // first MMA of a group starts from C = 0
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            tot[mt][0] = fmaf(ka, Sg[mt][0], fmaf(la, Xg[mt][0], tot[mt][0]));
-            tot[mt][1] = fmaf(ka, Sg[mt][1], fmaf(la, Xg[mt][1], tot[mt][1]));
-            tot[mt][2] = fmaf(kb, Sg[mt][2], fmaf(lb, Xg[mt][0], tot[mt][2]));
-            tot[mt][3] = fmaf(kb, Sg[mt][3], fmaf(lb, Xg[mt][1], tot[mt][3]));
+            const uint32_t b0 = (j == 0) ? ya[mt].x : (j == 1) ? ya[mt].z : (j == 2) ? yb[mt].x : yb[mt].z;
+            const uint32_t b1 = (j == 0) ? ya[mt].y : (j == 1) ? ya[mt].w : (j == 2) ? yb[mt].y : yb[mt].w;
+            if (first) {
+              MM::mma0(Sg[mt], a0, a1, a2, a3, b0, b1);
+              MM::mma0(Xg[mt], MM::ONE2, MM::ONE2, MM::ONE2, MM::ONE2, b0, b1);
+            } else {
+              MM::mma(Sg[mt], a0, a1, a2, a3, b0, b1);
+              MM::mma(Xg[mt], MM::ONE2, MM::ONE2, MM::ONE2, MM::ONE2, b0, b1);
+            }
           }
-        }
-      }
-    }
-
-    // ---- end of unit: close the tile if this was its last unit in our slice -----------------------------------
-    const bool tile_end = (c_kb == a.KB - 1);
-    if (tile_end || u == u1 - 1) {
-      const bool covers_start = (k_first == 0);
-      if (!covers_start) {
-        // contributor: the tile began in an earlier warp's slice -> publish our partial (fragment layout)
-        float* dst = a.ws_partial + (gw * MT) * 128 + lane * 4;
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-          *reinterpret_cast<float4*>(dst + mt * 128) = make_float4(tot[mt][0], tot[mt][1], tot[mt][2], tot[mt][3]);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release(a.ws_flags + gw, 1);
-      } else {
-        if (!tile_end) {
-          // finisher: we hold the first k-chunk; later warps hold the rest.  Add their partials in warp order.
-          const long long tile_end_unit = ((long long)c_gt + 1) * a.KB;
-          for (long long w2 = gw + 1; w2 < TW; ++w2) {
-            const long long s2 = w2 * a.total_units / TW;
-            if (s2 >= tile_end_unit) break;
-            if (s2 >= (w2 + 1) * a.total_units / TW) continue;  // that warp has no units
-            while (ld_acquire(a.ws_flags + w2) == 0) {}
-            const float* src = a.ws_partial + (w2 * MT) * 128 + lane * 4;
+          if (((us * 4 + j + 1) % MPG) == 0) {
+            // a quantisation group is complete: tot += s*(Q - z*X), with lane value = OFF + q*V folded in
+            const int gi = (us * 4 + j) / MPG;
+            const float ka = sA[gi] * lanes.invV_a, la = -sA[gi] * (lanes.offV_a + zA[gi]);
+            const float kb2 = sB[gi] * lanes.invV_b, lb = -sB[gi] * (lanes.offV_b + zB[gi]);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(src + mt * 128));
-              tot[mt][0] += v.x; tot[mt][1] += v.y; tot[mt][2] += v.z; tot[mt][3] += v.w;
+              tot[mt][0] = fmaf(ka, Sg[mt][0], fmaf(la, Xg[mt][0], tot[mt][0]));
+              tot[mt][1] = fmaf(ka, Sg[mt][1], fmaf(la, Xg[mt][1], tot[mt][1]));
+              tot[mt][2] = fmaf(kb2, Sg[mt][2], fmaf(lb, Xg[mt][0], tot[mt][2]));
+              tot[mt][3] = fmaf(kb2, Sg[mt][3], fmaf(lb, Xg[mt][1], tot[mt][3]));
             }
-            __syncwarp();
-            if (lane == 0) a.ws_flags[w2] = 0;  // leave the workspace clean for the next launch / graph replay
-          }
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int m0 = mt * 8 + 2 * c;
-          if (m0 < a.M) {
-            if (ct.ok_a) MM::st(ct.y, (long long)m0 * ct.N + ct.n_a, tot[mt][0], ct.bias, ct.n_a);
-            if (ct.ok_b) MM::st(ct.y, (long long)m0 * ct.N + ct.n_b, tot[mt][2], ct.bias, ct.n_b);
-          }
-          if (m0 + 1 < a.M) {
-            if (ct.ok_a) MM::st(ct.y, (long long)(m0 + 1) * ct.N + ct.n_a, tot[mt][1], ct.bias, ct.n_a);
-            if (ct.ok_b) MM::st(ct.y, (long long)(m0 + 1) * ct.N + ct.n_b, tot[mt][3], ct.bias, ct.n_b);
           }
         }
       }
+      if (++stage == ST) stage = 0;
     }
-    if (tile_end) { c_kb = 0; ++c_gt; new_tile = true; } else { ++c_kb; }
-    if (++stage == ST) stage = 0;
+
+    // ---- tile done: partials meet in shared memory (double-buffered: one barrier per tile is enough) -----------
+    float* buf = part_s + (ti & 1) * (8 * MT * 128);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      *reinterpret_cast<float4*>(buf + (warp * MT + mt) * 128 + lane * 4) = make_float4(tot[mt][0], tot[mt][1], tot[mt][2], tot[mt][3]);
+    __syncthreads();
+    if (warp == (ti & 7)) {
+      const int gt = (int)blockIdx.x + ti * (int)gridDim.x;
+      Tile t; locate(gt, t);
+      const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+      const bool ok_a = prow_a < t.step, ok_b = prow_b < t.step;
+      const int n_a = fa * t.step + prow_a, n_b = fb * t.step + prow_b;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float4 v = *reinterpret_cast<const float4*>(buf + (w * MT + mt) * 128 + lane * 4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int m0 = mt * 8 + 2 * c;
+        if (m0 < a.M) {
+          if (ok_a) MM::st(t.y, (long long)m0 * t.N + n_a, acc.x, t.bias, n_a);
+          if (ok_b) MM::st(t.y, (long long)m0 * t.N + n_b, acc.z, t.bias, n_b);
+        }
+        if (m0 + 1 < a.M) {
+          if (ok_a) MM::st(t.y, (long long)(m0 + 1) * t.N + n_a, acc.y, t.bias, n_a);
+          if (ok_b) MM::st(t.y, (long long)(m0 + 1) * t.N + n_b, acc.w, t.bias, n_b);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// M == 1 specialisation (the decode hot path).  Same scheduling and staging as linear_small_kernel, but everything that
+// depends only on the activation is hoisted out of the per-tile loop: each warp stages ITS k-chunk of x once in shared
+// memory, already permuted to the lane pairing the bit-tricks produce ({k0,k2},{k1,k3}: no PRMT on the weights), and
+// sums it per quantisation group once (no all-ones MMA); the affine correction is applied to the single real column.
+template <typename T, int NBITS, int GS, int MAGIC, int ST>
+struct D1Cfg {
+  static constexpr int F = 8 / NBITS, P = 16 / F, MPG = GS / 16, GPB = 256 / GS, MB = GPB * 2;
+  static constexpr int NWV = (F == 1) ? 8 : 4;
+  static constexpr int W_BYTES = ST * NWV * 256 * 16;
+  static constexpr int M_BYTES = ST * 4 * 256 * MB;
+  static constexpr int P_BYTES = 2 * 8 * 16 * 4;  // double-buffered: 8 warps x 16 rows
+  static int smem(int K) { return W_BYTES + M_BYTES + P_BYTES + K * 2 + (K / GS) * 4; }
+};
+
+template <typename T, int NBITS, int GS, int MAGIC, int ST>
+__global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
+  using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
+  constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, MB = C::MB, NWV = C::NWV;
+  using MM = MT16<T>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint4* wring = reinterpret_cast<uint4*>(smem);
+  uint8_t* mring = smem + C::W_BYTES;
+  float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);       // [2][8][16]
+  T* xs = reinterpret_cast<T*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES);      // [K] permuted activations
+  float* xsum = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES + a.K * 2);  // [K/GS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = lane >> 2, c = lane & 3;
+  const int p = (F == 1) ? r : (r % P);
+  const int fa = (F == 1) ? 0 : (r / P), fb = (F == 1) ? 0 : (F / 2 + r / P);
+  Lanes<T, NBITS, MAGIC> lanes;
+  lanes.init(8 - NBITS * (fa + 1), 8 - NBITS * (fb + 1));
+
+  const int kb0 = a.KB * warp / 8, kb1 = a.KB * (warp + 1) / 8;
+  const int upt = kb1 - kb0;
+  const int n_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (n_tiles <= 0) return;
+
+  struct Tile { const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y; int N, step, tile0; };
+  auto locate = [&](int gt, Tile& t) {
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProb; ++i)
+      if (i < a.nprob && gt >= a.p[i].tile0) pi = i;
+    const uint8_t* Wq = a.p[0].Wq; const void* sc = a.p[0].scale; const void* ze = a.p[0].zero; const void* bi = a.p[0].bias;
+    void* y = a.p[0].y; int N = a.p[0].N, step = a.p[0].step, tile0 = a.p[0].tile0;
+#pragma unroll
+    for (int i = 1; i < kMaxProb; ++i)
+      if (pi == i) { Wq = a.p[i].Wq; sc = a.p[i].scale; ze = a.p[i].zero; bi = a.p[i].bias; y = a.p[i].y; N = a.p[i].N; step = a.p[i].step; tile0 = a.p[i].tile0; }
+    t.Wq = Wq; t.scale = reinterpret_cast<const T*>(sc); t.zero = reinterpret_cast<const T*>(ze);
+    t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.N = N; t.step = step; t.tile0 = tile0;
+  };
+
+  int i_tile = 0, i_k = 0;
+  const uint8_t *iw_a, *iw_b;
+  const T *is_a, *iz_a, *is_b, *iz_b;
+  auto issue_setup = [&]() {
+    const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
+    Tile t; locate(gt, t);
+    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
+    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
+    iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
+    iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
+    is_a = t.scale + na * a.Gk + kb0 * GPB; iz_a = t.zero + na * a.Gk + kb0 * GPB;
+    is_b = t.scale + nb * a.Gk + kb0 * GPB; iz_b = t.zero + nb * a.Gk + kb0 * GPB;
+  };
+  int to_issue = n_tiles * upt;
+  if (to_issue > 0) issue_setup();
+  auto issue = [&](int stage) {
+    if (to_issue > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
+      if (F == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
+      }
+      cp_async_small<MB>(mring + ((stage * 4 + 0) * 256 + tid) * MB, is_a);
+      cp_async_small<MB>(mring + ((stage * 4 + 1) * 256 + tid) * MB, iz_a);
+      cp_async_small<MB>(mring + ((stage * 4 + 2) * 256 + tid) * MB, is_b);
+      cp_async_small<MB>(mring + ((stage * 4 + 3) * 256 + tid) * MB, iz_b);
+      --to_issue;
+      if (++i_k == upt) {
+        i_k = 0; ++i_tile;
+        if (to_issue > 0) issue_setup();
+      } else {
+        iw_a += 256; iw_b += 256; is_a += GPB; iz_a += GPB; is_b += GPB; iz_b += GPB;
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) issue(s);
+  pdl_launch_dependents();
+  pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
+
+  // ---- stage this warp's k-chunk of x (permuted: k -> k with bits 0 and 1 swapped) and its per-group sums ----------
+  {
+    const T* x = reinterpret_cast<const T*>(a.x);
+    const int k_lo = kb0 * 256, k_hi = kb1 * 256;
+    for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
+      const Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+      Vec<T, 8> w;
+      w.v[0] = v.v[0]; w.v[1] = v.v[2]; w.v[2] = v.v[1]; w.v[3] = v.v[3];
+      w.v[4] = v.v[4]; w.v[5] = v.v[6]; w.v[6] = v.v[5]; w.v[7] = v.v[7];
+      *reinterpret_cast<Vec<T, 8>*>(xs + k8) = w;
+    }
+    __syncwarp();
+    for (int g = k_lo / GS + lane; g < k_hi / GS; g += 32) {
+      float acc = 0.0f;
+#pragma unroll 4
+      for (int i = 0; i < GS; i += 8) {
+        const Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(xs + g * GS + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += to_f32<T>(v.v[j]);
+      }
+      xsum[g] = acc;
+    }
+    __syncwarp();
+  }
+
+  int stage = 0;
+  for (int ti = 0; ti < n_tiles; ++ti) {
+    float tot_a = 0.0f, tot_b = 0.0f;
+    for (int ku = 0; ku < upt; ++ku) {
+      {
+        int is = stage + (ST - 1);
+        if (is >= ST) is -= ST;
+        issue(is);
+      }
+      cp_async_wait<ST - 1>();
+      float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
+      {
+        const Vec<T, GPB> v0 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 0) * 256 + tid) * MB);
+        const Vec<T, GPB> v1 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 1) * 256 + tid) * MB);
+        const Vec<T, GPB> v2 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 2) * 256 + tid) * MB);
+        const Vec<T, GPB> v3 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 3) * 256 + tid) * MB);
+#pragma unroll
+        for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(v0.v[i]); zA[i] = to_f32<T>(v1.v[i]); sB[i] = to_f32<T>(v2.v[i]); zB[i] = to_f32<T>(v3.v[i]); }
+      }
+      const int kb = kb0 + ku;
+      const T* xk = xs + kb * 256 + 16 * c;
+      float Sg[4];
+#pragma unroll
+      for (int us = 0; us < 4; ++us) {
+        const uint4 xa = *reinterpret_cast<const uint4*>(xk + us * 64);      // permuted: {k0,k2},{k1,k3},{k4,k6},{k5,k7}
+        const uint4 xb = *reinterpret_cast<const uint4*>(xk + us * 64 + 8);
+        const uint4 va = wring[(stage * NWV + us) * 256 + tid];
+        uint4 vb = va;
+        if (F == 1) vb = wring[(stage * NWV + 4 + us) * 256 + tid];
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w};
+        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t a0, a1, a2, a3;
+          if constexpr (F == 1) lanes.extract2_np(wa[j], wb[j], a0, a1, a2, a3);
+          else lanes.extract_np(wa[j], a0, a1, a2, a3);
+          const uint32_t b0 = (j == 0) ? xa.x : (j == 1) ? xa.z : (j == 2) ? xb.x : xb.z;
+          const uint32_t b1 = (j == 0) ? xa.y : (j == 1) ? xa.w : (j == 2) ? xb.y : xb.w;
+          if (((us * 4 + j) % MPG) == 0) MM::mma0(Sg, a0, a1, a2, a3, b0, b1);
+          else MM::mma(Sg, a0, a1, a2, a3, b0, b1);
+          if (((us * 4 + j + 1) % MPG) == 0) {
+            const int gi = (us * 4 + j) / MPG;
+            const float X = xsum[kb * GPB + gi];
+            tot_a = fmaf(sA[gi] * lanes.invV_a, Sg[0], fmaf(-sA[gi] * (lanes.offV_a + zA[gi]), X, tot_a));
+            tot_b = fmaf(sB[gi] * lanes.invV_b, Sg[2], fmaf(-sB[gi] * (lanes.offV_b + zB[gi]), X, tot_b));
+          }
+        }
+      }
+      if (++stage == ST) stage = 0;
+    }
+    // ---- tile done: every lane of a 4-lane group holds the same two row results; lane c == 0 publishes them ------
+    float* buf = part_s + (ti & 1) * 128;
+    if (c == 0) { buf[warp * 16 + r] = tot_a; buf[warp * 16 + 8 + r] = tot_b; }
+    __syncthreads();
+    if (warp == (ti & 7) && lane < 16) {
+      const int gt = (int)blockIdx.x + ti * (int)gridDim.x;
+      Tile t; locate(gt, t);
+      const int rr = lane & 7, hi = lane >> 3;  // fragment row lane = rr + 8*hi
+      const int pp = (F == 1) ? rr : (rr % P);
+      const int ff = (F == 1) ? 0 : (hi ? F / 2 + rr / P : rr / P);
+      const int prow = (gt - t.tile0) * P + pp + ((F == 1 && hi) ? 8 : 0);
+      if (prow < t.step) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += buf[w * 16 + lane];
+        const int n = ff * t.step + prow;
+        MM::st(t.y, n, acc, t.bias, n);
+      }
+    }
   }
   cp_async_wait<0>();
 }
@@ -462,13 +668,12 @@ static int sm_count() {
   return n;
 }
 
-// The persistent grid: every CTA must be co-resident (split tiles are finished by spinning on peer warps).
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
 static int grid_for_kernel(int* grid_out) {
   using C = SKCfg<T, NBITS, GS, MT, MAGIC>;
   static int grid = 0;
   if (!grid) {
-    auto k = linear_streamk_kernel<T, NBITS, GS, MT, MAGIC>;
+    auto k = linear_small_kernel<T, NBITS, GS, MT, MAGIC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
     int occ = 0;
@@ -481,55 +686,138 @@ static int grid_for_kernel(int* grid_out) {
   return HQQ_OK;
 }
 
-constexpr int kMaxGrid = 2 * 160;  // upper bound used to size the workspace before the kernel variant is known
+// Persistent CTAs take tiles round-robin, so a grid that does not divide the tile count leaves most CTAs idle during the
+// last round (896 tiles on 296 CTAs = 3.03 -> 4 rounds, 76 %).  The kernel is bound by aggregate HBM bandwidth, not by
+// per-SM work, so it is better to launch fewer, equally loaded CTAs: pick g in [max_grid/2, max_grid] maximising
+// tiles / (ceil(tiles/g) * g); ties go to the larger grid.
+static int balanced_grid(int tiles, int max_grid) {
+  if (tiles <= max_grid) return tiles;
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("HQQ_B200_BALANCED_GRID"); mode = (e && e[0] == '1') ? 1 : 0; }
+  if (!mode) return max_grid;  // measured on B200: the kernel is bound per SM, so filling every CTA slot wins
+  int best = max_grid;
+  double best_eff = 0.0;
+  for (int g = max_grid; g >= max_grid / 2; --g) {
+    const int rounds = (tiles + g - 1) / g;
+    const double eff = (double)tiles / ((double)rounds * g);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = g; }
+  }
+  return best;
+}
+
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HQQ_B200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
-static int launch_sk(SKArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int launch_sk(SKArgs& a, cudaStream_t st) {
   using C = SKCfg<T, NBITS, GS, MT, MAGIC>;
   int grid = 0;
   int rc = grid_for_kernel<T, NBITS, GS, MT, MAGIC>(&grid);
   if (rc) return rc;
-  const size_t need = (size_t)grid * 8 * MT * 128 * sizeof(float) + (size_t)kMaxGrid * 8 * sizeof(int);
-  HQQ_REQUIRE(ws && ws_bytes >= need, HQQ_E_WORKSPACE, "hqq_b200_linear_fwd: workspace %zu < required %zu bytes", ws_bytes, need);
-  a.ws_flags = reinterpret_cast<int*>(ws);  // flags first: they must stay zero between launches
-  a.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)kMaxGrid * 8 * sizeof(int));
-  linear_streamk_kernel<T, NBITS, GS, MT, MAGIC><<<grid, 256, C::SMEM, st>>>(a);
-  HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/streamk");
+  grid = balanced_grid(a.total_tiles, grid);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_small_kernel<T, NBITS, GS, MT, MAGIC>, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd/small: CUDA launch failed: %s", cudaGetErrorString(e));
   return HQQ_OK;
 }
 
+template <typename T, int NBITS, int GS, int MAGIC, int ST>
+static int launch_d1(SKArgs& a, cudaStream_t st) {
+  using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
+  static int max_smem = 0, occ_grid = 0;
+  const int smem = C::smem(a.K);
+  auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST>;
+  if (smem > max_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    max_smem = smem;
+    occ_grid = 0;
+  }
+  if (!occ_grid) occ_grid = sm_count() * ((ST == 2 && NBITS != 8) ? 3 : 2);
+  int grid = occ_grid;
+  if (smem * (grid / sm_count()) > 224 * 1024) grid = sm_count() * (224 * 1024 / smem);
+  grid = balanced_grid(a.total_tiles, grid);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd/decode1: CUDA launch failed: %s", cudaGetErrorString(e));
+  return HQQ_OK;
+}
+
+static bool d1_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HQQ_B200_DECODE1");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 template <typename T, int NBITS, int GS, int MAGIC>
-static int sk_mt(SKArgs& a, void* ws, size_t wsb, cudaStream_t st) {
-  if (a.M <= 8) return launch_sk<T, NBITS, GS, 1, MAGIC>(a, ws, wsb, st);
-  if (a.M <= 16) return launch_sk<T, NBITS, GS, 2, MAGIC>(a, ws, wsb, st);
-  return launch_sk<T, NBITS, GS, 4, MAGIC>(a, ws, wsb, st);
+static int sk_mt(SKArgs& a, cudaStream_t st) {
+  if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
+    if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2>(a, st);
+    static int st_override = -1;
+    if (st_override < 0) { const char* e = getenv("HQQ_B200_D1_STAGES"); st_override = e ? atoi(e) : 0; }
+    if (st_override == 2) return launch_d1<T, NBITS, GS, MAGIC, 2>(a, st);
+    if (st_override == 3) return launch_d1<T, NBITS, GS, MAGIC, 3>(a, st);
+    return (a.K > 8192) ? launch_d1<T, NBITS, GS, MAGIC, 3>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 4>(a, st);
+  }
+  if (a.M <= 8) return launch_sk<T, NBITS, GS, 1, MAGIC>(a, st);
+  if (a.M <= 16) return launch_sk<T, NBITS, GS, 2, MAGIC>(a, st);
+  return launch_sk<T, NBITS, GS, 4, MAGIC>(a, st);
 }
 
 template <typename T, int NBITS, int MAGIC>
-static int sk_gs(SKArgs& a, int gs, void* ws, size_t wsb, cudaStream_t st) {
+static int sk_gs(SKArgs& a, int gs, cudaStream_t st) {
   switch (gs) {
-    case 64: return sk_mt<T, NBITS, 64, MAGIC>(a, ws, wsb, st);
-    case 128: return sk_mt<T, NBITS, 128, MAGIC>(a, ws, wsb, st);
+    case 64: return sk_mt<T, NBITS, 64, MAGIC>(a, st);
+    case 128: return sk_mt<T, NBITS, 128, MAGIC>(a, st);
   }
   return HQQ_E_UNSUPPORTED;
 }
 
 template <typename T>
-static int sk_bits(SKArgs& a, int gs, int nbits, void* ws, size_t wsb, cudaStream_t st) {
+static int sk_bits(SKArgs& a, int gs, int nbits, cudaStream_t st) {
   const bool sub = std::is_same<T, __half>::value && magic_mode() == MAGIC_SUBNORMAL;
   switch (nbits) {
     case 8:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 8, MAGIC_SUBNORMAL>(a, gs, ws, wsb, st) : sk_gs<T, 8, MAGIC_OFFSET>(a, gs, ws, wsb, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 8, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 8, MAGIC_OFFSET>(a, gs, st);
       else return HQQ_E_UNSUPPORTED;
     case 4:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 4, MAGIC_SUBNORMAL>(a, gs, ws, wsb, st) : sk_gs<T, 4, MAGIC_OFFSET>(a, gs, ws, wsb, st);
-      else return sk_gs<T, 4, MAGIC_OFFSET>(a, gs, ws, wsb, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 4, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 4, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 4, MAGIC_OFFSET>(a, gs, st);
     case 2:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 2, MAGIC_SUBNORMAL>(a, gs, ws, wsb, st) : sk_gs<T, 2, MAGIC_OFFSET>(a, gs, ws, wsb, st);
-      else return sk_gs<T, 2, MAGIC_OFFSET>(a, gs, ws, wsb, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 2, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 2, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 2, MAGIC_OFFSET>(a, gs, st);
     case 1:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 1, MAGIC_SUBNORMAL>(a, gs, ws, wsb, st) : sk_gs<T, 1, MAGIC_OFFSET>(a, gs, ws, wsb, st);
-      else return sk_gs<T, 1, MAGIC_OFFSET>(a, gs, ws, wsb, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 1, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 1, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 1, MAGIC_OFFSET>(a, gs, st);
   }
   return HQQ_E_UNSUPPORTED;
 }
@@ -547,17 +835,14 @@ bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis
   return true;
 }
 
-size_t small_workspace_bytes(int64_t M) {
-  const int MT = M <= 8 ? 1 : (M <= 16 ? 2 : 4);
-  return (size_t)kMaxGrid * 8 * sizeof(int) + (size_t)kMaxGrid * 8 * MT * 128 * sizeof(float);
-}
+size_t small_workspace_bytes(int64_t) { return 0; }  // split-K partials meet in shared memory
 
 int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
                        const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
                        void* ws, size_t ws_bytes, cudaStream_t st) {
   HQQ_REQUIRE(nprob >= 1 && nprob <= kMaxProb, HQQ_E_INVALID, "hqq_b200_linear_fwd_multi: 1..%d matrices per launch (got %d)", kMaxProb, nprob);
   HQQ_REQUIRE(aligned(x, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x must be 16-byte aligned");
-  HQQ_REQUIRE(aligned(ws, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: workspace must be 16-byte aligned");
+  (void)ws; (void)ws_bytes;
   const int F = 8 / nbits, P = 16 / F;
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
@@ -572,9 +857,8 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     if (i < nprob) tiles += (int)cdiv(a.p[i].step, P);
   }
   a.total_tiles = tiles;
-  a.total_units = (long long)tiles * a.KB;
-  if (dtype == HQQ_F16) return sk_bits<__half>(a, gs, nbits, ws, ws_bytes, st);
-  return sk_bits<__nv_bfloat16>(a, gs, nbits, ws, ws_bytes, st);
+  if (dtype == HQQ_F16) return sk_bits<__half>(a, gs, nbits, st);
+  return sk_bits<__nv_bfloat16>(a, gs, nbits, st);
 }
 
 }  // namespace hqq
