@@ -1,0 +1,238 @@
+// Decode-harness glue kernels (the caller of HQQLinear.forward, NOT the hot path): the few tiny ops
+// between the fused linears of a Llama-style block at batch 1, written so a decode step is 8 launches per block
+// instead of ~25 framework kernels.  fp16/bf16, one token.  All kernels are PDL-aware (griddepcontrol) so their
+// launch latency overlaps the tail of the previous kernel inside a CUDA graph.
+#include "common.cuh"
+
+namespace hqq {
+
+__device__ __forceinline__ void pdl_wait_g() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_g() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  __syncthreads();
+  return s;
+}
+
+// h += delta (optional); y = rmsnorm(h) * w         (one CTA; H <= 8 * blockDim * 4)
+template <typename T>
+__global__ void __launch_bounds__(1024) add_rmsnorm_kernel(T* __restrict__ h, const T* __restrict__ delta, const T* __restrict__ w,
+                                                           T* __restrict__ y, int H, float eps) {
+  __shared__ float red[32];
+  pdl_launch_g();
+  pdl_wait_g();
+  float v[8];
+  int n = 0;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x, ++n) {
+    float x = to_f32<T>(h[i]);
+    if (delta) {
+      x = to_f32<T>(from_f32<T>(x + to_f32<T>(delta[i])));  // residual stream stays in T, like h = h + o in the framework
+      h[i] = from_f32<T>(x);
+    }
+    v[n] = x;
+    ss += x * x;
+  }
+  const float tot = block_sum(ss, red);
+  const float inv = rsqrtf(tot / (float)H + eps);
+  n = 0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x, ++n) y[i] = from_f32<T>(to_f32<T>(from_f32<T>(v[n] * inv)) * to_f32<T>(w[i]));
+}
+
+// y = silu(g) * u
+template <typename T>
+__global__ void __launch_bounds__(256) silu_mul_kernel(const T* __restrict__ g, const T* __restrict__ u, T* __restrict__ y, int n) {
+  pdl_launch_g();
+  pdl_wait_g();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float a = to_f32<T>(g[i]);
+    const float s = to_f32<T>(from_f32<T>(a / (1.0f + __expf(-a))));
+    y[i] = from_f32<T>(s * to_f32<T>(u[i]));
+  }
+}
+
+// RoPE (rotate-half, cos/sin tables [L, hd]) + KV-cache append + single-token GQA attention over cache[0..pos].
+// grid = n_q_heads, block = hd (= 128) threads.  caches are [n_kv_heads, L, hd].
+template <typename T>
+__global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in, const T* __restrict__ v_in,
+                                                               const T* __restrict__ cos_t, const T* __restrict__ sin_t,
+                                                               T* __restrict__ k_cache, T* __restrict__ v_cache, const long long* __restrict__ pos_p,
+                                                               T* __restrict__ out, int n_q, int n_kv, int L, int hd, float scale) {
+  extern __shared__ float sm[];  // q[hd] | knew[hd] | p[L] | red[32]
+  float* qs = sm;
+  float* ks = sm + hd;
+  float* ps = sm + 2 * hd;
+  float* red = ps + L;
+  pdl_launch_g();
+  pdl_wait_g();
+  const int h = blockIdx.x, kvh = h / (n_q / n_kv), d = threadIdx.x;
+  const int pos = (int)pos_p[0];
+  const int half = hd / 2;
+  // rope: x*cos + rotate_half(x)*sin, computed in T like the framework ops
+  {
+    const float c = to_f32<T>(cos_t[(long long)pos * hd + d]), s = to_f32<T>(sin_t[(long long)pos * hd + d]);
+    const float qx = to_f32<T>(q_in[h * hd + d]);
+    const float qr = (d < half) ? -to_f32<T>(q_in[h * hd + d + half]) : to_f32<T>(q_in[h * hd + d - half]);
+    qs[d] = to_f32<T>(from_f32<T>(to_f32<T>(from_f32<T>(qx * c)) + to_f32<T>(from_f32<T>(qr * s))));
+    const float kx = to_f32<T>(k_in[kvh * hd + d]);
+    const float kr = (d < half) ? -to_f32<T>(k_in[kvh * hd + d + half]) : to_f32<T>(k_in[kvh * hd + d - half]);
+    const T kn = from_f32<T>(to_f32<T>(from_f32<T>(kx * c)) + to_f32<T>(from_f32<T>(kr * s)));
+    ks[d] = to_f32<T>(kn);
+    if (h % (n_q / n_kv) == 0) {  // one head of the group owns the cache write
+      k_cache[((long long)kvh * L + pos) * hd + d] = kn;
+      v_cache[((long long)kvh * L + pos) * hd + d] = v_in[kvh * hd + d];
+    }
+  }
+  __syncthreads();
+  // scores: thread t handles positions t, t+blockDim, ... ; the current position uses the freshly rotated k
+  float mx = -INFINITY;
+  for (int t = d; t <= pos; t += blockDim.x) {
+    float acc = 0.f;
+    if (t == pos) {
+      for (int i = 0; i < hd; ++i) acc += qs[i] * ks[i];
+    } else {
+      const T* kr = k_cache + ((long long)kvh * L + t) * hd;
+      for (int i = 0; i < hd; i += 8) {
+        const Vec<T, 8> kv = *reinterpret_cast<const Vec<T, 8>*>(kr + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += qs[i + j] * to_f32<T>(kv.v[j]);
+      }
+    }
+    acc *= scale;
+    ps[t] = acc;
+    mx = fmaxf(mx, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((d & 31) == 0) red[d >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = d; t <= pos; t += blockDim.x) {
+    const float e = __expf(ps[t] - mx);
+    ps[t] = e;
+    sum += e;
+  }
+  const float tot = block_sum(sum, red);
+  // output: thread d owns dimension d
+  float o = 0.f;
+  for (int t = 0; t < pos; ++t) o += ps[t] * to_f32<T>(v_cache[((long long)kvh * L + t) * hd + d]);
+  o += ps[pos] * to_f32<T>(v_in[kvh * hd + d]);
+  out[h * hd + d] = from_f32<T>(o / tot);
+}
+
+// argmax over n logits -> int64 index (two-stage in one launch via last-block pattern is overkill: one CTA, n ~ 128K)
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  pdl_launch_g();
+  pdl_wait_g();
+  float best = -INFINITY;
+  int idx = 0;
+  for (int i = threadIdx.x * 8; i < n; i += blockDim.x * 8) {
+    if (i + 8 <= n) {
+      const Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float f = to_f32<T>(v.v[j]); if (f > best) { best = f; idx = i + j; } }
+    } else {
+      for (int j = i; j < n; ++j) { const float f = to_f32<T>(x[j]); if (f > best) { best = f; idx = j; } }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+      if (bv[i] > best || (bv[i] == best && bi[i] < idx)) { best = bv[i]; idx = bi[i]; }
+    out[0] = idx;
+  }
+}
+
+template <typename K, typename... Args>
+static int launch_pdl(const char* name, K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "%s: CUDA launch failed: %s", name, cudaGetErrorString(e));
+  return HQQ_OK;
+}
+
+}  // namespace hqq
+
+using namespace hqq;
+
+extern "C" int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y, int H, float eps, int dtype, void* stream) {
+  HQQ_REQUIRE(h && weight && y && H > 0 && H <= 8 * 1024, HQQ_E_INVALID, "hqq_b200_glue_add_rmsnorm: bad arguments (H=%d)", H);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = H >= 4096 ? 1024 : 256;
+  if (dtype == HQQ_F16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__half>, dim3(1), dim3(threads), 0, st, (__half*)h, (const __half*)delta, (const __half*)weight, (__half*)y, H, eps);
+  if (dtype == HQQ_BF16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__nv_bfloat16>, dim3(1), dim3(threads), 0, st, (__nv_bfloat16*)h, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, (__nv_bfloat16*)y, H, eps);
+  set_error("hqq_b200_glue_add_rmsnorm: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_silu_mul(const void* gate, const void* up, void* y, int n, int dtype, void* stream) {
+  HQQ_REQUIRE(gate && up && y && n > 0, HQQ_E_INVALID, "hqq_b200_glue_silu_mul: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)cdiv(n, 256));
+  if (dtype == HQQ_F16) return launch_pdl("silu_mul", silu_mul_kernel<__half>, grid, dim3(256), 0, st, (const __half*)gate, (const __half*)up, (__half*)y, n);
+  if (dtype == HQQ_BF16) return launch_pdl("silu_mul", silu_mul_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)y, n);
+  set_error("hqq_b200_glue_silu_mul: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v, const void* cos_table, const void* sin_table,
+                                              void* k_cache, void* v_cache, const int64_t* pos, void* out, int n_q_heads, int n_kv_heads,
+                                              int cache_len, int head_dim, int dtype, void* stream) {
+  HQQ_REQUIRE(q && k && v && cos_table && sin_table && k_cache && v_cache && pos && out, HQQ_E_INVALID, "hqq_b200_glue_rope_attn_decode: null pointer");
+  HQQ_REQUIRE(head_dim == 128 && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && cache_len > 0 && cache_len <= 8192, HQQ_E_UNSUPPORTED,
+              "hqq_b200_glue_rope_attn_decode: needs head_dim 128, cache_len <= 8192");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (2 * head_dim + cache_len + 32) * sizeof(float);
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  if (dtype == HQQ_F16)
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads), dim3(head_dim), smem, st, (const __half*)q, (const __half*)k,
+                      (const __half*)v, (const __half*)cos_table, (const __half*)sin_table, (__half*)k_cache, (__half*)v_cache, (const long long*)pos,
+                      (__half*)out, n_q_heads, n_kv_heads, cache_len, head_dim, scale);
+  if (dtype == HQQ_BF16)
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads), dim3(head_dim), smem, st, (const __nv_bfloat16*)q,
+                      (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
+                      (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, (const long long*)pos, (__nv_bfloat16*)out, n_q_heads, n_kv_heads, cache_len,
+                      head_dim, scale);
+  set_error("hqq_b200_glue_rope_attn_decode: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {
+  HQQ_REQUIRE(logits && out && n > 0, HQQ_E_INVALID, "hqq_b200_glue_argmax: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(1), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(1), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out);
+  set_error("hqq_b200_glue_argmax: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}

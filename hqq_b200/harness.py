@@ -59,8 +59,9 @@ def shard_dims(shape: LlamaShape, tp: int):
 class DecodeModel:
     def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
                  device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
-                 n_layers: int | None = None):
+                 n_layers: int | None = None, fused: bool = True):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
+        self.fused = fused
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
         self.n_layers = n_layers if n_layers is not None else shape.n_layers
@@ -152,19 +153,57 @@ class DecodeModel:
         self.next_tok.copy_(torch.argmax(logits, dim=-1))
         self.pos.add_(1).remainder_(self.cache_len)
 
+    def step_fused(self):
+        """Same token step with the package's glue kernels (8 launches per block): add+RMSNorm, fused q/k/v, RoPE+cache+
+        attention, o, add+RMSNorm, fused gate/up, SiLU*mul, down.  Single GPU only."""
+        from ._lib import DTYPE_CODE, check, load, ptr, stream_ptr
+        lib, s = load(), self.shape
+        st = stream_ptr(self.device)
+        code = DTYPE_CODE[self.dtype]
+        hd, hq, hkv = s.head_dim, s.n_heads, s.n_kv_heads
+        b = self._bufs
+        torch.index_select(self.embed, 0, self.tok, out=b["h"])
+        delta = None
+        for blk in self.blocks:
+            check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(blk["norm1"]), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+            ops.linear_fwd_multi(b["x"], (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]])
+            check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
+                                                     ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
+            ops.linear_fwd_multi(b["a"], (blk["o"],), [b["o"]])
+            check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(b["o"]), ptr(blk["norm2"]), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+            ops.linear_fwd_multi(b["x"], (blk["gate"], blk["up"]), [b["gate"], b["up"]])
+            check(lib.hqq_b200_glue_silu_mul(ptr(b["gate"]), ptr(b["up"]), ptr(b["act"]), s.inter, code, st))
+            ops.linear_fwd_multi(b["act"], (blk["down"],), [b["down"]])
+            delta = b["down"]
+        check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+        torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
+        check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
+        self.pos.add_(1).remainder_(self.cache_len)
+
+    def _alloc_bufs(self):
+        s, dev, dt = self.shape, self.device, self.dtype
+        z = lambda n: torch.zeros(1, n, device=dev, dtype=dt)
+        self._bufs = {"h": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads * s.head_dim), "k": z(s.n_kv_heads * s.head_dim),
+                      "v": z(s.n_kv_heads * s.head_dim), "a": z(s.n_heads * s.head_dim), "o": z(s.hidden), "gate": z(s.inter),
+                      "up": z(s.inter), "act": z(s.inter), "down": z(s.hidden), "logits": z(s.vocab)}
+
     def capture(self, warmup: int = 3):
         """Warm up on a side stream, then capture one decode step into a CUDA graph."""
+        fused = self.fused and self.tp == 1
+        if fused and not hasattr(self, "_bufs"):
+            self._alloc_bufs()
+        step = self.step_fused if fused else self.step
         st = torch.cuda.Stream(device=self.device)
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st), torch.no_grad():
             for _ in range(warmup):
-                self.step()
+                step()
         torch.cuda.current_stream(self.device).wait_stream(st)
         torch.cuda.synchronize(self.device)
         self.pos.zero_()
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.step()
+            step()
         return self.graph
 
     def decode(self, feed_back: bool = True):

@@ -142,6 +142,28 @@ int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, 
 int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits,
                               int axis, int dtype);
 
+/* ---------------------------------------------------------------------------------------
+ * Decode-harness glue (the CALLER of HQQLinear.forward -- not part of the
+ * hot path and with no counterpart inside hqq/core): the handful of tiny batch-1 ops between
+ * the fused linears of a Llama-style block, so that one decoded token is 8 launches per
+ * block (hqq/utils/generation_hf.py:270-289 leaves these to HF transformers + torch.compile).
+ * fp16/bf16 only; every kernel is launched with programmatic dependent launch.
+ * ------------------------------------------------------------------------------------- */
+/* h += delta (delta may be NULL);  y = rmsnorm(h) * weight          (one token, H <= 8192) */
+int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y,
+                              int H, float eps, int dtype, void* stream);
+/* y = silu(gate) * up */
+int hqq_b200_glue_silu_mul(const void* gate, const void* up, void* y, int n, int dtype, void* stream);
+/* RoPE(q,k at *pos) + KV-cache append + one-token GQA attention over cache[0..*pos];
+ * caches [n_kv_heads, cache_len, head_dim], cos/sin tables [cache_len, head_dim], pos on device */
+int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v,
+                                   const void* cos_table, const void* sin_table,
+                                   void* k_cache, void* v_cache, const int64_t* pos, void* out,
+                                   int n_q_heads, int n_kv_heads, int cache_len, int head_dim,
+                                   int dtype, void* stream);
+/* out[0] = argmax(logits[0..n)) (first index on ties) */
+int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (used by bench.py for its gpu_launches claim).                                        */
 int64_t hqq_b200_launch_count(void);

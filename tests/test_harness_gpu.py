@@ -1,0 +1,77 @@
+"""GPU: the decode harness -- glue kernels vs the same ops in PyTorch, and the captured graph."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hqq_b200 import harness
+from hqq_b200._lib import DTYPE_CODE, check, load, ptr, stream_ptr
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_glue_kernels_match_torch_ops(dt):
+    lib = load()
+    st = stream_ptr(DEV)
+    code = DTYPE_CODE[dt]
+    torch.manual_seed(0)
+    H = 4096
+    h = torch.randn(1, H, device=DEV).to(dt); d = torch.randn(1, H, device=DEV).to(dt); w = torch.rand(H, device=DEV).to(dt)
+    h2 = h.clone(); y = torch.empty_like(h)
+    check(lib.hqq_b200_glue_add_rmsnorm(ptr(h2), ptr(d), ptr(w), ptr(y), H, 1e-5, code, st))
+    ref_h = h + d
+    assert torch.equal(h2, ref_h)
+    ref = F.rms_norm(ref_h, (H,), w, 1e-5)
+    assert torch.allclose(y.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    g = torch.randn(1, 14336, device=DEV).to(dt); u = torch.randn(1, 14336, device=DEV).to(dt); o = torch.empty_like(g)
+    check(lib.hqq_b200_glue_silu_mul(ptr(g), ptr(u), ptr(o), 14336, code, st))
+    assert torch.allclose(o.float(), (F.silu(g) * u).float(), rtol=2e-2, atol=2e-2)
+    lg = torch.randn(1, 128256, device=DEV).to(dt); out = torch.zeros(1, dtype=torch.long, device=DEV)
+    check(lib.hqq_b200_glue_argmax(ptr(lg), 128256, ptr(out), code, st))
+    assert int(out) == int(torch.argmax(lg.float(), dim=-1))
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_rope_attention_kernel(dt):
+    lib = load()
+    st, code = stream_ptr(DEV), DTYPE_CODE[dt]
+    torch.manual_seed(1)
+    hq, hkv, hd, L = 8, 2, 128, 64
+    m = harness.DecodeModel(harness.LlamaShape(hidden=hq * hd, inter=1024, n_layers=0, n_heads=hq, n_kv_heads=hkv, vocab=256), dtype=dt, device=DEV,
+                            cache_len=L)
+    kc = torch.randn(hkv, L, hd, device=DEV).to(dt); vc = torch.randn(hkv, L, hd, device=DEV).to(dt)
+    for pos in (0, 1, 37, 63):
+        q = torch.randn(1, hq * hd, device=DEV).to(dt); k = torch.randn(1, hkv * hd, device=DEV).to(dt); v = torch.randn(1, hkv * hd, device=DEV).to(dt)
+        kc1, vc1 = kc.clone(), vc.clone()
+        p = torch.tensor([pos], device=DEV)
+        out = torch.empty(1, hq * hd, device=DEV, dtype=dt)
+        check(lib.hqq_b200_glue_rope_attn_decode(ptr(q), ptr(k), ptr(v), ptr(m.cos), ptr(m.sin), ptr(kc1), ptr(vc1), ptr(p), ptr(out), hq, hkv, L, hd, code, st))
+        cos, sin = m.cos[pos].view(1, 1, hd), m.sin[pos].view(1, 1, hd)
+        qr, kr = m._rope(q.view(1, hq, hd), cos, sin), m._rope(k.view(1, hkv, hd), cos, sin)
+        kc2, vc2 = kc.clone(), vc.clone()
+        kc2[:, pos] = kr[0]; vc2[:, pos] = v.view(hkv, hd)
+        assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+        mask = (torch.arange(L, device=DEV) <= pos).view(1, 1, 1, L)
+        ref = F.scaled_dot_product_attention(qr.view(1, hq, 1, hd).float(), kc2[None].float(), vc2[None].float(), attn_mask=mask, enable_gqa=True)
+        assert torch.allclose(out.float().view(hq, hd), ref.view(hq, hd), rtol=3e-2, atol=3e-2), pos
+
+
+def test_decode_graph_fused_equals_framework_ops():
+    """A tiny 2-block model: the captured fused step (8 launches/block) and the PyTorch-op step produce the same tokens."""
+    torch.manual_seed(0)
+    shape = harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)
+    a = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=True, seed=3)
+    b = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=False, seed=3)
+    a.capture(); b.capture()
+    for m in (a, b):
+        m.tok.fill_(5); m.pos.zero_()
+        for blk in m.blocks:
+            blk["k_cache"].zero_(); blk["v_cache"].zero_()
+    ta, tb = [], []
+    for _ in range(12):
+        a.decode(); b.decode()
+        ta.append(int(a.next_tok)); tb.append(int(b.next_tok))
+    agree = sum(int(x == y) for x, y in zip(ta, tb))
+    assert agree >= 10, (ta, tb)  # fp16 reorderings may flip a near-tie late in the sequence, never the early tokens
+    assert ta[:4] == tb[:4]
