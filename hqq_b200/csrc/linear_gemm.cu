@@ -1,11 +1,434 @@
-// tcgen05 / TMA fused dequant-GEMM (large M).  Placeholder until the kernel lands: nothing routes here.
+// HQQLinear.forward for large M (prefill / batched decode): fused unpack -> group-dequant -> tcgen05 GEMM.
+//
+//   y[M,N] = x[M,K] @ dequantize(W_q)^T (+bias)          reference: hqq/core/quantize.py:184-199, 880-898
+//
+// One CTA computes a [128 weight rows] x [UN tokens] output tile, accumulated in TMEM (fp32) by tcgen05.mma:
+//   A operand (M=128 of the UMMA) = the weight tile.  The packed bytes keep the reference's slab layout (bitpack.py),
+//       so 128/F packed rows x F slabs give 128 output rows.  Eight "dequant" warps stream the packed bytes from HBM
+//       (read exactly once per token tile), expand them in registers with the reference's two roundings
+//       W_r = fl(fl(q - z) * s) (bit-identical to Quantizer.dequantize) and store the fp16/bf16 tile into shared memory
+//       in the K-major SWIZZLE_128B layout the tensor core reads.  The dequantised matrix never exists in HBM.
+//   B operand (N=UN of the UMMA) = the activation tile [UN tokens x 64 k], fetched by TMA (cp.async.bulk.tensor, 128B
+//       swizzle, out-of-range tokens zero-filled by the hardware).
+//   4-stage mbarrier ring: TMA warp / dequant warps fill, one elected thread issues the MMAs, tcgen05.commit frees the
+//   stage.  Epilogue: the dequant warps read the accumulator with tcgen05.ld (lane = weight row, column = token), add
+//   the bias and store y (32 consecutive n per token -> coalesced).
+// sm_100a only: tcgen05 / TMEM / TMA, no mma.sync fallback.
+#include <cuda.h>  // CUtensorMap types only; the encode entry point is resolved through the runtime (no -lcuda)
+
 #include "common.cuh"
+
 namespace hqq {
-bool gemm_route_ok(int64_t, int64_t, int64_t, int, int, int, int) { return false; }
-size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
-int linear_gemm(const void*, const void*, const void*, const void*, const void*, void*, int64_t, int64_t, int64_t, int, int, int, void*,
-                size_t, cudaStream_t) {
-  set_error("hqq_b200_linear_fwd: tcgen05 GEMM path not built");
+
+namespace gemm {
+
+constexpr int kStages = 4;
+constexpr int kBlockK = 64;          // k elements per stage = one 128-byte swizzle row
+constexpr int kTileRows = 128;       // weight rows per CTA = UMMA M
+constexpr int kDequantThreads = 256;
+constexpr int kThreads = 64 + kDequantThreads;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2..9: dequant + epilogue
+
+struct Args {
+  const uint8_t* Wq;
+  const void* scale;
+  const void* zero;
+  const void* bias;
+  void* y;
+  int M, N, K;
+  int step;  // packed rows = N / F
+  int Gk;    // groups per row = K / GS
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_in_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
+// leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte offset = 1024 B between 8-row groups in
+// [32,46), descriptor version 1 (Blackwell) in [46,48), layout type 2 = SWIZZLE_128B in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D = F32, A/B = F16 or BF16, both K-major, M = 128, N = UN.
+template <typename T>
+__device__ __forceinline__ uint32_t make_idesc(int UN) {
+  const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32
+  d |= fmt << 7;                     // a_format
+  d |= fmt << 10;                    // b_format
+  d |= (uint32_t)(UN >> 3) << 17;    // n_dim
+  d |= (uint32_t)(128 >> 4) << 24;   // m_dim
+  return d;
+}
+
+// ---- level -> T with the reference's roundings -------------------------------------------------------------------
+// Two k-adjacent levels (bytes b0, b1 already masked to the field) -> T2 {fl(fl(q0 - z) * s), fl(fl(q1 - z) * s)}.
+template <typename T> struct Pair;
+template <> struct Pair<__half> {
+  using T2 = __half2;
+  __device__ __forceinline__ static uint32_t deq(uint32_t q0, uint32_t q1, __half2 z2, __half2 s2) {
+    // 0x6400 | q == 1024 + q exactly; subtracting 1024 is exact, so (q - z) and (.. * s) round exactly like the reference
+    const uint32_t v = 0x64006400u | q0 | (q1 << 16);
+    __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+    h = __hmul2(__hsub2(h, z2), s2);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static __half2 bcast(__half v) { return __half2half2(v); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  __device__ __forceinline__ static uint32_t deq(uint32_t q0, uint32_t q1, __nv_bfloat162 z2, __nv_bfloat162 s2) {
+    __nv_bfloat162 h = __halves2bfloat162(__ushort2bfloat16_rn((unsigned short)q0), __ushort2bfloat16_rn((unsigned short)q1));
+    h = __hmul2(__hsub2(h, z2), s2);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static __nv_bfloat162 bcast(__nv_bfloat16 v) { return __bfloat162bfloat162(v); }
+};
+
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <int UN>
+struct Smem {
+  static constexpr int A_STAGE = kTileRows * 128;  // 128 rows x 128 B
+  static constexpr int B_STAGE = UN * 128;
+  static constexpr int BYTES = kStages * (A_STAGE + B_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <typename T, int NBITS, int GS, int UN>
+__global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  constexpr int F = 8 / NBITS;             // slabs per byte
+  constexpr int PR = kTileRows / F;        // packed rows per tile
+  constexpr int BPT = 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
+  constexpr int TPR = 64 / BPT;            // dequant threads per packed row
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = Smem<UN>;
+  using P2 = Pair<T>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * S::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (S::A_STAGE + S::B_STAGE));
+  uint64_t* full_a = bars;                 // [kStages] dequant warps -> MMA (256 arrivals)
+  uint64_t* full_b = bars + kStages;       // [kStages] TMA -> MMA (1 arrival + tx bytes)
+  uint64_t* empty = bars + 2 * kStages;    // [kStages] MMA (tcgen05.commit) -> producers
+  uint64_t* accum_full = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int prow0 = tile_n * PR;           // first packed row of the tile
+  const int m0 = tile_m * UN;
+  const int num_kb = a.K / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    __syncwarp();
+    tmem_alloc<UN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: activation tiles =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], S::B_STAGE);
+        tma_load_2d(sB + s * S::B_STAGE, &xmap, &full_b[s], kb * kBlockK, m0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    const uint32_t idesc = make_idesc<T>(UN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full_a[s], ph);
+      mbar_wait(&full_b[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_desc_sw128(smem_u32(sA + s * S::A_STAGE));
+        const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * S::B_STAGE));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(&empty[s]);                          // frees the stage when these MMAs have read it
+        if (kb == num_kb - 1) tc_commit(accum_full);   // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
+    const int td = threadIdx.x - 64;
+    const int pr = td / TPR, c = td % TPR;
+    const bool row_ok = (prow0 + pr) < a.step;
+    const uint8_t* wp = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
+    const T* sc = reinterpret_cast<const T*>(a.scale);
+    const T* ze = reinterpret_cast<const T*>(a.zero);
+    long long meta_row[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) meta_row[f] = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+
+    uint32_t wcur[BPT / 4], wnxt[BPT / 4];
+    auto load_w = [&](int kb, uint32_t (&w)[BPT / 4]) {
+      const uint8_t* p = wp + (long long)kb * kBlockK;
+      if constexpr (BPT == 32) { const uint4 v0 = ldg_stream_v4(p), v1 = ldg_stream_v4(p + 16); w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; }
+      else if constexpr (BPT == 16) { const uint4 v = ldg_stream_v4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      else if constexpr (BPT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+      else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    load_w(0, wnxt);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+#pragma unroll
+      for (int i = 0; i < BPT / 4; ++i) wcur[i] = wnxt[i];
+      if (kb + 1 < num_kb) load_w(kb + 1, wnxt);
+      const int g = (kb * kBlockK) / GS;
+      typename P2::T2 s2[F], z2[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) { s2[f] = P2::bcast(sc[meta_row[f] + g]); z2[f] = P2::bcast(ze[meta_row[f] + g]); }
+      mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+      uint8_t* stage = sA + s * S::A_STAGE;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const int row = f * PR + pr;
+        const int sh = 8 - NBITS * (f + 1);
+        uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
+#pragma unroll
+        for (int i = 0; i < BPT / 4; ++i) {
+          const uint32_t t = (wcur[i] >> sh) & (MASK * 0x01010101u);
+          out[2 * i] = P2::deq(t & 0xFFu, (t >> 8) & 0xFFu, z2[f], s2[f]);
+          out[2 * i + 1] = P2::deq((t >> 16) & 0xFFu, (t >> 24) & 0xFFu, z2[f], s2[f]);
+        }
+        // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
+        uint8_t* rowp = stage + row * 128;
+        if constexpr (BPT >= 8) {
+#pragma unroll
+          for (int ch = 0; ch < BPT / 8; ++ch) {
+            const int chunk = c * (BPT / 8) + ch;
+            *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = make_uint4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
+          }
+        } else {  // BPT == 4: half a chunk
+          const int chunk = c >> 1;
+          *reinterpret_cast<uint2*>(rowp + ((chunk ^ (row & 7)) << 4) + (c & 1) * 8) = make_uint2(out[0], out[1]);
+        }
+      }
+      fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
+      mbar_arrive(&full_a[s]);
+    }
+
+    // ================= epilogue: TMEM -> registers -> y =================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 2) >> 2;             // two warps share a quarter: split the token columns
+    const int t = quarter * 32 + lane;            // tile row = weight row inside the tile
+    const int tf = t / PR, tp = t % PR;
+    const bool n_ok = (prow0 + tp) < a.step;
+    const int n = tf * a.step + prow0 + tp;
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const bool has_bias = bias != nullptr;
+    T bn = cvt_out<T>(0.0f);
+    if (has_bias && n_ok) bn = bias[n];
+#pragma unroll 1
+    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + col + j;
+        if (n_ok && m < a.M) {
+          T o = cvt_out<T>(__uint_as_float(v[j]));
+          if (has_bias) o = __hadd(o, bn);  // out += bias: second rounding, as in the reference
+          y[(long long)m * a.N + n] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<UN>(tmem_base);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <typename T, int NBITS, int GS, int UN>
+static int launch(const void* x, const Args& a, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  HQQ_REQUIRE(enc != nullptr, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap xmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+  const cuuint64_t strides[1] = {(cuuint64_t)a.K * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)UN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(&xmap, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HQQ_REQUIRE(r == CUDA_SUCCESS, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  auto k = linear_gemm_kernel<T, NBITS, GS, UN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<UN>::BYTES);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem<UN>::BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  constexpr int PR = kTileRows / (8 / NBITS);
+  const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, UN));
+  k<<<grid, kThreads, Smem<UN>::BYTES, st>>>(xmap, a);
+  HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
+  return HQQ_OK;
+}
+
+template <typename T, int NBITS, int GS>
+static int by_un(const void* x, const Args& a, cudaStream_t st) {
+  if (a.M <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
+  if (a.M <= 128) return launch<T, NBITS, GS, 128>(x, a, st);
+  return launch<T, NBITS, GS, 256>(x, a, st);
+}
+
+template <typename T, int NBITS>
+static int by_gs(const void* x, const Args& a, int gs, cudaStream_t st) {
+  if (gs == 64) return by_un<T, NBITS, 64>(x, a, st);
+  return by_un<T, NBITS, 128>(x, a, st);
+}
+
+template <typename T>
+static int by_bits(const void* x, const Args& a, int gs, int nbits, cudaStream_t st) {
+  switch (nbits) {
+    case 8: return by_gs<T, 8>(x, a, gs, st);
+    case 4: return by_gs<T, 4>(x, a, gs, st);
+    case 2: return by_gs<T, 2>(x, a, gs, st);
+    case 1: return by_gs<T, 1>(x, a, gs, st);
+  }
   return HQQ_E_UNSUPPORTED;
 }
+
+}  // namespace gemm
+
+bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype) {
+  if (axis != 1) return false;
+  if (dtype != HQQ_F16 && dtype != HQQ_BF16) return false;
+  if (!(nbits == 8 || nbits == 4 || nbits == 2 || nbits == 1)) return false;
+  if (!(gs == 64 || gs == 128)) return false;     // one 64-k stage never straddles a group
+  if (M < 1 || K % 64 != 0 || K % gs != 0) return false;
+  if (N % (8 / nbits) != 0) return false;
+  if (K % 8 != 0 || N > (1 << 28) || K > (1 << 28) || M > (1 << 28)) return false;
+  return true;
+}
+
+size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+
+int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M, int64_t N,
+                int64_t K, int gs, int nbits, int dtype, void*, size_t, cudaStream_t st) {
+  HQQ_REQUIRE(aligned(x, 16) && aligned(Wq, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x and W_q must be 16-byte aligned");
+  gemm::Args a;
+  a.Wq = (const uint8_t*)Wq; a.scale = scale; a.zero = zero; a.bias = bias; a.y = y;
+  a.M = (int)M; a.N = (int)N; a.K = (int)K;
+  a.step = (int)(N / (8 / nbits));
+  a.Gk = (int)(K / gs);
+  if (dtype == HQQ_F16) return gemm::by_bits<__half>(x, a, gs, nbits, st);
+  return gemm::by_bits<__nv_bfloat16>(x, a, gs, nbits, st);
+}
+
 }  // namespace hqq

@@ -81,6 +81,42 @@ def test_small_m_kernel_vs_oracle(oracle, nbits, dtype, gs):
         assert rel(y.float().cpu().numpy(), ref) <= TOL[dtype], (M, use_bias)
 
 
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("gs", [64, 128])
+def test_tcgen05_gemm_vs_oracle(oracle, nbits, dtype, gs):
+    """The tcgen05/TMA kernel (route 2): every bit width, both group sizes, token counts that exercise every UMMA N
+    (64/128/256), partial token tiles, ragged weight tiles, K not a multiple of 256, bias."""
+    rng = np.random.RandomState(7 * nbits + gs)
+    f = 8 // nbits
+    N, K = 40 * f, 384  # 40 packed rows: partial 128-row tile for every bit width; K = 6 k-blocks (not a multiple of 256)
+    W_q, scale, zero = _random_layer(rng, N, K, nbits, gs, oracle)
+    bias = rng.randn(N).astype(np.float32)
+    meta_o = {"nbits": nbits, "group_size": gs, "shape": (N, K), "axis": 1, "packing": oracle.BIT_TO_PACKING[nbits], "scale": scale, "zero": zero}
+    for M, use_bias in [(33, False), (64, True), (100, False), (129, True), (300, False)]:
+        assert ops.linear_route(M, N, K, gs, nbits, 1, DT[dtype]) == 2
+        x = rng.randn(M, K).astype(np.float32)
+        layer = make_layer(W_q, scale, zero, (N, K), nbits, gs, 1, DT[dtype], bias if use_bias else None)
+        y = layer(torch.from_numpy(x).to(DEV).to(DT[dtype]))
+        ref = oracle.linear_forward(x, W_q, meta_o, bias if use_bias else None, dtype)
+        assert rel(y.float().cpu().numpy(), ref) <= TOL[dtype], (M, use_bias)
+
+
+@pytest.mark.parametrize("N,K,M", [(4096, 4096, 4096), (11008, 4096, 1024), (4096, 11008, 512), (14336, 4096, 64), (4096, 4096, 33)])
+def test_tcgen05_gemm_full_size(N, K, M):
+    """BASELINE sweep sizes: the fused GEMM against an fp32 GEMM over the (bit-exactly tested) dequantised matrix.  The A
+    operand the tensor core sees is bit-identical to Quantizer.dequantize, so only the accumulation order differs."""
+    torch.manual_seed(N + K + M)
+    W = (torch.randn(N, K, device=DEV) * 0.02).half()
+    layer = HQQLinear.from_weights(W, None, BaseQuantizeConfig(nbits=4, group_size=64, axis=1), compute_dtype=torch.float16, device=DEV)
+    assert ops.linear_route(M, N, K, 64, 4, 1, torch.float16) == 2
+    x = torch.randn(M, K, device=DEV).half()
+    y = layer(x).float()
+    ref = x.float() @ layer.dequantize().float().t()
+    assert (y - ref).norm() / ref.norm() <= 5e-4
+    assert torch.equal(layer(x), layer(x))
+
+
 @pytest.mark.parametrize("N,K", [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (11008, 4096)])
 def test_llama_shapes_vs_dequant_gemm(N, K):
     """BASELINE sizes (Llama-3-8B / Llama-2-7B linears), 4-bit gs=64, M=1 and M=16: fused kernel vs fp32 GEMM over the
