@@ -155,12 +155,14 @@ class DecodeModel:
 
     def step_fused(self):
         """Same token step with the package's glue kernels (8 launches per block): add+RMSNorm, fused q/k/v, RoPE+cache+
-        attention, o, add+RMSNorm, fused gate/up, SiLU*mul, down.  Single GPU only."""
+        attention, o, add+RMSNorm, fused gate/up, SiLU*mul, down.  With tensor parallelism every rank runs the same launches
+        on its shard (heads / inter split tp ways) and the two row-parallel outputs are summed with one all-reduce each."""
         from ._lib import DTYPE_CODE, check, load, ptr, stream_ptr
         lib, s = load(), self.shape
         st = stream_ptr(self.device)
         code = DTYPE_CODE[self.dtype]
-        hd, hq, hkv = s.head_dim, s.n_heads, s.n_kv_heads
+        hd, hq, hkv = s.head_dim, s.n_heads // self.tp, s.n_kv_heads // self.tp
+        inter = s.inter // self.tp
         b = self._bufs
         torch.index_select(self.embed, 0, self.tok, out=b["h"])
         delta = None
@@ -170,10 +172,14 @@ class DecodeModel:
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
             ops.linear_fwd_multi(b["a"], (blk["o"],), [b["o"]])
+            if self.tp > 1:
+                torch.distributed.all_reduce(b["o"], group=self.pg)
             check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(b["o"]), ptr(blk["norm2"]), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
             ops.linear_fwd_multi(b["x"], (blk["gate"], blk["up"]), [b["gate"], b["up"]])
-            check(lib.hqq_b200_glue_silu_mul(ptr(b["gate"]), ptr(b["up"]), ptr(b["act"]), s.inter, code, st))
+            check(lib.hqq_b200_glue_silu_mul(ptr(b["gate"]), ptr(b["up"]), ptr(b["act"]), inter, code, st))
             ops.linear_fwd_multi(b["act"], (blk["down"],), [b["down"]])
+            if self.tp > 1:
+                torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
         check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
@@ -183,13 +189,14 @@ class DecodeModel:
     def _alloc_bufs(self):
         s, dev, dt = self.shape, self.device, self.dtype
         z = lambda n: torch.zeros(1, n, device=dev, dtype=dt)
-        self._bufs = {"h": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads * s.head_dim), "k": z(s.n_kv_heads * s.head_dim),
-                      "v": z(s.n_kv_heads * s.head_dim), "a": z(s.n_heads * s.head_dim), "o": z(s.hidden), "gate": z(s.inter),
-                      "up": z(s.inter), "act": z(s.inter), "down": z(s.hidden), "logits": z(s.vocab)}
+        tp = self.tp
+        self._bufs = {"h": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads // tp * s.head_dim), "k": z(s.n_kv_heads // tp * s.head_dim),
+                      "v": z(s.n_kv_heads // tp * s.head_dim), "a": z(s.n_heads // tp * s.head_dim), "o": z(s.hidden),
+                      "gate": z(s.inter // tp), "up": z(s.inter // tp), "act": z(s.inter // tp), "down": z(s.hidden), "logits": z(s.vocab)}
 
     def capture(self, warmup: int = 3):
         """Warm up on a side stream, then capture one decode step into a CUDA graph."""
-        fused = self.fused and self.tp == 1
+        fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
         step = self.step_fused if fused else self.step

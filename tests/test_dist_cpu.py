@@ -1,0 +1,70 @@
+"""CPU, world_size 2, gloo: the multi-GPU host logic of the decode harness / bench -- shard shapes,
+the column-/row-parallel algebra with its single all-reduce, and the max-over-ranks timing reduction bench.py uses."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hqq_b200 import harness
+
+
+def test_shard_dims():
+    d = harness.shard_dims(harness.LLAMA3_8B, 1)
+    assert d["q"] == (4096, 4096) and d["k"] == (1024, 4096) and d["gate"] == (14336, 4096) and d["down"] == (4096, 14336)
+    d8 = harness.shard_dims(harness.LLAMA3_8B, 8)
+    assert d8["q"] == (512, 4096) and d8["k"] == (128, 4096) and d8["o"] == (4096, 512) and d8["down"] == (4096, 1792)
+    # every K handed to a row-parallel shard stays a multiple of the group size and of the 256-k unit of the fused kernel
+    for tp in (1, 2, 4, 8):
+        for name, (n, k) in harness.shard_dims(harness.LLAMA3_8B, tp).items():
+            assert k % 64 == 0 and n % 8 == 0, (tp, name)
+    d70 = harness.shard_dims(harness.LLAMA3_70B, 8)
+    assert d70["down"] == (8192, 3584) and d70["gate"] == (3584, 8192)
+    with pytest.raises(ValueError):
+        harness.shard_dims(harness.LLAMA3_8B, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # identical "unsharded" tensors on every rank
+    H, I, = 64, 256
+    x = torch.randn(1, H)
+    Wg, Wu, Wd = torch.randn(I, H), torch.randn(I, H), torch.randn(H, I)
+    full = (torch.nn.functional.silu(x @ Wg.t()) * (x @ Wu.t())) @ Wd.t()
+    sl = slice(rank * I // world, (rank + 1) * I // world)
+    # column-parallel gate/up: no traffic; row-parallel down: ONE all-reduce of the [1, hidden] partial
+    part = (torch.nn.functional.silu(x @ Wg[sl].t()) * (x @ Wu[sl].t())) @ Wd[:, sl].t()
+    dist.all_reduce(part)
+    ok = torch.allclose(part, full, rtol=1e-4, atol=1e-4)
+    # bench.py: time = max over ranks
+    t = torch.tensor([10.0 + rank, 5.0 - rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = ok and t.tolist() == [10.0 + world - 1, 5.0]
+    dist.barrier()
+    if rank == 0:
+        out.put(ok)
+    dist.destroy_process_group()
+
+
+def test_row_parallel_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
