@@ -287,7 +287,12 @@ def run_gpu(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without touching NCCL again: destroying a process group while captured graphs still hold its kernels
+        # can hang.  Everything is measured and printed; leave through the fast exit on every rank.
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
