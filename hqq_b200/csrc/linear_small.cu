@@ -225,7 +225,7 @@ struct SKCfg {
   static constexpr int NWV = (F == 1) ? 8 : 4;   // 16-byte weight vectors per thread and unit
   static constexpr int ST = (F == 1) ? 2 : 4;    // ring stages
   static constexpr int W_BYTES = ST * NWV * 256 * 16;
-  static constexpr int M_BYTES = ST * 4 * 256 * MB;
+  static constexpr int M_BYTES = 0;                     // scale/zero travel through registers
   static constexpr int P_BYTES = 2 * 8 * MT * 128 * 4;  // double-buffered split-K partials, one 16x8 tile per warp
   static constexpr int SMEM = W_BYTES + M_BYTES + P_BYTES;
   static constexpr int MIN_CTAS = (SMEM <= 110 * 1024 && MT <= 2) ? 2 : 1;
@@ -239,11 +239,10 @@ struct SKCfg {
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
 __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS) linear_small_kernel(const __grid_constant__ SKArgs a) {
   using C = SKCfg<T, NBITS, GS, MT, MAGIC>;
-  constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, MB = C::MB, NWV = C::NWV, ST = C::ST;
+  constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, NWV = C::NWV, ST = C::ST;
   using MM = MT16<T>;
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* wring = reinterpret_cast<uint4*>(smem);                             // [ST][NWV][256] one 16-byte slot per thread
-  uint8_t* mring = smem + C::W_BYTES;                                        // [ST][4][256][MB]
   float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);  // [2][8][MT][128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -280,21 +279,46 @@ __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS)
   // ---- issue cursor -------------------------------------------------------------------------------------------
   int i_tile = 0, i_k = 0;  // index into this CTA's tile list / unit within the warp's chunk
   const uint8_t *iw_a, *iw_b;
-  const T *is_a, *iz_a, *is_b, *iz_b;
   auto issue_setup = [&]() {
     Tile t; locate((int)blockIdx.x + i_tile * (int)gridDim.x, t);
     const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
     const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
     // rows past the ragged edge re-read row 0 (always mapped); their results are never stored
     const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
-    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
     iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
     iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
-    is_a = t.scale + na * a.Gk + kb0 * GPB; iz_a = t.zero + na * a.Gk + kb0 * GPB;
-    is_b = t.scale + nb * a.Gk + kb0 * GPB; iz_b = t.zero + nb * a.Gk + kb0 * GPB;
   };
   int to_issue = n_tiles * upt;
   if (to_issue > 0) issue_setup();
+  // ---- meta cursor: scale/zero of the NEXT unit travel through registers (plain cached loads, one unit ahead).  They
+  // used to ride the cp.async ring, but 8-byte cp.async costs one shared-memory wavefront per lane (ncu: 60 % of all
+  // shared wavefronts of the kernel).
+  int m_tile = 0, m_k = 0, m_left = n_tiles * upt;
+  const T *ms_a = nullptr, *mz_a = nullptr, *ms_b = nullptr, *mz_b = nullptr;
+  auto meta_setup = [&]() {
+    const int gt = (int)blockIdx.x + m_tile * (int)gridDim.x;
+    Tile t; locate(gt, t);
+    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
+    ms_a = t.scale + na * a.Gk + kb0 * GPB; mz_a = t.zero + na * a.Gk + kb0 * GPB;
+    ms_b = t.scale + nb * a.Gk + kb0 * GPB; mz_b = t.zero + nb * a.Gk + kb0 * GPB;
+  };
+  if (m_left > 0) meta_setup();
+  Vec<T, GPB> mv[4];
+  auto meta_fetch = [&]() {
+    if (m_left > 0) {
+      mv[0] = *reinterpret_cast<const Vec<T, GPB>*>(ms_a); mv[1] = *reinterpret_cast<const Vec<T, GPB>*>(mz_a);
+      mv[2] = *reinterpret_cast<const Vec<T, GPB>*>(ms_b); mv[3] = *reinterpret_cast<const Vec<T, GPB>*>(mz_b);
+      --m_left;
+      if (++m_k == upt) {
+        m_k = 0; ++m_tile;
+        if (m_left > 0) meta_setup();
+      } else {
+        ms_a += GPB; mz_a += GPB; ms_b += GPB; mz_b += GPB;
+      }
+    }
+  };
+  meta_fetch();
   auto issue = [&](int stage) {
     if (to_issue > 0) {
 #pragma unroll
@@ -303,16 +327,12 @@ __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS)
 #pragma unroll
         for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
       }
-      cp_async_small<MB>(mring + ((stage * 4 + 0) * 256 + tid) * MB, is_a);
-      cp_async_small<MB>(mring + ((stage * 4 + 1) * 256 + tid) * MB, iz_a);
-      cp_async_small<MB>(mring + ((stage * 4 + 2) * 256 + tid) * MB, is_b);
-      cp_async_small<MB>(mring + ((stage * 4 + 3) * 256 + tid) * MB, iz_b);
       --to_issue;
       if (++i_k == upt) {
         i_k = 0; ++i_tile;
         if (to_issue > 0) issue_setup();
       } else {
-        iw_a += 256; iw_b += 256; is_a += GPB; iz_a += GPB; is_b += GPB; iz_b += GPB;
+        iw_a += 256; iw_b += 256;
       }
     }
     cp_async_commit();  // always commit (possibly empty) so the group count per iteration is uniform
@@ -360,14 +380,9 @@ __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS)
       cp_async_wait<ST - 1>();  // the group of this unit (and everything older) has landed in this thread's slots
 
       float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
-      {
-        const Vec<T, GPB> v0 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 0) * 256 + tid) * MB);
-        const Vec<T, GPB> v1 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 1) * 256 + tid) * MB);
-        const Vec<T, GPB> v2 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 2) * 256 + tid) * MB);
-        const Vec<T, GPB> v3 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 3) * 256 + tid) * MB);
 #pragma unroll
-        for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(v0.v[i]); zA[i] = to_f32<T>(v1.v[i]); sB[i] = to_f32<T>(v2.v[i]); zB[i] = to_f32<T>(v3.v[i]); }
-      }
+      for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(mv[0].v[i]); zA[i] = to_f32<T>(mv[1].v[i]); sB[i] = to_f32<T>(mv[2].v[i]); zB[i] = to_f32<T>(mv[3].v[i]); }
+      meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
       const int kb = kb0 + ku;
       const int kb_next = (ku + 1 == upt) ? kb0 : kb + 1;  // x depends on k only: the next tile restarts at kb0
       float Sg[MT][4], Xg[MT][4];
@@ -463,7 +478,7 @@ struct D1Cfg {
   static constexpr int F = 8 / NBITS, P = 16 / F, MPG = GS / 16, GPB = 256 / GS, MB = GPB * 2;
   static constexpr int NWV = (F == 1) ? 8 : 4;
   static constexpr int W_BYTES = ST * NWV * 256 * 16;
-  static constexpr int M_BYTES = ST * 4 * 256 * MB;
+  static constexpr int M_BYTES = 0;               // scale/zero travel through registers
   static constexpr int P_BYTES = 2 * 8 * 16 * 4;  // double-buffered: 8 warps x 16 rows
   static int smem(int K) { return W_BYTES + M_BYTES + P_BYTES + K * 2 + (K / GS) * 4; }
 };
@@ -471,11 +486,10 @@ struct D1Cfg {
 template <typename T, int NBITS, int GS, int MAGIC, int ST>
 __global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
-  constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, MB = C::MB, NWV = C::NWV;
+  constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, NWV = C::NWV;
   using MM = MT16<T>;
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* wring = reinterpret_cast<uint4*>(smem);
-  uint8_t* mring = smem + C::W_BYTES;
   float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);       // [2][8][16]
   T* xs = reinterpret_cast<T*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES);      // [K] permuted activations
   float* xsum = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES + a.K * 2);  // [K/GS]
@@ -509,20 +523,45 @@ __global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_d
 
   int i_tile = 0, i_k = 0;
   const uint8_t *iw_a, *iw_b;
-  const T *is_a, *iz_a, *is_b, *iz_b;
   auto issue_setup = [&]() {
     const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
     Tile t; locate(gt, t);
     const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
     const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
-    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
     iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
     iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
-    is_a = t.scale + na * a.Gk + kb0 * GPB; iz_a = t.zero + na * a.Gk + kb0 * GPB;
-    is_b = t.scale + nb * a.Gk + kb0 * GPB; iz_b = t.zero + nb * a.Gk + kb0 * GPB;
   };
   int to_issue = n_tiles * upt;
   if (to_issue > 0) issue_setup();
+  // ---- meta cursor: scale/zero of the NEXT unit travel through registers (plain cached loads, one unit ahead).  They
+  // used to ride the cp.async ring, but 8-byte cp.async costs one shared-memory wavefront per lane (ncu: 60 % of all
+  // shared wavefronts of the kernel).
+  int m_tile = 0, m_k = 0, m_left = n_tiles * upt;
+  const T *ms_a = nullptr, *mz_a = nullptr, *ms_b = nullptr, *mz_b = nullptr;
+  auto meta_setup = [&]() {
+    const int gt = (int)blockIdx.x + m_tile * (int)gridDim.x;
+    Tile t; locate(gt, t);
+    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
+    ms_a = t.scale + na * a.Gk + kb0 * GPB; mz_a = t.zero + na * a.Gk + kb0 * GPB;
+    ms_b = t.scale + nb * a.Gk + kb0 * GPB; mz_b = t.zero + nb * a.Gk + kb0 * GPB;
+  };
+  if (m_left > 0) meta_setup();
+  Vec<T, GPB> mv[4];
+  auto meta_fetch = [&]() {
+    if (m_left > 0) {
+      mv[0] = *reinterpret_cast<const Vec<T, GPB>*>(ms_a); mv[1] = *reinterpret_cast<const Vec<T, GPB>*>(mz_a);
+      mv[2] = *reinterpret_cast<const Vec<T, GPB>*>(ms_b); mv[3] = *reinterpret_cast<const Vec<T, GPB>*>(mz_b);
+      --m_left;
+      if (++m_k == upt) {
+        m_k = 0; ++m_tile;
+        if (m_left > 0) meta_setup();
+      } else {
+        ms_a += GPB; mz_a += GPB; ms_b += GPB; mz_b += GPB;
+      }
+    }
+  };
+  meta_fetch();
   auto issue = [&](int stage) {
     if (to_issue > 0) {
 #pragma unroll
@@ -531,16 +570,12 @@ __global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_d
 #pragma unroll
         for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
       }
-      cp_async_small<MB>(mring + ((stage * 4 + 0) * 256 + tid) * MB, is_a);
-      cp_async_small<MB>(mring + ((stage * 4 + 1) * 256 + tid) * MB, iz_a);
-      cp_async_small<MB>(mring + ((stage * 4 + 2) * 256 + tid) * MB, is_b);
-      cp_async_small<MB>(mring + ((stage * 4 + 3) * 256 + tid) * MB, iz_b);
       --to_issue;
       if (++i_k == upt) {
         i_k = 0; ++i_tile;
         if (to_issue > 0) issue_setup();
       } else {
-        iw_a += 256; iw_b += 256; is_a += GPB; iz_a += GPB; is_b += GPB; iz_b += GPB;
+        iw_a += 256; iw_b += 256;
       }
     }
     cp_async_commit();
@@ -586,14 +621,9 @@ __global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_d
       }
       cp_async_wait<ST - 1>();
       float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
-      {
-        const Vec<T, GPB> v0 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 0) * 256 + tid) * MB);
-        const Vec<T, GPB> v1 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 1) * 256 + tid) * MB);
-        const Vec<T, GPB> v2 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 2) * 256 + tid) * MB);
-        const Vec<T, GPB> v3 = *reinterpret_cast<const Vec<T, GPB>*>(mring + ((stage * 4 + 3) * 256 + tid) * MB);
 #pragma unroll
-        for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(v0.v[i]); zA[i] = to_f32<T>(v1.v[i]); sB[i] = to_f32<T>(v2.v[i]); zB[i] = to_f32<T>(v3.v[i]); }
-      }
+      for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(mv[0].v[i]); zA[i] = to_f32<T>(mv[1].v[i]); sB[i] = to_f32<T>(mv[2].v[i]); zB[i] = to_f32<T>(mv[3].v[i]); }
+      meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
       const int kb = kb0 + ku;
       const T* xk = xs + kb * 256 + 16 * c;
       float Sg[4];

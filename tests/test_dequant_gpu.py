@@ -81,3 +81,26 @@ def test_full_size_matches_unpack_then_affine():
     from hqq_b200.core.bitpack import BitPack
     ref = ((BitPack.unpack_4bit_u8(W_q, dtype=torch.float16) - zero) * scale).reshape(N, K)
     assert torch.equal(out, ref)
+
+
+def test_hqq_aten_module_surface(oracle):
+    """hqq/kernels/hqq_aten_cuda.cpp:57-73 names, served by the same library (tests/test_bitpack.py:37-47 pattern:
+    python pack -> native unpack must agree)."""
+    import hqq_b200.hqq_aten as hqq_aten
+    from hqq_b200.core.bitpack import BitPack
+    torch.manual_seed(42)
+    for nbits, pack, unpack in ((4, BitPack.pack_4bit_u8, hqq_aten.unpack_4bit_u8), (2, BitPack.pack_2bit_u8, hqq_aten.unpack_2bit_u8),
+                                (1, BitPack.pack_1bit_u8, hqq_aten.unpack_1bit_u8), (3, BitPack.pack_3bit_32, hqq_aten.unpack_3bit_32)):
+        W = torch.randint(0, 2 ** nbits, (128, 256), device=DEV)
+        assert torch.equal(W, unpack(pack(W))[: len(W)].to(W.dtype))
+    W = torch.randn(128, 256, device=DEV) * 0.02
+    for axis in (0, 1):
+        W_q, meta = Quantizer.quantize(W, nbits=4, group_size=64, axis=axis, compute_dtype=torch.float16)
+        s, z = meta["scale"].half(), meta["zero"].half()
+        out = hqq_aten.dequantize(W_q, s, z, 128, 256, 64, 4, axis, "4bit_u8")
+        meta["compute_dtype"] = torch.float16
+        assert out.dtype == torch.float16 and torch.equal(out, Quantizer.dequantize(W_q, dict(meta, scale=s, zero=z)))
+    Wg = torch.randint(0, 16, (64, 512), device=DEV)  # grouped [gs, C] matrix, axis-0 meta [1, C]
+    s = torch.rand(1, 512, device=DEV).half(); z = (torch.rand(1, 512, device=DEV) * 15).half()
+    out = hqq_aten.dequantize_4bit_u8(BitPack.pack_4bit_u8(Wg), s, z)
+    assert torch.equal(out, (Wg.half() - z) * s)
