@@ -136,24 +136,39 @@ __device__ __forceinline__ uint32_t make_idesc(int UN) {
 
 // ---- level -> T with the reference's roundings -------------------------------------------------------------------
 // Two k-adjacent levels (bytes b0, b1 already masked to the field) -> T2 {fl(fl(q0 - z) * s), fl(fl(q1 - z) * s)}.
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+// Four k-adjacent levels (one per byte of `t`, already masked to the field) -> two packed T2
+//   {fl(fl(q0 - z) * s), fl(fl(q1 - z) * s)}, {.. q2, q3 ..}
 template <typename T> struct Pair;
 template <> struct Pair<__half> {
   using T2 = __half2;
-  __device__ __forceinline__ static uint32_t deq(uint32_t q0, uint32_t q1, __half2 z2, __half2 s2) {
-    // 0x6400 | q == 1024 + q exactly; subtracting 1024 is exact, so (q - z) and (.. * s) round exactly like the reference
-    const uint32_t v = 0x64006400u | q0 | (q1 << 16);
-    __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
-    h = __hmul2(__hsub2(h, z2), s2);
-    return *reinterpret_cast<uint32_t*>(&h);
+  __device__ __forceinline__ static void deq4(uint32_t t, __half2 z2, __half2 s2, uint32_t& lo, uint32_t& hi) {
+    // byte | 0x6400 == 1024 + q exactly (one PRMT per pair); subtracting 1024 is exact, so (q - z) and (.. * s) round
+    // exactly like the reference's two steps
+    const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    uint32_t a = prmt_b32(t, 0x64646464u, 0x4140u), b = prmt_b32(t, 0x64646464u, 0x4342u);
+    __half2 ha = __hmul2(__hsub2(__hsub2(*reinterpret_cast<__half2*>(&a), k1024), z2), s2);
+    __half2 hb = __hmul2(__hsub2(__hsub2(*reinterpret_cast<__half2*>(&b), k1024), z2), s2);
+    lo = *reinterpret_cast<uint32_t*>(&ha);
+    hi = *reinterpret_cast<uint32_t*>(&hb);
   }
   __device__ __forceinline__ static __half2 bcast(__half v) { return __half2half2(v); }
 };
 template <> struct Pair<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
-  __device__ __forceinline__ static uint32_t deq(uint32_t q0, uint32_t q1, __nv_bfloat162 z2, __nv_bfloat162 s2) {
-    __nv_bfloat162 h = __halves2bfloat162(__ushort2bfloat16_rn((unsigned short)q0), __ushort2bfloat16_rn((unsigned short)q1));
-    h = __hmul2(__hsub2(h, z2), s2);
-    return *reinterpret_cast<uint32_t*>(&h);
+  __device__ __forceinline__ static void deq4(uint32_t t, __nv_bfloat162 z2, __nv_bfloat162 s2, uint32_t& lo, uint32_t& hi) {
+    // levels < 256 are exact in bf16 (8 significant bits); convert through the exact float 2^23 + q trick
+    const float f0 = __uint_as_float(0x4B000000u | (t & 0xFFu)) - 8388608.0f, f1 = __uint_as_float(0x4B000000u | ((t >> 8) & 0xFFu)) - 8388608.0f;
+    const float f2 = __uint_as_float(0x4B000000u | ((t >> 16) & 0xFFu)) - 8388608.0f, f3 = __uint_as_float(0x4B000000u | (t >> 24)) - 8388608.0f;
+    __nv_bfloat162 ha = __hmul2(__hsub2(__floats2bfloat162_rn(f0, f1), z2), s2);
+    __nv_bfloat162 hb = __hmul2(__hsub2(__floats2bfloat162_rn(f2, f3), z2), s2);
+    lo = *reinterpret_cast<uint32_t*>(&ha);
+    hi = *reinterpret_cast<uint32_t*>(&hb);
   }
   __device__ __forceinline__ static __nv_bfloat162 bcast(__nv_bfloat16 v) { return __bfloat162bfloat162(v); }
 };
@@ -294,8 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < BPT / 4; ++i) {
               const uint32_t t = (wcur[i] >> sh) & (MASK * 0x01010101u);
-              out[2 * i] = P2::deq(t & 0xFFu, (t >> 8) & 0xFFu, z2[f], s2[f]);
-              out[2 * i + 1] = P2::deq((t >> 16) & 0xFFu, (t >> 24) & 0xFFu, z2[f], s2[f]);
+              P2::deq4(t, z2[f], s2[f], out[2 * i], out[2 * i + 1]);
             }
             // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
             uint8_t* rowp = stage + row * 128;

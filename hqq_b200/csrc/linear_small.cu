@@ -483,8 +483,8 @@ struct D1Cfg {
   static int smem(int K) { return W_BYTES + M_BYTES + P_BYTES + K * 2 + (K / GS) * 4; }
 };
 
-template <typename T, int NBITS, int GS, int MAGIC, int ST>
-__global__ void __launch_bounds__(256, (ST == 2 && NBITS != 8) ? 3 : 2) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
+template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC>
+__global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
   constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, NWV = C::NWV;
   using MM = MT16<T>;
@@ -767,22 +767,20 @@ static int launch_sk(SKArgs& a, cudaStream_t st) {
   return HQQ_OK;
 }
 
-template <typename T, int NBITS, int GS, int MAGIC, int ST>
+template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC>
 static int launch_d1(SKArgs& a, cudaStream_t st) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
-  static int max_smem = 0, occ_grid = 0;
+  static int max_smem = 0;
   const int smem = C::smem(a.K);
-  auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST>;
+  auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST, MC>;
   if (smem > max_smem) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
     max_smem = smem;
-    occ_grid = 0;
   }
-  if (!occ_grid) occ_grid = sm_count() * ((ST == 2 && NBITS != 8) ? 3 : 2);
-  int grid = occ_grid;
-  if (smem * (grid / sm_count()) > 224 * 1024) grid = sm_count() * (224 * 1024 / smem);
-  grid = balanced_grid(a.total_tiles, grid);
+  int per_sm = MC;
+  while (per_sm > 1 && (smem + 1024) * per_sm > 227 * 1024) --per_sm;
+  int grid = balanced_grid(a.total_tiles, sm_count() * per_sm);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(256);
@@ -811,12 +809,18 @@ static bool d1_enabled() {
 template <typename T, int NBITS, int GS, int MAGIC>
 static int sk_mt(SKArgs& a, cudaStream_t st) {
   if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
-    if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2>(a, st);
-    static int st_override = -1;
-    if (st_override < 0) { const char* e = getenv("HQQ_B200_D1_STAGES"); st_override = e ? atoi(e) : 0; }
-    if (st_override == 2) return launch_d1<T, NBITS, GS, MAGIC, 2>(a, st);
-    if (st_override == 3) return launch_d1<T, NBITS, GS, MAGIC, 3>(a, st);
-    return (a.K > 8192) ? launch_d1<T, NBITS, GS, MAGIC, 3>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 4>(a, st);
+    if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
+    static int variant = -1;  // HQQ_B200_D1_VARIANT = <stages><ctas per SM>, e.g. 42 (default), 43, 33, 23
+    if (variant < 0) { const char* e = getenv("HQQ_B200_D1_VARIANT"); variant = e ? atoi(e) : 0; }
+    switch (variant) {
+      case 43: return launch_d1<T, NBITS, GS, MAGIC, 4, 3>(a, st);
+      case 33: return launch_d1<T, NBITS, GS, MAGIC, 3, 3>(a, st);
+      case 23: return launch_d1<T, NBITS, GS, MAGIC, 2, 3>(a, st);
+      case 62: return launch_d1<T, NBITS, GS, MAGIC, 6, 2>(a, st);
+      case 32: return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
+      default: break;
+    }
+    return (a.K > 8192) ? launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);
   }
   if (a.M <= 8) return launch_sk<T, NBITS, GS, 1, MAGIC>(a, st);
   if (a.M <= 16) return launch_sk<T, NBITS, GS, 2, MAGIC>(a, st);
