@@ -48,6 +48,14 @@ struct SKArgs {
   int Gk;           // groups per output row = K / GS
   int KB;           // 256-k units per row tile = K / 256
   int total_tiles;
+  // optional activation prologue (M == 1 decode kernel only; used by the decode harness to drop a launch):
+  //   xop 0: x as is;  1: x = rmsnorm(x + x2) * xw, and h_out = x + x2 is written by CTA 0 (x2 may be null);
+  //   xop 2: x = silu(x) * x2
+  int xop;
+  const void* x2;
+  const void* xw;
+  void* h_out;
+  float eps;
 };
 
 template <typename T> struct MT16;
@@ -211,6 +219,10 @@ __device__ __forceinline__ void cp_async_small(void* smem, const void* g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T> __device__ __forceinline__ T from_f32_t(float v);
+template <> __device__ __forceinline__ __half from_f32_t<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -588,9 +600,54 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   // ---- stage this warp's k-chunk of x (permuted: k -> k with bits 0 and 1 swapped) and its per-group sums ----------
   {
     const T* x = reinterpret_cast<const T*>(a.x);
+    const T* x2 = reinterpret_cast<const T*>(a.x2);
     const int k_lo = kb0 * 256, k_hi = kb1 * 256;
+    float inv = 1.0f;
+    if (a.xop == 1) {
+      // fused residual add + RMSNorm: every CTA needs the sum of squares of the whole vector (K elements, L2-resident)
+      float ss = 0.0f;
+      T* hout = reinterpret_cast<T*>(a.h_out);
+      for (int k8 = tid * 8; k8 < a.K; k8 += 256 * 8) {
+        Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+        if (x2) {
+          const Vec<T, 8> d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
+        }
+        if (hout && blockIdx.x == 0) *reinterpret_cast<Vec<T, 8>*>(hout + k8) = v;  // the residual stream, written once
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float f = to_f32<T>(v.v[j]); ss += f * f; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) part_s[warp] = ss;
+      __syncthreads();  // all 8 warps are still here (CTAs without tiles returned as a whole)
+      float tot = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += part_s[w];
+      inv = rsqrtf(tot / (float)a.K + a.eps);
+      __syncthreads();  // part_s is reused by the tile reduction below
+    }
+    const T* xw = reinterpret_cast<const T*>(a.xw);
     for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
-      const Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+      Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+      if (a.xop == 1) {
+        if (x2) {
+          const Vec<T, 8> d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
+        }
+        const Vec<T, 8> g = *reinterpret_cast<const Vec<T, 8>*>(xw + k8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(to_f32<T>(v.v[j]) * inv)) * to_f32<T>(g.v[j]));
+      } else if (a.xop == 2) {
+        const Vec<T, 8> u = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = to_f32<T>(v.v[j]);
+          v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(f / (1.0f + __expf(-f)))) * to_f32<T>(u.v[j]));
+        }
+      }
       Vec<T, 8> w;
       w.v[0] = v.v[0]; w.v[1] = v.v[2]; w.v[2] = v.v[1]; w.v[3] = v.v[3];
       w.v[4] = v.v[4]; w.v[5] = v.v[6]; w.v[6] = v.v[5]; w.v[7] = v.v[7];
@@ -871,15 +928,23 @@ bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis
 
 size_t small_workspace_bytes(int64_t) { return 0; }  // split-K partials meet in shared memory
 
+bool small_xop_ok(int64_t M, int64_t K) { return M == 1 && K <= 16384 && d1_enabled(); }
+
 int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
                        const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
-                       void* ws, size_t ws_bytes, cudaStream_t st) {
+                       void* ws, size_t ws_bytes, cudaStream_t st, int xop, const void* x2, const void* xw, void* h_out, float eps) {
   HQQ_REQUIRE(nprob >= 1 && nprob <= kMaxProb, HQQ_E_INVALID, "hqq_b200_linear_fwd_multi: 1..%d matrices per launch (got %d)", kMaxProb, nprob);
   HQQ_REQUIRE(aligned(x, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x must be 16-byte aligned");
   (void)ws; (void)ws_bytes;
   const int F = 8 / nbits, P = 16 / F;
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
+  a.xop = xop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
+  if (xop != 0) {
+    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd: the activation prologue needs M == 1 and K <= 16384");
+    HQQ_REQUIRE((xop == 1 && xw) || (xop == 2 && x2), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: missing operand for x_op %d", xop);
+    HQQ_REQUIRE(aligned(x2, 16) && aligned(xw, 16) && aligned(h_out, 16), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: operands must be 16-byte aligned");
+  }
   int tiles = 0;
   for (int i = 0; i < kMaxProb; ++i) {
     const int j = i < nprob ? i : 0;

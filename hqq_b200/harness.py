@@ -59,7 +59,7 @@ def shard_dims(shape: LlamaShape, tp: int):
 class DecodeModel:
     def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
                  device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
-                 n_layers: int | None = None, fused: bool = True):
+                 n_layers: int | None = None, fused=5):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
         self.fused = fused
         self.tp, self.rank, self.pg = tp, rank, process_group
@@ -186,11 +186,45 @@ class DecodeModel:
         check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
         self.pos.add_(1).remainder_(self.cache_len)
 
+    def step_fused5(self):
+        """Five launches per block: [add+RMSNorm -> q/k/v], RoPE+cache+attention, o, [add+RMSNorm -> gate/up],
+        [SiLU*mul -> down]; the bracketed prologues run inside the fused linear's activation staging."""
+        from ._lib import DTYPE_CODE, check, load, ptr, stream_ptr
+        lib, s = load(), self.shape
+        st = stream_ptr(self.device)
+        code = DTYPE_CODE[self.dtype]
+        hd, hq, hkv = s.head_dim, s.n_heads // self.tp, s.n_kv_heads // self.tp
+        b = self._bufs
+        h_cur, h_nxt = b["h"], b["h2"]
+        torch.index_select(self.embed, 0, self.tok, out=h_cur)
+        delta = None
+        ok = True
+        for blk in self.blocks:
+            ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps)
+            h_cur, h_nxt = h_nxt, h_cur
+            check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
+                                                     ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
+            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
+            if self.tp > 1:
+                torch.distributed.all_reduce(b["o"], group=self.pg)
+            ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
+            h_cur, h_nxt = h_nxt, h_cur
+            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
+            if self.tp > 1:
+                torch.distributed.all_reduce(b["down"], group=self.pg)
+            delta = b["down"]
+        if not ok:
+            raise RuntimeError("hqq_b200: this model shape is outside the fused M=1 decode kernel; use fused=False or step_fused")
+        check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+        torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
+        check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
+        self.pos.add_(1).remainder_(self.cache_len)
+
     def _alloc_bufs(self):
         s, dev, dt = self.shape, self.device, self.dtype
         z = lambda n: torch.zeros(1, n, device=dev, dtype=dt)
         tp = self.tp
-        self._bufs = {"h": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads // tp * s.head_dim), "k": z(s.n_kv_heads // tp * s.head_dim),
+        self._bufs = {"h": z(s.hidden), "h2": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads // tp * s.head_dim), "k": z(s.n_kv_heads // tp * s.head_dim),
                       "v": z(s.n_kv_heads // tp * s.head_dim), "a": z(s.n_heads // tp * s.head_dim), "o": z(s.hidden),
                       "gate": z(s.inter // tp), "up": z(s.inter // tp), "act": z(s.inter // tp), "down": z(s.hidden), "logits": z(s.vocab)}
 
@@ -199,7 +233,7 @@ class DecodeModel:
         fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
-        step = self.step_fused if fused else self.step
+        step = (self.step_fused5 if self.fused == 5 else self.step_fused) if fused else self.step
         st = torch.cuda.Stream(device=self.device)
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st), torch.no_grad():

@@ -225,4 +225,29 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
     return outs
 
 
+def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0) -> bool:
+    """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
+    residual add + RMSNorm, 2 = SiLU(x) * x2.  Returns False when the configuration is outside the fused M = 1 kernel."""
+    import ctypes
+    lib = load()
+    n = len(layers)
+    m0 = layers[0].meta
+    K = int(m0["shape"][1])
+    nbits = {"8bit_u8": 8, "4bit_u8": 4, "3bit_32": 3, "2bit_u8": 2, "1bit_u8": 1}.get(m0["packing"], 0)
+    code = DTYPE_CODE.get(x.dtype, -1)
+    if code < 0 or m0["group_size"] is None or nbits == 0 or m0["axis"] != 1:
+        return False
+    VP = ctypes.c_void_p * n
+    arr = lambda ts: VP(*[ptr(t) for t in ts])
+    Narr = (ctypes.c_int64 * n)(*[int(l.meta["shape"][0]) for l in layers])
+    rc = lib.hqq_b200_decode_linear_fwd(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
+                                        arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
+                                        arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
+                                        stream_ptr(x.device))
+    if rc == HQQ_E_UNSUPPORTED:
+        return False
+    check(rc)
+    return True
+
+
 __all__ = ["pack", "unpack", "dequantize", "quantize", "linear_fwd", "linear_fwd_multi", "linear_route", "packed_shape", "HQQB200Error"]

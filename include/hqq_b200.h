@@ -149,6 +149,15 @@ int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, i
  * block (hqq/utils/generation_hf.py:270-289 leaves these to HF transformers + torch.compile).
  * fp16/bf16 only; every kernel is launched with programmatic dependent launch.
  * ------------------------------------------------------------------------------------- */
+/* One-token linear(s) with the activation prologue folded into the kernel's x staging, so a block needs 5 launches:
+ *   x_op 0: y_i = x @ W_i^T                               (== hqq_b200_linear_fwd_multi at M = 1)
+ *   x_op 1: t = x + x2 (x2 may be NULL); h_out = t (may be NULL); y_i = (rmsnorm(t, eps) * x_weight) @ W_i^T
+ *   x_op 2: y_i = (silu(x) * x2) @ W_i^T
+ * Roundings follow the stand-alone glue kernels (every intermediate is rounded to `dtype`).  h_out must not alias x. */
+int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps,
+                               int count, const void* const* W_q, const void* const* scale, const void* const* zero,
+                               const void* const* bias, void* const* y, const int64_t* N, int64_t K,
+                               int group_size, int nbits, int dtype, void* stream);
 /* h += delta (delta may be NULL);  y = rmsnorm(h) * weight          (one token, H <= 8192) */
 int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y,
                               int H, float eps, int dtype, void* stream);

@@ -61,17 +61,20 @@ def test_decode_graph_fused_equals_framework_ops():
     """A tiny 2-block model: the captured fused step (8 launches/block) and the PyTorch-op step produce the same tokens."""
     torch.manual_seed(0)
     shape = harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)
-    a = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=True, seed=3)
-    b = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=False, seed=3)
-    a.capture(); b.capture()
-    for m in (a, b):
+    models = [harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3) for f in (5, True, False)]
+    toks = []
+    for m in models:
+        m.capture()
         m.tok.fill_(5); m.pos.zero_()
         for blk in m.blocks:
             blk["k_cache"].zero_(); blk["v_cache"].zero_()
-    ta, tb = [], []
-    for _ in range(12):
-        a.decode(); b.decode()
-        ta.append(int(a.next_tok)); tb.append(int(b.next_tok))
-    agree = sum(int(x == y) for x, y in zip(ta, tb))
-    assert agree >= 10, (ta, tb)  # fp16 reorderings may flip a near-tie late in the sequence, never the early tokens
-    assert ta[:4] == tb[:4]
+        t = []
+        for _ in range(12):
+            m.decode()
+            t.append(int(m.next_tok))
+        toks.append(t)
+    t5, t8, tref = toks
+    assert t5 == t8, (t5, t8)  # the in-kernel prologues round exactly like the stand-alone glue kernels
+    agree = sum(int(x == y) for x, y in zip(t8, tref))
+    assert agree >= 10, (t8, tref)  # fp16 reorderings may flip a near-tie late in the sequence, never the early tokens
+    assert t8[:4] == tref[:4]
