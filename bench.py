@@ -142,25 +142,28 @@ def run_reference(args, rank, world):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def kernel_roofline(model, torch, peaks, reps=4):
-    """Average duration of the fused forward kernel per linear shape.  All launches of one shape over all layers (x reps)
-    are captured into a CUDA graph so the measurement is not bound by Python launch overhead, replayed, and timed with CUDA
-    events on the launching stream.  Cycling through every layer's weights means each launch streams cold weights
-    (per-shape footprint x 32 layers exceeds the 126 MB L2 for everything but k/v).
-    achieved = algorithmic bytes of the 224 launches of one step / their summed average durations."""
+    """Average duration of the fused forward kernel for each of the four launch groups a decode step issues per block
+    (q+k+v, o, gate+up, down -- the matrices that share an activation go out in ONE launch).  All launches of one group over
+    all layers (x reps) are captured into a CUDA graph so the measurement is not bound by Python launch overhead, replayed,
+    and timed with CUDA events on the launching stream.  Cycling through every layer's weights means each launch streams cold
+    weights (per-group footprint x 32 layers exceeds the 126 MB L2).
+    achieved = algorithmic bytes of the 128 launches (224 matrices) of one step / their summed average durations."""
     from hqq_b200 import ops
     dev = model.device
-    names = ["q", "k", "v", "o", "gate", "up", "down"]
+    groups = [("qkv", ("q", "k", "v")), ("o", ("o",)), ("gate_up", ("gate", "up")), ("down", ("down",))]
     per = {}
     tot_bytes = tot_ms = 0.0
-    for name in names:
-        layers = [blk[name] for blk in model.blocks]
-        N, K = layers[0].meta["shape"]
+    for gname, names in groups:
+        sets = [[blk[n] for n in names] for blk in model.blocks]
+        K = sets[0][0].meta["shape"][1]
+        Ns = [l.meta["shape"][0] for l in sets[0]]
         x = torch.randn(1, K, device=dev).to(model.dtype)
-        outs = torch.empty(1, N, device=dev, dtype=model.dtype)
+        outs = [torch.empty(1, N, device=dev, dtype=model.dtype) for N in Ns]
 
         def run_all():
-            for l in layers:
-                ops.linear_fwd(x, l.W_q, l.meta["scale"], l.meta["zero"], None, N, K, 64, 4, 1, out=outs)
+            for ls in sets:
+                if not ops.decode_linear_fwd(x, ls, outs):
+                    ops.linear_fwd_multi(x, ls, outs)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -180,16 +183,16 @@ def kernel_roofline(model, torch, peaks, reps=4):
         g.replay()
         e1.record(stream)
         torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / (reps * len(layers))
-        nbytes = N * K * 0.5 + 2 * (N * K // 64) * 2 + K * 2 + N * 2
-        per[name] = {"N": N, "K": K, "us": round(ms * 1e3, 3), "GBps": round(nbytes / ms / 1e6, 1)}
+        ms = e0.elapsed_time(e1) / (reps * len(sets))
+        nbytes = sum(N * K * 0.5 + 2 * (N * K // 64) * 2 + N * 2 for N in Ns) + K * 2
+        per[gname] = {"N": Ns, "K": K, "us": round(ms * 1e3, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         tot_bytes += nbytes
         tot_ms += ms
     achieved = tot_bytes / tot_ms / 1e6
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "kernel": "hqq::linear_small_kernel<half,4,64,1> (224 launches/step)", "peak_source": peaks["source"],
-            "per_shape": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
-            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights)"}
+            "traffic": None, "kernel": "hqq::linear_decode1_kernel<half,4,64> (4 launches/block, 128/step)", "peak_source": peaks["source"],
+            "per_launch_group": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
+            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: see profiles/"}
 
 
 def run_gpu(args, rank, world, local_rank):

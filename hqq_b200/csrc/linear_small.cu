@@ -874,6 +874,9 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
       case 33: return launch_d1<T, NBITS, GS, MAGIC, 3, 3>(a, st);
       case 23: return launch_d1<T, NBITS, GS, MAGIC, 2, 3>(a, st);
       case 62: return launch_d1<T, NBITS, GS, MAGIC, 6, 2>(a, st);
+      case 41: return launch_d1<T, NBITS, GS, MAGIC, 4, 1>(a, st);
+      case 61: return launch_d1<T, NBITS, GS, MAGIC, 6, 1>(a, st);
+      case 81: return launch_d1<T, NBITS, GS, MAGIC, 8, 1>(a, st);
       case 32: return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
       default: break;
     }
