@@ -258,75 +258,89 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     }
   } else {
     // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
+    static_assert(kStages == 4, "the dequant loop is unrolled over the 4 ring stages");
     const int td = threadIdx.x - 64;
     const int pr = td / TPR, c = td % TPR;
     const bool row_ok = (prow0 + pr) < a.step;
-    const uint8_t* wp = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
-    const T* sc = reinterpret_cast<const T*>(a.scale);
-    const T* ze = reinterpret_cast<const T*>(a.zero);
-    long long meta_row[F];
+    const uint8_t* wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
+    // per-slab meta rows and shared-memory offsets are loop invariant
+    constexpr int GPQ = 256 / GS;  // quantisation groups per 4 k-blocks (4 or 2): one vector load per slab and array
+    const T* sptr[F];
+    const T* zptr[F];
+    uint32_t soff[F];
 #pragma unroll
-    for (int f = 0; f < F; ++f) meta_row[f] = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+    for (int f = 0; f < F; ++f) {
+      const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+      sptr[f] = reinterpret_cast<const T*>(a.scale) + mrow;
+      zptr[f] = reinterpret_cast<const T*>(a.zero) + mrow;
+      const int row = f * PR + pr;
+      // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
+      if constexpr (BPT >= 8) soff[f] = (uint32_t)(row * 128) | ((uint32_t)(row & 7) << 16);  // chunk applied below
+      else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
 
-    // Packed bytes and scale/zero are prefetched kPre k-blocks ahead through a register ring: their HBM/L2 latency would
-    // otherwise sit on the critical path of every 64-k stage (measured: ~630 ns per stage with a depth of one).
-    constexpr int kPre = 4;
-    uint32_t wbuf[kPre][BPT / 4];
-    T sbuf[kPre][F], zbuf[kPre][F];
-    auto load_kb = [&](int kb, uint32_t (&w)[BPT / 4], T (&sv)[F], T (&zv)[F]) {
-      const uint8_t* p = wp + (long long)kb * kBlockK;
+    // Packed bytes and scale/zero for the NEXT four k-blocks sit in registers while the current four are expanded: their
+    // HBM/L2 latency stays off the critical path of the 64-k stages.
+    uint32_t wbuf[4][BPT / 4];
+    Vec<T, GPQ> sv[F], zv[F];
+    auto load_w = [&](const uint8_t* p, uint32_t (&w)[BPT / 4]) {
       if constexpr (BPT == 32) { const uint4 v0 = ldg_stream_v4(p), v1 = ldg_stream_v4(p + 16); w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; }
       else if constexpr (BPT == 16) { const uint4 v = ldg_stream_v4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
       else if constexpr (BPT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
       else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
-      const int g = (kb * kBlockK) / GS;
-#pragma unroll
-      for (int f = 0; f < F; ++f) { sv[f] = sc[meta_row[f] + g]; zv[f] = ze[meta_row[f] + g]; }
     };
+    auto load_quad = [&]() {  // the four k-blocks starting at wptr, and their groups
 #pragma unroll
-    for (int d = 0; d < kPre; ++d)
-      if (d < num_kb) load_kb(d, wbuf[d], sbuf[d], zbuf[d]);
-    for (int kb0 = 0; kb0 < num_kb; kb0 += kPre) {
+      for (int d = 0; d < 4; ++d) load_w(wptr + d * kBlockK, wbuf[d]);
 #pragma unroll
-      for (int d = 0; d < kPre; ++d) {
-        const int kb = kb0 + d;
-        if (kb < num_kb) {
-          const int s = kb % kStages;
-          uint32_t wcur[BPT / 4];
-          typename P2::T2 s2[F], z2[F];
+      for (int f = 0; f < F; ++f) { sv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(sptr[f]); zv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(zptr[f]); }
+    };
+    load_quad();
+    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router)
+    for (int q = 0; q < num_quads; ++q) {
+      uint32_t wq[4][BPT / 4];
+      typename P2::T2 s2[4][F], z2[4][F];
 #pragma unroll
-          for (int i = 0; i < BPT / 4; ++i) wcur[i] = wbuf[d][i];
+      for (int d = 0; d < 4; ++d) {
 #pragma unroll
-          for (int f = 0; f < F; ++f) { s2[f] = P2::bcast(sbuf[d][f]); z2[f] = P2::bcast(zbuf[d][f]); }
-          if (kb + kPre < num_kb) load_kb(kb + kPre, wbuf[d], sbuf[d], zbuf[d]);
-          mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
-          uint8_t* stage = sA + s * S::A_STAGE;
+        for (int i = 0; i < BPT / 4; ++i) wq[d][i] = wbuf[d][i];
 #pragma unroll
-          for (int f = 0; f < F; ++f) {
-            const int row = f * PR + pr;
-            const int sh = 8 - NBITS * (f + 1);
-            uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
+        for (int f = 0; f < F; ++f) { s2[d][f] = P2::bcast(sv[f].v[(d * kBlockK) / GS]); z2[d][f] = P2::bcast(zv[f].v[(d * kBlockK) / GS]); }
+      }
+      if (q + 1 < num_quads) {
+        wptr += 4 * kBlockK;
 #pragma unroll
-            for (int i = 0; i < BPT / 4; ++i) {
-              const uint32_t t = (wcur[i] >> sh) & (MASK * 0x01010101u);
-              P2::deq4(t, z2[f], s2[f], out[2 * i], out[2 * i + 1]);
-            }
-            // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
-            uint8_t* rowp = stage + row * 128;
-            if constexpr (BPT >= 8) {
+        for (int f = 0; f < F; ++f) { sptr[f] += GPQ; zptr[f] += GPQ; }
+        load_quad();
+      }
+      const uint32_t parity = (uint32_t)(q & 1) ^ 1u;
 #pragma unroll
-              for (int ch = 0; ch < BPT / 8; ++ch) {
-                const int chunk = c * (BPT / 8) + ch;
-                *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = make_uint4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
-              }
-            } else {  // BPT == 4: half a chunk
-              const int chunk = c >> 1;
-              *reinterpret_cast<uint2*>(rowp + ((chunk ^ (row & 7)) << 4) + (c & 1) * 8) = make_uint2(out[0], out[1]);
-            }
+      for (int d = 0; d < 4; ++d) {  // stage index == d because the ring has exactly four stages
+        mbar_wait(&empty[d], parity);
+        const uint32_t stage = sA_u32 + d * S::A_STAGE;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int sh = 8 - NBITS * (f + 1);
+          uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
+#pragma unroll
+          for (int i = 0; i < BPT / 4; ++i) {
+            const uint32_t t = (wq[d][i] >> sh) & (MASK * 0x01010101u);
+            P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
           }
-          fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
-          mbar_arrive(&full_a[s]);
+          if constexpr (BPT >= 8) {
+            const uint32_t rowbase = stage + (soff[f] & 0xFFFFu), rx = soff[f] >> 16;
+#pragma unroll
+            for (int ch = 0; ch < BPT / 8; ++ch) {
+              const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+            }
+          } else {  // BPT == 4: half a chunk
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+          }
         }
+        fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
+        mbar_arrive(&full_a[d]);
       }
     }
 
@@ -440,7 +454,7 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
   if (dtype != HQQ_F16 && dtype != HQQ_BF16) return false;
   if (!(nbits == 8 || nbits == 4 || nbits == 2 || nbits == 1)) return false;
   if (!(gs == 64 || gs == 128)) return false;     // one 64-k stage never straddles a group
-  if (M < 1 || K % 64 != 0 || K % gs != 0) return false;
+  if (M < 1 || K % 256 != 0 || K % gs != 0) return false;  // the dequant loop handles four 64-k stages per iteration
   if (N % (8 / nbits) != 0) return false;
   if (K % 8 != 0 || N > (1 << 28) || K > (1 << 28) || M > (1 << 28)) return false;
   return true;

@@ -89,7 +89,7 @@ def test_tcgen05_gemm_vs_oracle(oracle, nbits, dtype, gs):
     (64/128/256), partial token tiles, ragged weight tiles, K not a multiple of 256, bias."""
     rng = np.random.RandomState(7 * nbits + gs)
     f = 8 // nbits
-    N, K = 40 * f, 384  # 40 packed rows: partial 128-row tile for every bit width; K = 6 k-blocks (not a multiple of 256)
+    N, K = 40 * f, 512  # 40 packed rows: partial 128-row tile for every bit width; K = 8 k-blocks = 2 register quads
     W_q, scale, zero = _random_layer(rng, N, K, nbits, gs, oracle)
     bias = rng.randn(N).astype(np.float32)
     meta_o = {"nbits": nbits, "group_size": gs, "shape": (N, K), "axis": 1, "packing": oracle.BIT_TO_PACKING[nbits], "scale": scale, "zero": zero}
