@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libhqq_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
-STAMP = os.path.join(OBJ_DIR, "sources.sha256")
+STAMP = os.path.join(PKG_DIR, "libhqq_b200.stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * S::A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (S::A_STAGE + S::B_STAGE));
-  uint64_t* full_a = bars;                 // [kStages] dequant warps -> MMA (256 arrivals)
+  uint64_t* full_a = bars;                 // [kStages] dequant warps -> MMA (one arrival per warp)
   uint64_t* full_b = bars + kStages;       // [kStages] TMA -> MMA (1 arrival + tx bytes)
   uint64_t* empty = bars + 2 * kStages;    // [kStages] MMA (tcgen05.commit) -> producers
   uint64_t* accum_full = bars + 3 * kStages;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
       asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           }
         }
         fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
-        mbar_arrive(&full_a[d]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[d]);  // one arrival per warp: every lane has fenced its stores before the syncwarp
       }
     }
 
