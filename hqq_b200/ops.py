@@ -142,19 +142,16 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor | None:
-    """Per-device scratch for the fused forward, allocated ONCE at its maximum size (so a captured CUDA graph never
-    holds a stale pointer) and zero-initialised: the stream-K kernel keeps its ready-flags there and leaves them zero
-    on exit, so the buffer is reusable across launches and graph replays.  Launches that share it must be
-    stream-ordered (one decode stream per device); concurrent streams need their own `hqq_b200_linear_fwd` workspace."""
+    """Per-device scratch for the fused forward (the current kernels need none: nbytes == 0).  Allocated once and kept
+    alive so a captured CUDA graph never holds a stale pointer."""
     if nbytes == 0:
         return None
     key = device.index if device.index is not None else torch.cuda.current_device()
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        size = max(nbytes, load().hqq_b200_linear_fwd_workspace_bytes(32, 4096, 4096, 64, 4, _lib.HQQ_F16))
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("hqq_b200: run one forward outside CUDA-graph capture first (the workspace is allocated lazily)")
-        buf = torch.zeros(size, dtype=torch.uint8, device=device)
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         _ws_cache.setdefault("keepalive", []).append(buf)
         _ws_cache[key] = buf
     return buf

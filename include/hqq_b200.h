@@ -118,7 +118,8 @@ int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int64_t K,
  *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
  *   axis must be 1.  Returns HQQ_E_UNSUPPORTED for configurations the fused kernels do
  *   not cover (the Python layer then runs hqq_b200_dequantize + a library GEMM).
- *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, zero-initialised once by the caller (see _multi).  */
+ *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes (currently 0 for every route: split-K partials meet in
+ *   shared memory; the parameter is kept so the ABI does not change when a kernel needs scratch).              */
 size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size,
                                            int nbits, int dtype);
 int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero,
@@ -130,8 +131,7 @@ int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const
  * the 16-row tiles of all `count` (<= 4) matrices form one stream-K work list, so small matrices no longer pay a
  * launch each.  Arrays hold `count` device pointers / sizes; bias may be NULL or hold NULL entries; all matrices share
  * K, group_size, nbits, dtype.  Same math per layer as hqq_b200_linear_fwd (quantize.py:880-898).
- * Workspace: hqq_b200_linear_fwd_workspace_bytes(M, ...) bytes, ZERO-INITIALISED once by the caller (the kernel uses
- * its first bytes as ready-flags and leaves them zero on exit); do not share one workspace between concurrent streams. */
+ * Workspace: hqq_b200_linear_fwd_workspace_bytes(M, ...) bytes (currently 0).                                         */
 int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, const void* const* scale,
                               const void* const* zero, const void* const* bias, void* const* y, const int64_t* N,
                               int64_t M, int64_t K, int group_size, int nbits, int axis, int dtype,
