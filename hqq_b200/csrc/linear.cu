@@ -2,12 +2,21 @@
 #include "common.cuh"
 
 namespace hqq {
+struct TpExchange {
+  int tp, rank;
+  void* const* peer_data;
+  int* const* peer_flag;
+  int* prod_ctr;
+  const void* red_data;
+  const int* red_flag;
+  int* red_ctr;
+};
 bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t small_workspace_bytes(int64_t M);
 int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
                        const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
                        void* ws, size_t ws_bytes, cudaStream_t st, int xop = 0, const void* x2 = nullptr, const void* xw = nullptr,
-                       void* h_out = nullptr, float eps = 0.0f);
+                       void* h_out = nullptr, float eps = 0.0f, const TpExchange* tpx = nullptr);
 bool small_xop_ok(int64_t M, int64_t K);
 bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int gs, int nbits, int dtype);
@@ -86,4 +95,25 @@ extern "C" int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x
   }
   return linear_small_multi(x, count, W_q, scale, zero, bias, y, N, 1, K, group_size, nbits, dtype, nullptr, 0, (cudaStream_t)stream, x_op, x2,
                             x_weight, h_out, eps);
+}
+
+extern "C" int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps, int count,
+                                             const void* const* W_q, const void* const* scale, const void* const* zero,
+                                             const void* const* bias, void* const* y, const int64_t* N, int64_t K, int group_size,
+                                             int nbits, int dtype, int tp, int rank, void* const* peer_data, int* const* peer_flag,
+                                             int* prod_ctr, const void* red_data, const int* red_flag, int* red_ctr, void* stream) {
+  int rc = check_common(x, 1, K, group_size, nbits, 1);
+  if (rc) return rc;
+  HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: 1..4 matrices, non-null arrays");
+  HQQ_REQUIRE(x_op >= 0 && x_op <= 2, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: x_op must be 0, 1 or 2");
+  for (int i = 0; i < count; ++i) {
+    if (!small_route_ok(1, N[i], K, group_size, nbits, 1, dtype) || !small_xop_ok(1, K)) {
+      set_error("hqq_b200_decode_linear_fwd_tp: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i,
+                (long long)N[i], (long long)K, group_size, nbits, dtype);
+      return HQQ_E_UNSUPPORTED;
+    }
+  }
+  TpExchange t{tp, rank, peer_data, peer_flag, prod_ctr, red_data, red_flag, red_ctr};
+  return linear_small_multi(x, count, W_q, scale, zero, bias, y, N, 1, K, group_size, nbits, dtype, nullptr, 0, (cudaStream_t)stream, x_op, x2,
+                            x_weight, h_out, eps, &t);
 }

@@ -27,6 +27,16 @@
 
 namespace hqq {
 
+struct TpExchange {  // host-side view of the optional tensor-parallel exchange (see SKArgs)
+  int tp, rank;
+  void* const* peer_data;
+  int* const* peer_flag;
+  int* prod_ctr;
+  const void* red_data;
+  const int* red_flag;
+  int* red_ctr;
+};
+
 constexpr int kMaxProb = 4;   // weight matrices sharing one activation in a single launch (q/k/v, gate/up)
 
 struct SKProb {
@@ -56,6 +66,19 @@ struct SKArgs {
   const void* xw;
   void* h_out;
   float eps;
+  // optional tensor-parallel exchange over NVLink peer memory (M == 1 decode kernel, single matrix):
+  //   producer (row-parallel o / down): besides y, every result is stored into EVERY rank's exchange buffer
+  //     peer_data[dst][parity][rank][n]; when the whole grid is done the last CTA raises peer_flag[dst][rank] = epoch.
+  //   consumer (xop 1): instead of x2, sums red_data[parity][r][k] over the tp ranks after their flags reached the epoch.
+  // Epochs live in device memory (`*_ctr`) so a captured graph can be replayed; two parities because ranks may be one
+  // exchange apart.
+  int tp, rank;
+  void* peer_data[8];
+  int* peer_flag[8];
+  int* prod_ctr;       // [0] CTAs done, [1] epochs sent
+  const void* red_data;
+  const int* red_flag;
+  int* red_ctr;        // [0] CTAs done, [1] epochs consumed
 };
 
 template <typename T> struct MT16;
@@ -223,6 +246,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <typename T> __device__ __forceinline__ T from_f32_t(float v);
 template <> __device__ __forceinline__ __half from_f32_t<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -596,6 +628,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   for (int s = 0; s < ST - 1; ++s) issue(s);
   pdl_launch_dependents();
   pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
+  const int send_epoch = (a.tp > 1 && a.peer_data[0]) ? *reinterpret_cast<volatile int*>(a.prod_ctr + 1) + 1 : 0;
 
   // ---- stage this warp's k-chunk of x (permuted: k -> k with bits 0 and 1 swapped) and its per-group sums ----------
   {
@@ -603,14 +636,40 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const T* x2 = reinterpret_cast<const T*>(a.x2);
     const int k_lo = kb0 * 256, k_hi = kb1 * 256;
     float inv = 1.0f;
+    const T* red = nullptr;  // this exchange's [tp][K] partial results, written into our memory by the peers
+    if (a.xop == 1 && a.red_data) {
+      const int epoch = *reinterpret_cast<volatile const int*>(a.red_ctr + 1) + 1;
+      if (tid < a.tp) { while (ld_acquire_sys(a.red_flag + tid) - epoch < 0) {} }
+      __syncthreads();
+      red = reinterpret_cast<const T*>(a.red_data) + (long long)(epoch & 1) * a.tp * a.K;
+    }
+    // delta of the residual stream: x2, or the sum of the tp partials (fp32 sum, rounded once like an all-reduce result)
+    auto delta8 = [&](int k8, Vec<T, 8>& d) -> bool {
+      if (red) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        for (int rr = 0; rr < a.tp; ++rr) {
+          const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(red + (long long)rr * a.K + k8));
+          const Vec<T, 8> p8 = *reinterpret_cast<const Vec<T, 8>*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += to_f32<T>(p8.v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = from_f32_t<T>(acc[j]);
+        return true;
+      }
+      if (x2) { d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8); return true; }
+      return false;
+    };
     if (a.xop == 1) {
       // fused residual add + RMSNorm: every CTA needs the sum of squares of the whole vector (K elements, L2-resident)
       float ss = 0.0f;
       T* hout = reinterpret_cast<T*>(a.h_out);
       for (int k8 = tid * 8; k8 < a.K; k8 += 256 * 8) {
         Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
-        if (x2) {
-          const Vec<T, 8> d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+        Vec<T, 8> d;
+        if (delta8(k8, d)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
         }
@@ -632,8 +691,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
       Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
       if (a.xop == 1) {
-        if (x2) {
-          const Vec<T, 8> d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+        Vec<T, 8> d;
+        if (delta8(k8, d)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
         }
@@ -729,10 +788,39 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
         for (int w = 0; w < 8; ++w) acc += buf[w * 16 + lane];
         const int n = ff * t.step + prow;
         MM::st(t.y, n, acc, t.bias, n);
+        if (a.tp > 1 && a.peer_data[0]) {
+          // scatter the (bias-free) partial over NVLink: slot [parity][rank][n] of every rank's exchange buffer
+          const T pv = from_f32_t<T>(acc);
+          const long long off = ((long long)(send_epoch & 1) * a.tp + a.rank) * t.N + n;
+#pragma unroll
+          for (int dst = 0; dst < 8; ++dst)
+            if (dst < a.tp) reinterpret_cast<T*>(a.peer_data[dst])[off] = pv;
+        }
       }
     }
   }
   cp_async_wait<0>();
+  if (a.tp > 1 && (a.peer_data[0] || a.red_data)) {
+    // grid-wide completion: the last CTA to get here publishes / retires the epoch (graph-replay safe: counters live in memory)
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      if (a.peer_data[0]) {
+        if (atomicAdd(a.prod_ctr, 1) == (int)gridDim.x - 1) {
+          a.prod_ctr[0] = 0;
+          a.prod_ctr[1] = send_epoch;
+          __threadfence_system();
+          for (int dst = 0; dst < a.tp; ++dst) st_release_sys(a.peer_flag[dst] + a.rank, send_epoch);
+        }
+      }
+      if (a.red_data) {
+        if (atomicAdd(a.red_ctr, 1) == (int)gridDim.x - 1) {
+          a.red_ctr[0] = 0;
+          a.red_ctr[1] = a.red_ctr[1] + 1;
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -935,7 +1023,8 @@ bool small_xop_ok(int64_t M, int64_t K) { return M == 1 && K <= 16384 && d1_enab
 
 int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
                        const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
-                       void* ws, size_t ws_bytes, cudaStream_t st, int xop, const void* x2, const void* xw, void* h_out, float eps) {
+                       void* ws, size_t ws_bytes, cudaStream_t st, int xop, const void* x2, const void* xw, void* h_out, float eps,
+                       const TpExchange* tpx) {
   HQQ_REQUIRE(nprob >= 1 && nprob <= kMaxProb, HQQ_E_INVALID, "hqq_b200_linear_fwd_multi: 1..%d matrices per launch (got %d)", kMaxProb, nprob);
   HQQ_REQUIRE(aligned(x, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x must be 16-byte aligned");
   (void)ws; (void)ws_bytes;
@@ -943,6 +1032,22 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
   a.xop = xop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
+  a.tp = 1; a.rank = 0; a.prod_ctr = nullptr; a.red_data = nullptr; a.red_flag = nullptr; a.red_ctr = nullptr;
+  for (int i = 0; i < 8; ++i) { a.peer_data[i] = nullptr; a.peer_flag[i] = nullptr; }
+  if (tpx) {
+    HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_tp: needs the M == 1 kernel");
+    HQQ_REQUIRE(tpx->tp >= 2 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: bad tp/rank");
+    a.tp = tpx->tp; a.rank = tpx->rank;
+    if (tpx->peer_data) {
+      HQQ_REQUIRE(nprob == 1 && tpx->peer_flag && tpx->prod_ctr, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: producer needs one matrix, flags and counters");
+      for (int i = 0; i < tpx->tp; ++i) { a.peer_data[i] = tpx->peer_data[i]; a.peer_flag[i] = tpx->peer_flag[i]; }
+      a.prod_ctr = tpx->prod_ctr;
+    }
+    if (tpx->red_data) {
+      HQQ_REQUIRE(xop == 1 && tpx->red_flag && tpx->red_ctr, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: consumer needs x_op 1, flags and counters");
+      a.red_data = tpx->red_data; a.red_flag = tpx->red_flag; a.red_ctr = tpx->red_ctr;
+    }
+  }
   if (xop != 0) {
     HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd: the activation prologue needs M == 1 and K <= 16384");
     HQQ_REQUIRE((xop == 1 && xw) || (xop == 2 && x2), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: missing operand for x_op %d", xop);

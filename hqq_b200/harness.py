@@ -59,9 +59,11 @@ def shard_dims(shape: LlamaShape, tp: int):
 class DecodeModel:
     def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
                  device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
-                 n_layers: int | None = None, fused=5):
+                 n_layers: int | None = None, fused=5, tp_mode: str | None = None):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
         self.fused = fused
+        import os
+        self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
         self.n_layers = n_layers if n_layers is not None else shape.n_layers
@@ -186,6 +188,36 @@ class DecodeModel:
         check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
         self.pos.add_(1).remainder_(self.cache_len)
 
+    def _setup_exchange(self):
+        """Peer-mapped exchange buffers for the fused tensor-parallel all-reduce (`hqq_b200_decode_linear_fwd_tp`): one symmetric
+        allocation per rank holding, for the two row-parallel matrices of a block (o, down): data [2 parities][tp][hidden] and
+        tp ready-flags; the epoch counters stay in local memory."""
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        s, tp, dev = self.shape, self.tp, self.device
+        es = torch.finfo(self.dtype).bits // 8
+        data_bytes = (2 * tp * s.hidden * es + 255) // 256 * 256
+        slot_bytes = data_bytes + 256
+        buf = symm.empty(2 * slot_bytes, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._xbuf, self._xhdl = buf, hdl
+        self._xctr = torch.zeros(2, 4, dtype=torch.int32, device=dev)
+        VP = ctypes.c_void_p * tp
+        self._tp_prod, self._tp_cons, self._tp_keep = [], [], []
+        for slot in range(2):
+            pd = VP(*[p + slot * slot_bytes for p in ptrs])
+            pf = VP(*[p + slot * slot_bytes + data_bytes for p in ptrs])
+            self._tp_keep += [pd, pf]
+            ctr = self._xctr[slot].data_ptr()
+            self._tp_prod.append({"tp": tp, "rank": self.rank, "peer_data": pd, "peer_flag": pf, "prod_ctr": ctr})
+            self._tp_cons.append({"tp": tp, "rank": self.rank, "red_data": ptrs[self.rank] + slot * slot_bytes,
+                                  "red_flag": ptrs[self.rank] + slot * slot_bytes + data_bytes, "red_ctr": ctr + 8})
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+
     def step_fused5(self):
         """Five launches per block: [add+RMSNorm -> q/k/v], RoPE+cache+attention, o, [add+RMSNorm -> gate/up],
         [SiLU*mul -> down]; the bracketed prologues run inside the fused linear's activation staging."""
@@ -199,23 +231,36 @@ class DecodeModel:
         torch.index_select(self.embed, 0, self.tok, out=h_cur)
         delta = None
         ok = True
+        p2p = self.tp > 1 and self.tp_mode == "p2p"
+        prod_o, prod_d = (self._tp_prod if p2p else (None, None))
+        cons_o, cons_d = (self._tp_cons if p2p else (None, None))
+        first = True
         for blk in self.blocks:
-            ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps)
+            # [residual add + RMSNorm] -> q/k/v.  With p2p the delta is the sum of the ranks' down-proj partials.
+            ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None if p2p else delta, blk["norm1"], h_nxt,
+                                        s.rms_eps, tpx=(cons_d if (p2p and not first) else None))
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
-            if self.tp > 1:
+            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=prod_o)
+            if self.tp > 1 and not p2p:
                 torch.distributed.all_reduce(b["o"], group=self.pg)
-            ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
+            ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None if p2p else b["o"], blk["norm2"], h_nxt, s.rms_eps,
+                                        tpx=cons_o)
             h_cur, h_nxt = h_nxt, h_cur
-            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
-            if self.tp > 1:
+            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=prod_d)
+            if self.tp > 1 and not p2p:
                 torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
+            first = False
         if not ok:
             raise RuntimeError("hqq_b200: this model shape is outside the fused M=1 decode kernel; use fused=False or step_fused")
-        check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+        if p2p:
+            c = cons_d
+            check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), c["red_data"], c["red_flag"], c["red_ctr"], self.tp, ptr(self.final_norm), ptr(b["x"]),
+                                                   s.hidden, s.rms_eps, code, st))
+        else:
+            check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
         check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
         self.pos.add_(1).remainder_(self.cache_len)
@@ -233,6 +278,12 @@ class DecodeModel:
         fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
+        if self.tp > 1 and fused and self.fused == 5 and self.tp_mode == "p2p" and not hasattr(self, "_xbuf"):
+            try:
+                self._setup_exchange()
+            except Exception as e:  # symmetric memory unavailable -> NCCL all-reduce between the kernels
+                print(f"hqq_b200: peer-memory exchange unavailable ({e}); using NCCL all-reduce")
+                self.tp_mode = "nccl"
         step = (self.step_fused5 if self.fused == 5 else self.step_fused) if fused else self.step
         st = torch.cuda.Stream(device=self.device)
         st.wait_stream(torch.cuda.current_stream(self.device))

@@ -222,9 +222,12 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
     return outs
 
 
-def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0) -> bool:
+def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None) -> bool:
     """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
-    residual add + RMSNorm, 2 = SiLU(x) * x2.  Returns False when the configuration is outside the fused M = 1 kernel."""
+    residual add + RMSNorm, 2 = SiLU(x) * x2.  `tpx` (dict) switches on the peer-memory exchange of
+    `hqq_b200_decode_linear_fwd_tp`: keys tp, rank and either peer_data/peer_flag/prod_ctr (producer: ctypes pointer arrays and an
+    int address) or red_data/red_flag/red_ctr (consumer: int addresses).  Returns False when the configuration is outside the
+    fused M = 1 kernel."""
     import ctypes
     lib = load()
     n = len(layers)
@@ -237,10 +240,17 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
     VP = ctypes.c_void_p * n
     arr = lambda ts: VP(*[ptr(t) for t in ts])
     Narr = (ctypes.c_int64 * n)(*[int(l.meta["shape"][0]) for l in layers])
-    rc = lib.hqq_b200_decode_linear_fwd(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
-                                        arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
-                                        arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
-                                        stream_ptr(x.device))
+    if tpx is None:
+        rc = lib.hqq_b200_decode_linear_fwd(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
+                                            arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
+                                            arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
+                                            stream_ptr(x.device))
+    else:
+        rc = lib.hqq_b200_decode_linear_fwd_tp(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
+                                               arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
+                                               arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
+                                               int(tpx["tp"]), int(tpx["rank"]), tpx.get("peer_data"), tpx.get("peer_flag"), tpx.get("prod_ctr"),
+                                               tpx.get("red_data"), tpx.get("red_flag"), tpx.get("red_ctr"), stream_ptr(x.device))
     if rc == HQQ_E_UNSUPPORTED:
         return False
     check(rc)
