@@ -50,27 +50,30 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_kernel(T* __restrict__ h, co
   for (int i = threadIdx.x; i < H; i += blockDim.x, ++n) y[i] = from_f32<T>(to_f32<T>(from_f32<T>(v[n] * inv)) * to_f32<T>(w[i]));
 }
 
-// Same as add_rmsnorm_kernel, but the residual delta is the sum of `tp` partial vectors that the peers' row-parallel
-// kernels scattered into this rank's exchange buffer (see SKArgs in linear_small.cu); retires the exchange epoch.
+// Same as add_rmsnorm_kernel, but the residual delta is the sum of `tp` tagged partial vectors that the peers' row-parallel
+// kernels scattered into this rank's exchange buffer (see SKArgs in linear_small.cu).  As the last consumer of a token it
+// bumps the step counter the exchange tags are derived from.
 template <typename T>
-__global__ void __launch_bounds__(1024) add_rmsnorm_tp_kernel(T* __restrict__ h, const T* red_data, const int* red_flag, int* red_ctr, int tp,
-                                                              const T* __restrict__ w, T* __restrict__ y, int H, float eps) {
+__global__ void __launch_bounds__(1024) add_rmsnorm_tp_kernel(T* __restrict__ h, const uint32_t* red_data, int* step_ctr, int x_index, int x_per_step,
+                                                              int tp, const T* __restrict__ w, T* __restrict__ y, int H, float eps) {
   __shared__ float red[32];
   pdl_launch_g();
   pdl_wait_g();
-  const int epoch = *reinterpret_cast<volatile int*>(red_ctr + 1) + 1;
-  if ((int)threadIdx.x < tp) {
-    int v;
-    do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(red_flag + threadIdx.x) : "memory"); } while (v - epoch < 0);
-  }
-  __syncthreads();
-  const T* part = red_data + (long long)(epoch & 1) * tp * H;
+  const int step = *reinterpret_cast<volatile int*>(step_ctr);
+  const uint32_t ex = (uint32_t)step * (uint32_t)x_per_step + (uint32_t)x_index;
+  const uint32_t tag = ex & 0xFFFFu;
+  const uint32_t* part = red_data + (size_t)(ex & 1u) * tp * H;
   float v[8];
   int n = 0;
   float ss = 0.f;
   for (int i = threadIdx.x; i < H; i += blockDim.x, ++n) {
     float d = 0.f;
-    for (int r = 0; r < tp; ++r) d += to_f32<T>(__ldcg(part + (long long)r * H + i));
+    for (int r = 0; r < tp; ++r) {
+      uint32_t wv;
+      do { asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(wv) : "l"(part + (size_t)r * H + i) : "memory"); } while ((wv >> 16) != tag);
+      const unsigned short hb = (unsigned short)(wv & 0xFFFFu);
+      d += to_f32<T>(*reinterpret_cast<const T*>(&hb));
+    }
     float x = to_f32<T>(from_f32<T>(to_f32<T>(h[i]) + to_f32<T>(from_f32<T>(d))));
     h[i] = from_f32<T>(x);
     v[n] = x;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_tp_kernel(T* __restrict__ h,
   const float inv = rsqrtf(tot / (float)H + eps);
   n = 0;
   for (int i = threadIdx.x; i < H; i += blockDim.x, ++n) y[i] = from_f32<T>(to_f32<T>(from_f32<T>(v[n] * inv)) * to_f32<T>(w[i]));
-  if (threadIdx.x == 0) red_ctr[1] = epoch;
+  if (threadIdx.x == 0) *step_ctr = step + 1;
 }
 
 // y = silu(g) * u
@@ -229,14 +232,14 @@ extern "C" int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void*
   return HQQ_E_INVALID;
 }
 
-extern "C" int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, const int* red_flag, int* red_ctr, int tp, const void* weight, void* y,
-                                            int H, float eps, int dtype, void* stream) {
-  HQQ_REQUIRE(h && red_data && red_flag && red_ctr && weight && y && H > 0 && H <= 8 * 1024 && tp >= 2 && tp <= 8, HQQ_E_INVALID,
+extern "C" int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp, const void* weight,
+                                            void* y, int H, float eps, int dtype, void* stream) {
+  HQQ_REQUIRE(h && red_data && step_ctr && weight && y && H > 0 && H <= 8 * 1024 && tp >= 2 && tp <= 8 && x_per_step > 0, HQQ_E_INVALID,
               "hqq_b200_glue_add_rmsnorm_tp: bad arguments (H=%d tp=%d)", H, tp);
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = H >= 4096 ? 1024 : 256;
-  if (dtype == HQQ_F16) return launch_pdl("add_rmsnorm_tp", add_rmsnorm_tp_kernel<__half>, dim3(1), dim3(threads), 0, st, (__half*)h, (const __half*)red_data, red_flag, red_ctr, tp, (const __half*)weight, (__half*)y, H, eps);
-  if (dtype == HQQ_BF16) return launch_pdl("add_rmsnorm_tp", add_rmsnorm_tp_kernel<__nv_bfloat16>, dim3(1), dim3(threads), 0, st, (__nv_bfloat16*)h, (const __nv_bfloat16*)red_data, red_flag, red_ctr, tp, (const __nv_bfloat16*)weight, (__nv_bfloat16*)y, H, eps);
+  if (dtype == HQQ_F16) return launch_pdl("add_rmsnorm_tp", add_rmsnorm_tp_kernel<__half>, dim3(1), dim3(threads), 0, st, (__half*)h, (const uint32_t*)red_data, step_ctr, x_index, x_per_step, tp, (const __half*)weight, (__half*)y, H, eps);
+  if (dtype == HQQ_BF16) return launch_pdl("add_rmsnorm_tp", add_rmsnorm_tp_kernel<__nv_bfloat16>, dim3(1), dim3(threads), 0, st, (__nv_bfloat16*)h, (const uint32_t*)red_data, step_ctr, x_index, x_per_step, tp, (const __nv_bfloat16*)weight, (__nv_bfloat16*)y, H, eps);
   set_error("hqq_b200_glue_add_rmsnorm_tp: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }

@@ -5,11 +5,9 @@ namespace hqq {
 struct TpExchange {
   int tp, rank;
   void* const* peer_data;
-  int* const* peer_flag;
-  int* prod_ctr;
   const void* red_data;
-  const int* red_flag;
-  int* red_ctr;
+  const int* step_ctr;
+  int x_index, x_per_step;
 };
 bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t small_workspace_bytes(int64_t M);
@@ -100,8 +98,8 @@ extern "C" int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x
 extern "C" int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps, int count,
                                              const void* const* W_q, const void* const* scale, const void* const* zero,
                                              const void* const* bias, void* const* y, const int64_t* N, int64_t K, int group_size,
-                                             int nbits, int dtype, int tp, int rank, void* const* peer_data, int* const* peer_flag,
-                                             int* prod_ctr, const void* red_data, const int* red_flag, int* red_ctr, void* stream) {
+                                             int nbits, int dtype, int tp, int rank, void* const* peer_data, const void* red_data,
+                                             const int* step_ctr, int x_index, int x_per_step, void* stream) {
   int rc = check_common(x, 1, K, group_size, nbits, 1);
   if (rc) return rc;
   HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: 1..4 matrices, non-null arrays");
@@ -113,7 +111,7 @@ extern "C" int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void
       return HQQ_E_UNSUPPORTED;
     }
   }
-  TpExchange t{tp, rank, peer_data, peer_flag, prod_ctr, red_data, red_flag, red_ctr};
+  TpExchange t{tp, rank, peer_data, red_data, step_ctr, x_index, x_per_step};
   return linear_small_multi(x, count, W_q, scale, zero, bias, y, N, 1, K, group_size, nbits, dtype, nullptr, 0, (cudaStream_t)stream, x_op, x2,
                             x_weight, h_out, eps, &t);
 }

@@ -30,11 +30,9 @@ namespace hqq {
 struct TpExchange {  // host-side view of the optional tensor-parallel exchange (see SKArgs)
   int tp, rank;
   void* const* peer_data;
-  int* const* peer_flag;
-  int* prod_ctr;
   const void* red_data;
-  const int* red_flag;
-  int* red_ctr;
+  const int* step_ctr;
+  int x_index, x_per_step;
 };
 
 constexpr int kMaxProb = 4;   // weight matrices sharing one activation in a single launch (q/k/v, gate/up)
@@ -66,19 +64,19 @@ struct SKArgs {
   const void* xw;
   void* h_out;
   float eps;
-  // optional tensor-parallel exchange over NVLink peer memory (M == 1 decode kernel, single matrix):
-  //   producer (row-parallel o / down): besides y, every result is stored into EVERY rank's exchange buffer
-  //     peer_data[dst][parity][rank][n]; when the whole grid is done the last CTA raises peer_flag[dst][rank] = epoch.
-  //   consumer (xop 1): instead of x2, sums red_data[parity][r][k] over the tp ranks after their flags reached the epoch.
-  // Epochs live in device memory (`*_ctr`) so a captured graph can be replayed; two parities because ranks may be one
-  // exchange apart.
+  // optional tensor-parallel exchange over NVLink peer memory (M == 1 decode kernel), "LL" style: every fp16/bf16 result
+  // travels as one 32-bit word {tag16 : value16}, written with a single store into EVERY rank's exchange buffer
+  // peer_data[dst][parity][rank][n]; a consumer polls the words until the tag matches -- no fences, no flags, no
+  // collective launch.  tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0
+  // (ranks can be at most one exchange apart).  *step_ctr lives in device memory and is bumped once per token by the
+  // last consumer, so a captured graph can be replayed.
+  //   producer (row-parallel o / down, single matrix): peer_data != null
+  //   consumer (xop 1): red_data != null, the residual delta is sum_r red_data[parity][r][k]
   int tp, rank;
-  void* peer_data[8];
-  int* peer_flag[8];
-  int* prod_ctr;       // [0] CTAs done, [1] epochs sent
-  const void* red_data;
-  const int* red_flag;
-  int* red_ctr;        // [0] CTAs done, [1] epochs consumed
+  uint32_t* peer_data[8];
+  const uint32_t* red_data;
+  const int* step_ctr;
+  int x_index, x_per_step;
 };
 
 template <typename T> struct MT16;
@@ -628,7 +626,12 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   for (int s = 0; s < ST - 1; ++s) issue(s);
   pdl_launch_dependents();
   pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
-  const int send_epoch = (a.tp > 1 && a.peer_data[0]) ? *reinterpret_cast<volatile int*>(a.prod_ctr + 1) + 1 : 0;
+  uint32_t send_tag = 0, send_par = 0;
+  if (a.tp > 1 && a.peer_data[0]) {
+    const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
+    send_tag = ex & 0xFFFFu;
+    send_par = ex & 1u;
+  }
 
   // ---- stage this warp's k-chunk of x (permuted: k -> k with bits 0 and 1 swapped) and its per-group sums ----------
   {
@@ -636,12 +639,12 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const T* x2 = reinterpret_cast<const T*>(a.x2);
     const int k_lo = kb0 * 256, k_hi = kb1 * 256;
     float inv = 1.0f;
-    const T* red = nullptr;  // this exchange's [tp][K] partial results, written into our memory by the peers
+    const uint32_t* red = nullptr;  // this exchange's [tp][K] tagged partial results, written into our memory by the peers
+    uint32_t rtag = 0;
     if (a.xop == 1 && a.red_data) {
-      const int epoch = *reinterpret_cast<volatile const int*>(a.red_ctr + 1) + 1;
-      if (tid < a.tp) { while (ld_acquire_sys(a.red_flag + tid) - epoch < 0) {} }
-      __syncthreads();
-      red = reinterpret_cast<const T*>(a.red_data) + (long long)(epoch & 1) * a.tp * a.K;
+      const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
+      rtag = ex & 0xFFFFu;
+      red = a.red_data + (size_t)(ex & 1u) * a.tp * a.K;
     }
     // delta of the residual stream: x2, or the sum of the tp partials (fp32 sum, rounded once like an all-reduce result)
     auto delta8 = [&](int k8, Vec<T, 8>& d) -> bool {
@@ -650,10 +653,21 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
         for (int rr = 0; rr < a.tp; ++rr) {
-          const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(red + (long long)rr * a.K + k8));
-          const Vec<T, 8> p8 = *reinterpret_cast<const Vec<T, 8>*>(&raw);
+          const uint32_t* src = red + (size_t)rr * a.K + k8;
+          uint4 w0, w1;
+          bool ok;
+          do {  // poll until all eight words carry this exchange's tag (they arrive over NVLink in any order)
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src) : "memory");
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 4) : "memory");
+            ok = ((w0.x >> 16) == rtag) & ((w0.y >> 16) == rtag) & ((w0.z >> 16) == rtag) & ((w0.w >> 16) == rtag) &
+                 ((w1.x >> 16) == rtag) & ((w1.y >> 16) == rtag) & ((w1.z >> 16) == rtag) & ((w1.w >> 16) == rtag);
+          } while (!ok);
+          const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += to_f32<T>(p8.v[j]);
+          for (int j = 0; j < 8; ++j) {
+            const unsigned short hb = (unsigned short)(ws[j] & 0xFFFFu);
+            acc[j] += to_f32<T>(*reinterpret_cast<const T*>(&hb));
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) d.v[j] = from_f32_t<T>(acc[j]);
@@ -789,38 +803,18 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
         const int n = ff * t.step + prow;
         MM::st(t.y, n, acc, t.bias, n);
         if (a.tp > 1 && a.peer_data[0]) {
-          // scatter the (bias-free) partial over NVLink: slot [parity][rank][n] of every rank's exchange buffer
+          // scatter the (bias-free) partial over NVLink as one tagged word per value: slot [parity][rank][n] on every rank
           const T pv = from_f32_t<T>(acc);
-          const long long off = ((long long)(send_epoch & 1) * a.tp + a.rank) * t.N + n;
+          const uint32_t word = (send_tag << 16) | (uint32_t)(*reinterpret_cast<const unsigned short*>(&pv));
+          const size_t off = ((size_t)send_par * a.tp + a.rank) * t.N + n;
 #pragma unroll
           for (int dst = 0; dst < 8; ++dst)
-            if (dst < a.tp) reinterpret_cast<T*>(a.peer_data[dst])[off] = pv;
+            if (dst < a.tp) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer_data[dst] + off), "r"(word) : "memory");
         }
       }
     }
   }
   cp_async_wait<0>();
-  if (a.tp > 1 && (a.peer_data[0] || a.red_data)) {
-    // grid-wide completion: the last CTA to get here publishes / retires the epoch (graph-replay safe: counters live in memory)
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      if (a.peer_data[0]) {
-        if (atomicAdd(a.prod_ctr, 1) == (int)gridDim.x - 1) {
-          a.prod_ctr[0] = 0;
-          a.prod_ctr[1] = send_epoch;
-          __threadfence_system();
-          for (int dst = 0; dst < a.tp; ++dst) st_release_sys(a.peer_flag[dst] + a.rank, send_epoch);
-        }
-      }
-      if (a.red_data) {
-        if (atomicAdd(a.red_ctr, 1) == (int)gridDim.x - 1) {
-          a.red_ctr[0] = 0;
-          a.red_ctr[1] = a.red_ctr[1] + 1;
-        }
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1032,26 +1026,21 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
   a.xop = xop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
-  a.tp = 1; a.rank = 0; a.prod_ctr = nullptr; a.red_data = nullptr; a.red_flag = nullptr; a.red_ctr = nullptr;
-  for (int i = 0; i < 8; ++i) { a.peer_data[i] = nullptr; a.peer_flag[i] = nullptr; }
+  a.tp = 1; a.rank = 0; a.red_data = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
+  for (int i = 0; i < 8; ++i) a.peer_data[i] = nullptr;
   if (tpx) {
     HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_tp: needs the M == 1 kernel");
-    HQQ_REQUIRE(tpx->tp >= 2 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: bad tp/rank");
-    a.tp = tpx->tp; a.rank = tpx->rank;
+    HQQ_REQUIRE(tpx->tp >= 2 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,
+                "hqq_b200_decode_linear_fwd_tp: bad tp/rank/step counter");
+    a.tp = tpx->tp; a.rank = tpx->rank; a.step_ctr = tpx->step_ctr; a.x_index = tpx->x_index; a.x_per_step = tpx->x_per_step;
     if (tpx->peer_data) {
-      HQQ_REQUIRE(nprob == 1 && tpx->peer_flag && tpx->prod_ctr, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: producer needs one matrix, flags and counters");
-      for (int i = 0; i < tpx->tp; ++i) { a.peer_data[i] = tpx->peer_data[i]; a.peer_flag[i] = tpx->peer_flag[i]; }
-      a.prod_ctr = tpx->prod_ctr;
+      HQQ_REQUIRE(nprob == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: the producer side takes exactly one matrix");
+      for (int i = 0; i < tpx->tp; ++i) a.peer_data[i] = reinterpret_cast<uint32_t*>(tpx->peer_data[i]);
     }
     if (tpx->red_data) {
-      HQQ_REQUIRE(xop == 1 && tpx->red_flag && tpx->red_ctr, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: consumer needs x_op 1, flags and counters");
-      a.red_data = tpx->red_data; a.red_flag = tpx->red_flag; a.red_ctr = tpx->red_ctr;
+      HQQ_REQUIRE(xop == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: the consumer side needs x_op 1");
+      a.red_data = reinterpret_cast<const uint32_t*>(tpx->red_data);
     }
-  }
-  if (xop != 0) {
-    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd: the activation prologue needs M == 1 and K <= 16384");
-    HQQ_REQUIRE((xop == 1 && xw) || (xop == 2 && x2), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: missing operand for x_op %d", xop);
-    HQQ_REQUIRE(aligned(x2, 16) && aligned(xw, 16) && aligned(h_out, 16), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: operands must be 16-byte aligned");
   }
   int tiles = 0;
   for (int i = 0; i < kMaxProb; ++i) {

@@ -190,33 +190,32 @@ class DecodeModel:
 
     def _setup_exchange(self):
         """Peer-mapped exchange buffers for the fused tensor-parallel all-reduce (`hqq_b200_decode_linear_fwd_tp`): one symmetric
-        allocation per rank holding, for the two row-parallel matrices of a block (o, down): data [2 parities][tp][hidden] and
-        tp ready-flags; the epoch counters stay in local memory."""
+        allocation per rank holding, for the two row-parallel matrices of a block (o, down), [2 parities][tp][hidden] tagged
+        32-bit words; the step counter the tags derive from stays in local memory."""
         import ctypes
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         s, tp, dev = self.shape, self.tp, self.device
-        es = torch.finfo(self.dtype).bits // 8
-        data_bytes = (2 * tp * s.hidden * es + 255) // 256 * 256
-        slot_bytes = data_bytes + 256
+        slot_bytes = 2 * tp * s.hidden * 4
         buf = symm.empty(2 * slot_bytes, dtype=torch.uint8, device=dev)
-        buf.zero_()
+        buf.fill_(0xFF)  # tag 0xFFFF is only reached after 65535 exchanges; by then every word has been overwritten
         hdl = symm.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         self._xbuf, self._xhdl = buf, hdl
-        self._xctr = torch.zeros(2, 4, dtype=torch.int32, device=dev)
+        self._xstep = torch.zeros(1, dtype=torch.int32, device=dev)
         VP = ctypes.c_void_p * tp
-        self._tp_prod, self._tp_cons, self._tp_keep = [], [], []
-        for slot in range(2):
-            pd = VP(*[p + slot * slot_bytes for p in ptrs])
-            pf = VP(*[p + slot * slot_bytes + data_bytes for p in ptrs])
-            self._tp_keep += [pd, pf]
-            ctr = self._xctr[slot].data_ptr()
-            self._tp_prod.append({"tp": tp, "rank": self.rank, "peer_data": pd, "peer_flag": pf, "prod_ctr": ctr})
-            self._tp_cons.append({"tp": tp, "rank": self.rank, "red_data": ptrs[self.rank] + slot * slot_bytes,
-                                  "red_flag": ptrs[self.rank] + slot * slot_bytes + data_bytes, "red_ctr": ctr + 8})
+        self._tp_keep = [VP(*[p + slot * slot_bytes for p in ptrs]) for slot in range(2)]
+        self._tp_local = [ptrs[self.rank] + slot * slot_bytes for slot in range(2)]
         torch.cuda.synchronize(dev)
         dist.barrier()
+
+    def _tpx(self, slot, block, producer):
+        d = {"tp": self.tp, "rank": self.rank, "step_ctr": self._xstep.data_ptr(), "x_index": block + 1, "x_per_step": len(self.blocks)}
+        if producer:
+            d["peer_data"] = self._tp_keep[slot]
+        else:
+            d["red_data"] = self._tp_local[slot]
+        return d
 
     def step_fused5(self):
         """Five launches per block: [add+RMSNorm -> q/k/v], RoPE+cache+attention, o, [add+RMSNorm -> gate/up],
@@ -232,33 +231,29 @@ class DecodeModel:
         delta = None
         ok = True
         p2p = self.tp > 1 and self.tp_mode == "p2p"
-        prod_o, prod_d = (self._tp_prod if p2p else (None, None))
-        cons_o, cons_d = (self._tp_cons if p2p else (None, None))
-        first = True
-        for blk in self.blocks:
-            # [residual add + RMSNorm] -> q/k/v.  With p2p the delta is the sum of the ranks' down-proj partials.
+        nb = len(self.blocks)
+        for bi, blk in enumerate(self.blocks):
+            # [residual add + RMSNorm] -> q/k/v.  With p2p the delta is the sum of the ranks' down-proj partials of block bi-1.
             ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None if p2p else delta, blk["norm1"], h_nxt,
-                                        s.rms_eps, tpx=(cons_d if (p2p and not first) else None))
+                                        s.rms_eps, tpx=(self._tpx(1, bi - 1, False) if (p2p and bi > 0) else None))
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=prod_o)
+            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=(self._tpx(0, bi, True) if p2p else None))
             if self.tp > 1 and not p2p:
                 torch.distributed.all_reduce(b["o"], group=self.pg)
             ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None if p2p else b["o"], blk["norm2"], h_nxt, s.rms_eps,
-                                        tpx=cons_o)
+                                        tpx=(self._tpx(0, bi, False) if p2p else None))
             h_cur, h_nxt = h_nxt, h_cur
-            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=prod_d)
+            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=(self._tpx(1, bi, True) if p2p else None))
             if self.tp > 1 and not p2p:
                 torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
-            first = False
         if not ok:
             raise RuntimeError("hqq_b200: this model shape is outside the fused M=1 decode kernel; use fused=False or step_fused")
         if p2p:
-            c = cons_d
-            check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), c["red_data"], c["red_flag"], c["red_ctr"], self.tp, ptr(self.final_norm), ptr(b["x"]),
-                                                   s.hidden, s.rms_eps, code, st))
+            check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), self._tp_local[1], self._xstep.data_ptr(), nb, nb, self.tp, ptr(self.final_norm),
+                                                   ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         else:
             check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])

@@ -225,8 +225,8 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
 def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None) -> bool:
     """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
     residual add + RMSNorm, 2 = SiLU(x) * x2.  `tpx` (dict) switches on the peer-memory exchange of
-    `hqq_b200_decode_linear_fwd_tp`: keys tp, rank and either peer_data/peer_flag/prod_ctr (producer: ctypes pointer arrays and an
-    int address) or red_data/red_flag/red_ctr (consumer: int addresses).  Returns False when the configuration is outside the
+    `hqq_b200_decode_linear_fwd_tp`: keys tp, rank, step_ctr, x_index, x_per_step and peer_data (producer: ctypes array of peer
+    pointers) or red_data (consumer: address of the local exchange region).  Returns False when the configuration is outside the
     fused M = 1 kernel."""
     import ctypes
     lib = load()
@@ -249,8 +249,8 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
         rc = lib.hqq_b200_decode_linear_fwd_tp(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
                                                arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
                                                arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
-                                               int(tpx["tp"]), int(tpx["rank"]), tpx.get("peer_data"), tpx.get("peer_flag"), tpx.get("prod_ctr"),
-                                               tpx.get("red_data"), tpx.get("red_flag"), tpx.get("red_ctr"), stream_ptr(x.device))
+                                               int(tpx["tp"]), int(tpx["rank"]), tpx.get("peer_data"), tpx.get("red_data"), tpx["step_ctr"],
+                                               int(tpx["x_index"]), int(tpx["x_per_step"]), stream_ptr(x.device))
     if rc == HQQ_E_UNSUPPORTED:
         return False
     check(rc)

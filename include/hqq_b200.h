@@ -159,22 +159,22 @@ int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const vo
                                const void* const* bias, void* const* y, const int64_t* N, int64_t K,
                                int group_size, int nbits, int dtype, void* stream);
 /* Tensor-parallel variant (SURVEY.md 8e, row-parallel o_proj / down_proj): the all-reduce of the [1, hidden] partial is
- * fused into the kernels that produce and consume it, over NVLink peer memory (no collective launch):
- *   producer  (peer_data != NULL, count == 1): every result is also stored to peer_data[dst][parity][rank][n] of all `tp`
- *             ranks; the last CTA of the grid then raises peer_flag[dst][rank] = epoch (st.release.sys).
- *   consumer  (red_data != NULL, x_op == 1): the residual delta is sum_r red_data[parity][r][k] once red_flag[r] has
- *             reached the epoch (ld.acquire.sys); the last CTA retires the epoch.
- * peer_data / peer_flag are arrays of `tp` device pointers into symmetric (peer-mapped) allocations; prod_ctr / red_ctr are
- * int[2] in local device memory, zero-initialised once (CTAs-done counter, epoch).  Epochs live in memory, so a captured
- * graph can be replayed; two parities because ranks can be at most one exchange apart.                                   */
+ * fused into the kernels that produce and consume it, over NVLink peer memory (no collective launch, no fences).  Every
+ * value travels as one 32-bit word {tag16 : value16} ("LL" protocol):
+ *   producer  (peer_data != NULL, count == 1): every result is also stored to peer_data[dst][parity][rank][n] of all `tp` ranks
+ *   consumer  (red_data != NULL, x_op == 1): the residual delta is sum_r red_data[parity][r][k]; words are polled until their
+ *             tag matches.
+ * tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0 (ranks are at most one exchange
+ * apart).  peer_data: `tp` device pointers into symmetric (peer-mapped) allocations of 2*tp*N uint32 each; step_ctr: an int in
+ * local device memory that hqq_b200_glue_add_rmsnorm_tp bumps once per token, so a captured graph can be replayed.            */
 int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps,
                                   int count, const void* const* W_q, const void* const* scale, const void* const* zero,
                                   const void* const* bias, void* const* y, const int64_t* N, int64_t K,
                                   int group_size, int nbits, int dtype, int tp, int rank,
-                                  void* const* peer_data, int* const* peer_flag, int* prod_ctr,
-                                  const void* red_data, const int* red_flag, int* red_ctr, void* stream);
-/* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight */
-int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, const int* red_flag, int* red_ctr, int tp,
+                                  void* const* peer_data, const void* red_data, const int* step_ctr,
+                                  int x_index, int x_per_step, void* stream);
+/* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */
+int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp,
                                  const void* weight, void* y, int H, float eps, int dtype, void* stream);
 /* h += delta (delta may be NULL);  y = rmsnorm(h) * weight          (one token, H <= 8192) */
 int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y,
