@@ -78,3 +78,15 @@ def test_decode_graph_fused_equals_framework_ops():
     agree = sum(int(x == y) for x, y in zip(t8, tref))
     assert agree >= 10, (t8, tref)  # fp16 reorderings may flip a near-tie late in the sequence, never the early tokens
     assert t8[:4] == tref[:4]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (the fused NVLink exchange is exercised by tools/tp_check.py under gpurun --gpus 2)")
+def test_tensor_parallel_peer_exchange_matches_nccl():
+    """TP=2: the all-reduce fused into the row-parallel kernels over peer memory produces the same tokens as NCCL all-reduce."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(root, "tools", "tp_check.py")], capture_output=True, text=True, timeout=300)
+    assert "AGREE 16 of 16" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
