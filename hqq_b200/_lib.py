@@ -43,9 +43,7 @@ SIGNATURES = {
     "hqq_b200_linear_fwd_route": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "hqq_b200_decode_linear_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
-    "hqq_b200_decode_linear_fwd_tp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                              c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                              c_int, c_int, c_void_p]),
+    "hqq_b200_decode_linear_fwd_desc": (c_int, [c_void_p, c_void_p]),
     "hqq_b200_glue_add_rmsnorm_tp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_silu_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -55,6 +53,15 @@ SIGNATURES = {
     "hqq_b200_launch_count": (c_int64, []),
     "hqq_b200_launch_count_reset": (None, []),
 }
+
+
+class DecodeDesc(ctypes.Structure):
+    """Mirror of `hqq_b200_decode_desc` (include/hqq_b200.h)."""
+    _fields_ = [("x", c_void_p), ("x_op", c_int), ("x2", c_void_p), ("x_weight", c_void_p), ("h_out", c_void_p), ("eps", c_float),
+                ("count", c_int), ("W_q", c_void_p), ("scale", c_void_p), ("zero", c_void_p), ("bias", c_void_p), ("y", c_void_p),
+                ("N", c_void_p), ("K", c_int64), ("group_size", c_int), ("nbits", c_int), ("dtype", c_int), ("tp", c_int), ("rank", c_int),
+                ("peer_data", c_void_p), ("red_data", c_void_p), ("y_tagged", c_void_p), ("x_tagged", c_void_p), ("x2_tagged", c_void_p),
+                ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int), ("skip_wait", c_int)]
 
 
 class HQQB200Error(RuntimeError):

@@ -234,7 +234,7 @@ extern "C" int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void*
 
 extern "C" int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp, const void* weight,
                                             void* y, int H, float eps, int dtype, void* stream) {
-  HQQ_REQUIRE(h && red_data && step_ctr && weight && y && H > 0 && H <= 8 * 1024 && tp >= 2 && tp <= 8 && x_per_step > 0, HQQ_E_INVALID,
+  HQQ_REQUIRE(h && red_data && step_ctr && weight && y && H > 0 && H <= 8 * 1024 && tp >= 1 && tp <= 8 && x_per_step > 0, HQQ_E_INVALID,
               "hqq_b200_glue_add_rmsnorm_tp: bad arguments (H=%d tp=%d)", H, tp);
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = H >= 4096 ? 1024 : 256;

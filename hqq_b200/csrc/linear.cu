@@ -6,8 +6,11 @@ struct TpExchange {
   int tp, rank;
   void* const* peer_data;
   const void* red_data;
+  void* const* y_tagged;
+  const void* x_tagged;
+  const void* x2_tagged;
   const int* step_ctr;
-  int x_index, x_per_step;
+  int x_index, x_per_step, skip_wait;
 };
 bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t small_workspace_bytes(int64_t M);
@@ -95,23 +98,25 @@ extern "C" int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x
                             x_weight, h_out, eps);
 }
 
-extern "C" int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps, int count,
-                                             const void* const* W_q, const void* const* scale, const void* const* zero,
-                                             const void* const* bias, void* const* y, const int64_t* N, int64_t K, int group_size,
-                                             int nbits, int dtype, int tp, int rank, void* const* peer_data, const void* red_data,
-                                             const int* step_ctr, int x_index, int x_per_step, void* stream) {
-  int rc = check_common(x, 1, K, group_size, nbits, 1);
+extern "C" int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* d, void* stream) {
+  HQQ_REQUIRE(d != nullptr, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: null descriptor");
+  int rc = check_common(d->x ? d->x : d->x_tagged, 1, d->K, d->group_size, d->nbits, 1);
   if (rc) return rc;
-  HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: 1..4 matrices, non-null arrays");
-  HQQ_REQUIRE(x_op >= 0 && x_op <= 2, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: x_op must be 0, 1 or 2");
-  for (int i = 0; i < count; ++i) {
-    if (!small_route_ok(1, N[i], K, group_size, nbits, 1, dtype) || !small_xop_ok(1, K)) {
-      set_error("hqq_b200_decode_linear_fwd_tp: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i,
-                (long long)N[i], (long long)K, group_size, nbits, dtype);
+  HQQ_REQUIRE(d->count >= 1 && d->count <= 4 && d->W_q && d->scale && d->zero && d->y && d->N, HQQ_E_INVALID,
+              "hqq_b200_decode_linear_fwd_desc: 1..4 matrices, non-null arrays");
+  HQQ_REQUIRE(d->x_op >= 0 && d->x_op <= 2, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: x_op must be 0, 1 or 2");
+  HQQ_REQUIRE(d->x || (d->x_op == 2 && d->x_tagged), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: no activation given");
+  for (int i = 0; i < d->count; ++i) {
+    if (!small_route_ok(1, d->N[i], d->K, d->group_size, d->nbits, 1, d->dtype) || !small_xop_ok(1, d->K)) {
+      set_error("hqq_b200_decode_linear_fwd_desc: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i,
+                (long long)d->N[i], (long long)d->K, d->group_size, d->nbits, d->dtype);
       return HQQ_E_UNSUPPORTED;
     }
   }
-  TpExchange t{tp, rank, peer_data, red_data, step_ctr, x_index, x_per_step};
-  return linear_small_multi(x, count, W_q, scale, zero, bias, y, N, 1, K, group_size, nbits, dtype, nullptr, 0, (cudaStream_t)stream, x_op, x2,
-                            x_weight, h_out, eps, &t);
+  TpExchange t{d->tp, d->rank, d->peer_data, d->red_data, d->y_tagged, d->x_tagged, d->x2_tagged, d->step_ctr, d->x_index, d->x_per_step, d->skip_wait};
+  const bool exchange = d->step_ctr != nullptr;
+  // a tagged x still needs a mapped pointer for the alignment checks / unused plain path: reuse the tagged buffer itself
+  const void* x = d->x ? d->x : d->x_tagged;
+  return linear_small_multi(x, d->count, d->W_q, d->scale, d->zero, d->bias, d->y, d->N, 1, d->K, d->group_size, d->nbits, d->dtype, nullptr, 0,
+                            (cudaStream_t)stream, d->x_op, d->x2, d->x_weight, d->h_out, d->eps, exchange ? &t : nullptr);
 }

@@ -27,12 +27,15 @@
 
 namespace hqq {
 
-struct TpExchange {  // host-side view of the optional tensor-parallel exchange (see SKArgs)
+struct TpExchange {  // host-side view of the optional tagged-word exchange (see SKArgs)
   int tp, rank;
   void* const* peer_data;
   const void* red_data;
+  void* const* y_tagged;
+  const void* x_tagged;
+  const void* x2_tagged;
   const int* step_ctr;
-  int x_index, x_per_step;
+  int x_index, x_per_step, skip_wait;
 };
 
 constexpr int kMaxProb = 4;   // weight matrices sharing one activation in a single launch (q/k/v, gate/up)
@@ -43,6 +46,7 @@ struct SKProb {
   const void* zero;
   const void* bias;
   void* y;
+  uint32_t* ytag;  // optional tagged copy of the output [2 parities][N] (see the exchange notes in SKArgs)
   int N;
   int step;   // packed rows = N / F
   int tile0;  // first global 16-row tile of this matrix
@@ -72,11 +76,18 @@ struct SKArgs {
   // last consumer, so a captured graph can be replayed.
   //   producer (row-parallel o / down, single matrix): peer_data != null
   //   consumer (xop 1): red_data != null, the residual delta is sum_r red_data[parity][r][k]
+  // The same tagged words chain kernels on ONE GPU: a producer may keep a tagged copy of its outputs (SKProb::ytag) and a
+  // consumer may take x / x2 of the SiLU*mul prologue from tagged buffers (xtag / x2tag) or its residual delta from
+  // red_data with tp == 1.  A consumer whose only inputs from the preceding kernel are tagged can skip griddepcontrol.wait
+  // (skip_wait) and overlap that kernel's tail: the polling is the synchronisation.
   int tp, rank;
   uint32_t* peer_data[8];
   const uint32_t* red_data;
+  const uint32_t* xtag;
+  const uint32_t* x2tag;
   const int* step_ctr;
   int x_index, x_per_step;
+  int skip_wait;
 };
 
 template <typename T> struct MT16;
@@ -548,19 +559,19 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   const int n_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_tiles <= 0) return;
 
-  struct Tile { const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y; int N, step, tile0; };
+  struct Tile { const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y; uint32_t* ytag; int N, step, tile0; };
   auto locate = [&](int gt, Tile& t) {
     int pi = 0;
 #pragma unroll
     for (int i = 1; i < kMaxProb; ++i)
       if (i < a.nprob && gt >= a.p[i].tile0) pi = i;
     const uint8_t* Wq = a.p[0].Wq; const void* sc = a.p[0].scale; const void* ze = a.p[0].zero; const void* bi = a.p[0].bias;
-    void* y = a.p[0].y; int N = a.p[0].N, step = a.p[0].step, tile0 = a.p[0].tile0;
+    void* y = a.p[0].y; uint32_t* yt = a.p[0].ytag; int N = a.p[0].N, step = a.p[0].step, tile0 = a.p[0].tile0;
 #pragma unroll
     for (int i = 1; i < kMaxProb; ++i)
-      if (pi == i) { Wq = a.p[i].Wq; sc = a.p[i].scale; ze = a.p[i].zero; bi = a.p[i].bias; y = a.p[i].y; N = a.p[i].N; step = a.p[i].step; tile0 = a.p[i].tile0; }
+      if (pi == i) { Wq = a.p[i].Wq; sc = a.p[i].scale; ze = a.p[i].zero; bi = a.p[i].bias; y = a.p[i].y; yt = a.p[i].ytag; N = a.p[i].N; step = a.p[i].step; tile0 = a.p[i].tile0; }
     t.Wq = Wq; t.scale = reinterpret_cast<const T*>(sc); t.zero = reinterpret_cast<const T*>(ze);
-    t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.N = N; t.step = step; t.tile0 = tile0;
+    t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.ytag = yt; t.N = N; t.step = step; t.tile0 = tile0;
   };
 
   int i_tile = 0, i_k = 0;
@@ -625,9 +636,9 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue(s);
   pdl_launch_dependents();
-  pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
-  uint32_t send_tag = 0, send_par = 0;
-  if (a.tp > 1 && a.peer_data[0]) {
+  if (!a.skip_wait) pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
+  uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
+  if (a.step_ctr) {
     const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
     send_tag = ex & 0xFFFFu;
     send_par = ex & 1u;
@@ -640,12 +651,25 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const int k_lo = kb0 * 256, k_hi = kb1 * 256;
     float inv = 1.0f;
     const uint32_t* red = nullptr;  // this exchange's [tp][K] tagged partial results, written into our memory by the peers
-    uint32_t rtag = 0;
-    if (a.xop == 1 && a.red_data) {
-      const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
-      rtag = ex & 0xFFFFu;
-      red = a.red_data + (size_t)(ex & 1u) * a.tp * a.K;
-    }
+    const uint32_t rtag = send_tag;
+    if (a.xop == 1 && a.red_data) red = a.red_data + (size_t)send_par * a.tp * a.K;
+    // poll eight consecutive tagged words until they all carry this exchange's tag (they may arrive in any order)
+    auto poll8 = [&](const uint32_t* src, Vec<T, 8>& out) {
+      uint4 w0, w1;
+      bool ok;
+      do {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 4) : "memory");
+        ok = ((w0.x >> 16) == rtag) & ((w0.y >> 16) == rtag) & ((w0.z >> 16) == rtag) & ((w0.w >> 16) == rtag) &
+             ((w1.x >> 16) == rtag) & ((w1.y >> 16) == rtag) & ((w1.z >> 16) == rtag) & ((w1.w >> 16) == rtag);
+      } while (!ok);
+      const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned short hb = (unsigned short)(ws[j] & 0xFFFFu);
+        out.v[j] = *reinterpret_cast<const T*>(&hb);
+      }
+    };
     // delta of the residual stream: x2, or the sum of the tp partials (fp32 sum, rounded once like an all-reduce result)
     auto delta8 = [&](int k8, Vec<T, 8>& d) -> bool {
       if (red) {
@@ -653,21 +677,10 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
         for (int rr = 0; rr < a.tp; ++rr) {
-          const uint32_t* src = red + (size_t)rr * a.K + k8;
-          uint4 w0, w1;
-          bool ok;
-          do {  // poll until all eight words carry this exchange's tag (they arrive over NVLink in any order)
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src) : "memory");
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 4) : "memory");
-            ok = ((w0.x >> 16) == rtag) & ((w0.y >> 16) == rtag) & ((w0.z >> 16) == rtag) & ((w0.w >> 16) == rtag) &
-                 ((w1.x >> 16) == rtag) & ((w1.y >> 16) == rtag) & ((w1.z >> 16) == rtag) & ((w1.w >> 16) == rtag);
-          } while (!ok);
-          const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          Vec<T, 8> p8;
+          poll8(red + (size_t)rr * a.K + k8, p8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const unsigned short hb = (unsigned short)(ws[j] & 0xFFFFu);
-            acc[j] += to_f32<T>(*reinterpret_cast<const T*>(&hb));
-          }
+          for (int j = 0; j < 8; ++j) acc[j] += to_f32<T>(p8.v[j]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) d.v[j] = from_f32_t<T>(acc[j]);
@@ -703,7 +716,9 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     }
     const T* xw = reinterpret_cast<const T*>(a.xw);
     for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
-      Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+      Vec<T, 8> v;
+      if (a.xop == 2 && a.xtag) poll8(a.xtag + (size_t)send_par * a.K + k8, v);
+      else v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
       if (a.xop == 1) {
         Vec<T, 8> d;
         if (delta8(k8, d)) {
@@ -714,7 +729,9 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(to_f32<T>(v.v[j]) * inv)) * to_f32<T>(g.v[j]));
       } else if (a.xop == 2) {
-        const Vec<T, 8> u = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+        Vec<T, 8> u;
+        if (a.x2tag) poll8(a.x2tag + (size_t)send_par * a.K + k8, u);
+        else u = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float f = to_f32<T>(v.v[j]);
@@ -802,14 +819,17 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
         for (int w = 0; w < 8; ++w) acc += buf[w * 16 + lane];
         const int n = ff * t.step + prow;
         MM::st(t.y, n, acc, t.bias, n);
-        if (a.tp > 1 && a.peer_data[0]) {
-          // scatter the (bias-free) partial over NVLink as one tagged word per value: slot [parity][rank][n] on every rank
+        if (a.peer_data[0] || t.ytag) {
           const T pv = from_f32_t<T>(acc);
           const uint32_t word = (send_tag << 16) | (uint32_t)(*reinterpret_cast<const unsigned short*>(&pv));
-          const size_t off = ((size_t)send_par * a.tp + a.rank) * t.N + n;
+          if (a.peer_data[0]) {
+            // scatter the (bias-free) partial over NVLink as one tagged word per value: slot [parity][rank][n] on every rank
+            const size_t off = ((size_t)send_par * a.tp + a.rank) * t.N + n;
 #pragma unroll
-          for (int dst = 0; dst < 8; ++dst)
-            if (dst < a.tp) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer_data[dst] + off), "r"(word) : "memory");
+            for (int dst = 0; dst < 8; ++dst)
+              if (dst < a.tp) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer_data[dst] + off), "r"(word) : "memory");
+          }
+          if (t.ytag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(t.ytag + (size_t)send_par * t.N + n), "r"(word) : "memory");
         }
       }
     }
@@ -1026,20 +1046,26 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
   a.xop = xop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
-  a.tp = 1; a.rank = 0; a.red_data = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
+  a.tp = 1; a.rank = 0; a.red_data = nullptr; a.xtag = nullptr; a.x2tag = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
+  a.skip_wait = 0;
   for (int i = 0; i < 8; ++i) a.peer_data[i] = nullptr;
   if (tpx) {
-    HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_tp: needs the M == 1 kernel");
-    HQQ_REQUIRE(tpx->tp >= 2 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,
-                "hqq_b200_decode_linear_fwd_tp: bad tp/rank/step counter");
+    HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
+    HQQ_REQUIRE(tpx->tp >= 1 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,
+                "hqq_b200_decode_linear_fwd_desc: bad tp/rank/step counter");
     a.tp = tpx->tp; a.rank = tpx->rank; a.step_ctr = tpx->step_ctr; a.x_index = tpx->x_index; a.x_per_step = tpx->x_per_step;
+    a.skip_wait = tpx->skip_wait ? 1 : 0;
     if (tpx->peer_data) {
-      HQQ_REQUIRE(nprob == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: the producer side takes exactly one matrix");
+      HQQ_REQUIRE(nprob == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: the scatter side takes exactly one matrix");
       for (int i = 0; i < tpx->tp; ++i) a.peer_data[i] = reinterpret_cast<uint32_t*>(tpx->peer_data[i]);
     }
     if (tpx->red_data) {
-      HQQ_REQUIRE(xop == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_tp: the consumer side needs x_op 1");
+      HQQ_REQUIRE(xop == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: a reduced delta needs x_op 1");
       a.red_data = reinterpret_cast<const uint32_t*>(tpx->red_data);
+    }
+    if (tpx->x_tagged || tpx->x2_tagged) {
+      HQQ_REQUIRE(xop == 2 && tpx->x_tagged && tpx->x2_tagged, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: tagged activations need x_op 2 and both operands");
+      a.xtag = reinterpret_cast<const uint32_t*>(tpx->x_tagged); a.x2tag = reinterpret_cast<const uint32_t*>(tpx->x2_tagged);
     }
   }
   int tiles = 0;
@@ -1049,7 +1075,7 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     HQQ_REQUIRE(aligned(Wq[j], 16) && aligned(scale[j], 8) && aligned(zero[j], 8), HQQ_E_INVALID,
                 "hqq_b200_linear_fwd: W_q must be 16-byte and scale/zero 8-byte aligned");
     a.p[i].Wq = (const uint8_t*)Wq[j]; a.p[i].scale = scale[j]; a.p[i].zero = zero[j]; a.p[i].bias = bias ? bias[j] : nullptr;
-    a.p[i].y = y[j]; a.p[i].N = (int)N[j]; a.p[i].step = (int)(N[j] / F); a.p[i].tile0 = tiles;
+    a.p[i].y = y[j]; a.p[i].ytag = (tpx && tpx->y_tagged) ? reinterpret_cast<uint32_t*>(tpx->y_tagged[j]) : nullptr; a.p[i].N = (int)N[j]; a.p[i].step = (int)(N[j] / F); a.p[i].tile0 = tiles;
     if (i < nprob) tiles += (int)cdiv(a.p[i].step, P);
   }
   a.total_tiles = tiles;

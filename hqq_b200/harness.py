@@ -63,7 +63,8 @@ class DecodeModel:
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
         self.fused = fused
         import os
-        self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")
+        self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")  # "p2p": tagged-word chaining / fused exchange; "nccl": plain
+        self.skip_wait = int(os.environ.get("HQQ_B200_SKIP_WAIT", "1"))
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
         self.n_layers = n_layers if n_layers is not None else shape.n_layers
@@ -189,32 +190,37 @@ class DecodeModel:
         self.pos.add_(1).remainder_(self.cache_len)
 
     def _setup_exchange(self):
-        """Peer-mapped exchange buffers for the fused tensor-parallel all-reduce (`hqq_b200_decode_linear_fwd_tp`): one symmetric
-        allocation per rank holding, for the two row-parallel matrices of a block (o, down), [2 parities][tp][hidden] tagged
-        32-bit words; the step counter the tags derive from stays in local memory."""
+        """Buffers of tagged 32-bit words {tag16 : value16} through which the one-token kernels hand activations to each other
+        (`hqq_b200_decode_linear_fwd_desc`): o / down partials [2 parities][tp][hidden] -- peer-mapped symmetric memory when tp > 1,
+        so the scatter + reduce IS the tensor-parallel all-reduce -- and gate / up [2][inter/tp] (local).  The step counter the
+        tags derive from lives in local memory."""
         import ctypes
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
         s, tp, dev = self.shape, self.tp, self.device
         slot_bytes = 2 * tp * s.hidden * 4
-        buf = symm.empty(2 * slot_bytes, dtype=torch.uint8, device=dev)
-        buf.fill_(0xFF)  # tag 0xFFFF is only reached after 65535 exchanges; by then every word has been overwritten
-        hdl = symm.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        self._xbuf, self._xhdl = buf, hdl
+        if tp > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(2 * slot_bytes, dtype=torch.uint8, device=dev)
+            buf.fill_(0xFF)  # tag 0xFFFF is only reached after 65535 exchanges; by then every word has been overwritten
+            hdl = symm.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self._xhdl = hdl
+        else:
+            buf = torch.full((2 * slot_bytes,), 0xFF, dtype=torch.uint8, device=dev)
+            ptrs = [buf.data_ptr()]
+        self._xbuf = buf
+        self._xact = torch.full((2, 2, s.inter // tp), -1, dtype=torch.int32, device=dev)  # gate, up: [2 parities][inter/tp] words each
         self._xstep = torch.zeros(1, dtype=torch.int32, device=dev)
         VP = ctypes.c_void_p * tp
         self._tp_keep = [VP(*[p + slot * slot_bytes for p in ptrs]) for slot in range(2)]
         self._tp_local = [ptrs[self.rank] + slot * slot_bytes for slot in range(2)]
         torch.cuda.synchronize(dev)
-        dist.barrier()
+        if tp > 1:
+            dist.barrier()
 
-    def _tpx(self, slot, block, producer):
+    def _tpx(self, block, **kw):
         d = {"tp": self.tp, "rank": self.rank, "step_ctr": self._xstep.data_ptr(), "x_index": block + 1, "x_per_step": len(self.blocks)}
-        if producer:
-            d["peer_data"] = self._tp_keep[slot]
-        else:
-            d["red_data"] = self._tp_local[slot]
+        d.update(kw)
         return d
 
     def step_fused5(self):
@@ -230,29 +236,45 @@ class DecodeModel:
         torch.index_select(self.embed, 0, self.tok, out=h_cur)
         delta = None
         ok = True
-        p2p = self.tp > 1 and self.tp_mode == "p2p"
+        chain = self.tp_mode == "p2p"  # tagged-word chaining (and, with tp > 1, the fused NVLink all-reduce)
         nb = len(self.blocks)
+        if chain:
+            o_sc, d_sc = self._tp_keep            # scatter targets (every rank's buffer) for o / down
+            o_loc, d_loc = self._tp_local         # this rank's buffers
+            g_tag, u_tag = self._xact[0].data_ptr(), self._xact[1].data_ptr()
         for bi, blk in enumerate(self.blocks):
-            # [residual add + RMSNorm] -> q/k/v.  With p2p the delta is the sum of the ranks' down-proj partials of block bi-1.
-            ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None if p2p else delta, blk["norm1"], h_nxt,
-                                        s.rms_eps, tpx=(self._tpx(1, bi - 1, False) if (p2p and bi > 0) else None))
+            if chain:
+                # [residual add + RMSNorm] -> q/k/v; the delta is the sum of the ranks' down-proj partials of block bi-1
+                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None, blk["norm1"], h_nxt, s.rms_eps,
+                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None))
+            else:
+                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps)
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=(self._tpx(0, bi, True) if p2p else None))
-            if self.tp > 1 and not p2p:
-                torch.distributed.all_reduce(b["o"], group=self.pg)
-            ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None if p2p else b["o"], blk["norm2"], h_nxt, s.rms_eps,
-                                        tpx=(self._tpx(0, bi, False) if p2p else None))
-            h_cur, h_nxt = h_nxt, h_cur
-            ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=(self._tpx(1, bi, True) if p2p else None))
-            if self.tp > 1 and not p2p:
-                torch.distributed.all_reduce(b["down"], group=self.pg)
+            if chain:
+                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc))
+                # the next two kernels take everything the preceding kernel produces as tagged words: they skip the
+                # programmatic-dependency wait and start streaming their weights under its tail
+                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
+                                            tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait))
+                h_cur, h_nxt = h_nxt, h_cur
+                ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
+                                            tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait))
+            else:
+                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
+                if self.tp > 1:
+                    torch.distributed.all_reduce(b["o"], group=self.pg)
+                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
+                h_cur, h_nxt = h_nxt, h_cur
+                ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
+                if self.tp > 1:
+                    torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
         if not ok:
             raise RuntimeError("hqq_b200: this model shape is outside the fused M=1 decode kernel; use fused=False or step_fused")
-        if p2p:
-            check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), self._tp_local[1], self._xstep.data_ptr(), nb, nb, self.tp, ptr(self.final_norm),
+        if chain:
+            check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), d_loc, self._xstep.data_ptr(), nb, nb, self.tp, ptr(self.final_norm),
                                                    ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         else:
             check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
@@ -273,11 +295,11 @@ class DecodeModel:
         fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
-        if self.tp > 1 and fused and self.fused == 5 and self.tp_mode == "p2p" and not hasattr(self, "_xbuf"):
+        if fused and self.fused == 5 and self.tp_mode == "p2p" and not hasattr(self, "_xbuf"):
             try:
                 self._setup_exchange()
-            except Exception as e:  # symmetric memory unavailable -> NCCL all-reduce between the kernels
-                print(f"hqq_b200: peer-memory exchange unavailable ({e}); using NCCL all-reduce")
+            except Exception as e:  # symmetric memory unavailable -> plain buffers (+ NCCL all-reduce when tp > 1)
+                print(f"hqq_b200: tagged exchange unavailable ({e}); using plain buffers / NCCL all-reduce")
                 self.tp_mode = "nccl"
         step = (self.step_fused5 if self.fused == 5 else self.step_fused) if fused else self.step
         st = torch.cuda.Stream(device=self.device)

@@ -225,9 +225,9 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
 def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None) -> bool:
     """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
     residual add + RMSNorm, 2 = SiLU(x) * x2.  `tpx` (dict) switches on the peer-memory exchange of
-    `hqq_b200_decode_linear_fwd_tp`: keys tp, rank, step_ctr, x_index, x_per_step and peer_data (producer: ctypes array of peer
-    pointers) or red_data (consumer: address of the local exchange region).  Returns False when the configuration is outside the
-    fused M = 1 kernel."""
+    `hqq_b200_decode_linear_fwd_desc`: keys tp, rank, step_ctr, x_index, x_per_step and any of peer_data (ctypes array of peer
+    pointers), red_data, y_tagged (list of addresses), x_tagged, x2_tagged (addresses), skip_wait.  Returns False when the
+    configuration is outside the fused M = 1 kernel."""
     import ctypes
     lib = load()
     n = len(layers)
@@ -246,11 +246,18 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
                                             arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
                                             stream_ptr(x.device))
     else:
-        rc = lib.hqq_b200_decode_linear_fwd_tp(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
-                                               arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
-                                               arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
-                                               int(tpx["tp"]), int(tpx["rank"]), tpx.get("peer_data"), tpx.get("red_data"), tpx["step_ctr"],
-                                               int(tpx["x_index"]), int(tpx["x_per_step"]), stream_ptr(x.device))
+        cast = lambda a: ctypes.cast(a, ctypes.c_void_p) if a is not None else None
+        arrays = [arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
+                  arr([l.bias for l in layers]), arr(outs)]
+        ytag = tpx.get("y_tagged")
+        ytag_arr = VP(*ytag) if ytag is not None else None
+        d = _lib.DecodeDesc(x=ptr(x), x_op=int(x_op), x2=ptr(x2), x_weight=ptr(x_weight), h_out=ptr(h_out), eps=float(eps), count=n,
+                            W_q=cast(arrays[0]), scale=cast(arrays[1]), zero=cast(arrays[2]), bias=cast(arrays[3]), y=cast(arrays[4]),
+                            N=cast(Narr), K=K, group_size=int(m0["group_size"]), nbits=nbits, dtype=code, tp=int(tpx["tp"]), rank=int(tpx["rank"]),
+                            peer_data=cast(tpx.get("peer_data")), red_data=tpx.get("red_data"), y_tagged=cast(ytag_arr),
+                            x_tagged=tpx.get("x_tagged"), x2_tagged=tpx.get("x2_tagged"), step_ctr=tpx["step_ctr"],
+                            x_index=int(tpx["x_index"]), x_per_step=int(tpx["x_per_step"]), skip_wait=int(tpx.get("skip_wait", 0)))
+        rc = lib.hqq_b200_decode_linear_fwd_desc(ctypes.byref(d), stream_ptr(x.device))
     if rc == HQQ_E_UNSUPPORTED:
         return False
     check(rc)

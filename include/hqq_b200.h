@@ -158,21 +158,30 @@ int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const vo
                                int count, const void* const* W_q, const void* const* scale, const void* const* zero,
                                const void* const* bias, void* const* y, const int64_t* N, int64_t K,
                                int group_size, int nbits, int dtype, void* stream);
-/* Tensor-parallel variant (SURVEY.md 8e, row-parallel o_proj / down_proj): the all-reduce of the [1, hidden] partial is
- * fused into the kernels that produce and consume it, over NVLink peer memory (no collective launch, no fences).  Every
- * value travels as one 32-bit word {tag16 : value16} ("LL" protocol):
- *   producer  (peer_data != NULL, count == 1): every result is also stored to peer_data[dst][parity][rank][n] of all `tp` ranks
- *   consumer  (red_data != NULL, x_op == 1): the residual delta is sum_r red_data[parity][r][k]; words are polled until their
- *             tag matches.
- * tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0 (ranks are at most one exchange
- * apart).  peer_data: `tp` device pointers into symmetric (peer-mapped) allocations of 2*tp*N uint32 each; step_ctr: an int in
- * local device memory that hqq_b200_glue_add_rmsnorm_tp bumps once per token, so a captured graph can be replayed.            */
-int hqq_b200_decode_linear_fwd_tp(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps,
-                                  int count, const void* const* W_q, const void* const* scale, const void* const* zero,
-                                  const void* const* bias, void* const* y, const int64_t* N, int64_t K,
-                                  int group_size, int nbits, int dtype, int tp, int rank,
-                                  void* const* peer_data, const void* red_data, const int* step_ctr,
-                                  int x_index, int x_per_step, void* stream);
+/* Chained / tensor-parallel variant.  Kernels exchange one-token activations as 32-bit words {tag16 : value16} ("LL" protocol:
+ * a consumer polls until the tag matches, so there are no fences, flags or collective launches):
+ *   - SURVEY.md 8e, row-parallel o_proj / down_proj: with peer_data the producer scatters its [1, hidden] partial to
+ *     peer_data[dst][parity][rank][n] on all `tp` ranks over NVLink peer memory; the consumer (x_op 1, red_data) sums the `tp`
+ *     partials into the residual delta.  This IS the all-reduce, fused into the kernels that produce and consume it.
+ *   - on one GPU the same words chain kernels: y_tagged[i] keeps a tagged copy [2][N_i] of output i, x_tagged / x2_tagged feed
+ *     the SiLU*mul prologue, red_data with tp == 1 feeds the residual delta.  A consumer whose only inputs from the preceding
+ *     kernel are tagged may set skip_wait and overlap that kernel's tail (no griddepcontrol.wait).
+ * tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0.  step_ctr is an int in local
+ * device memory that hqq_b200_glue_add_rmsnorm_tp bumps once per token, so a captured CUDA graph can be replayed.  Buffers
+ * start filled with 0xFF.  All other fields as in hqq_b200_decode_linear_fwd.                                                  */
+typedef struct hqq_b200_decode_desc {
+  const void* x; int x_op; const void* x2; const void* x_weight; void* h_out; float eps;
+  int count; const void* const* W_q; const void* const* scale; const void* const* zero; const void* const* bias;
+  void* const* y; const int64_t* N; int64_t K; int group_size; int nbits; int dtype;
+  int tp; int rank;
+  void* const* peer_data;   /* `tp` peer-mapped pointers, each [2][tp][N] uint32, or NULL */
+  const void* red_data;     /* local [2][tp][K] uint32 to reduce into the delta (x_op 1), or NULL */
+  void* const* y_tagged;    /* `count` local [2][N_i] uint32 buffers, or NULL */
+  const void* x_tagged;     /* local [2][K] uint32 (x_op 2), or NULL */
+  const void* x2_tagged;
+  const int* step_ctr; int x_index; int x_per_step; int skip_wait;
+} hqq_b200_decode_desc;
+int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* desc, void* stream);
 /* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */
 int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp,
                                  const void* weight, void* y, int H, float eps, int dtype, void* stream);

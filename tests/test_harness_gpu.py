@@ -61,7 +61,8 @@ def test_decode_graph_fused_equals_framework_ops():
     """A tiny 2-block model: the captured fused step (8 launches/block) and the PyTorch-op step produce the same tokens."""
     torch.manual_seed(0)
     shape = harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)
-    models = [harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3) for f in (5, True, False)]
+    models = [harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3, tp_mode=m)
+              for f, m in ((5, "p2p"), (5, "nccl"), (True, None), (False, None))]
     toks = []
     for m in models:
         m.capture()
@@ -73,7 +74,8 @@ def test_decode_graph_fused_equals_framework_ops():
             m.decode()
             t.append(int(m.next_tok))
         toks.append(t)
-    t5, t8, tref = toks
+    t5c, t5, t8, tref = toks
+    assert t5c == t5, (t5c, t5)  # tagged-word chaining (skipped dependency waits) carries the same values
     assert t5 == t8, (t5, t8)  # the in-kernel prologues round exactly like the stand-alone glue kernels
     agree = sum(int(x == y) for x, y in zip(t8, tref))
     assert agree >= 10, (t8, tref)  # fp16 reorderings may flip a near-tie late in the sequence, never the early tokens
