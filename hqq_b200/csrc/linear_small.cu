@@ -635,8 +635,10 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   };
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue(s);
-  pdl_launch_dependents();
+  // Order matters: our dependents may skip THEIR wait (tagged inputs), so they must not be released before everything
+  // older than us has completed -- i.e. not before our own wait has returned.
   if (!a.skip_wait) pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
+  pdl_launch_dependents();
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
   if (a.step_ctr) {
     const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;

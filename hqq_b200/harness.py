@@ -64,6 +64,7 @@ class DecodeModel:
         self.fused = fused
         import os
         self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")  # "p2p": tagged-word chaining / fused exchange; "nccl": plain
+        self.chain_all = os.environ.get("HQQ_B200_CHAIN", "0") == "1"
         self.skip_wait = int(os.environ.get("HQQ_B200_SKIP_WAIT", "1"))
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -236,7 +237,10 @@ class DecodeModel:
         torch.index_select(self.embed, 0, self.tok, out=h_cur)
         delta = None
         ok = True
-        chain = self.tp_mode == "p2p"  # tagged-word chaining (and, with tp > 1, the fused NVLink all-reduce)
+        # tagged-word exchange: with tp > 1 it is the fused NVLink all-reduce of the o / down partials (default); chaining gate/up
+        # through tagged words with skipped dependency waits is experimental (HQQ_B200_CHAIN=1): on one GPU the polling costs
+        # more than the kernel boundary it removes (measured 414 vs 468 tok/s)
+        chain = self.tp_mode == "p2p" and (self.tp > 1 or self.chain_all)
         nb = len(self.blocks)
         if chain:
             o_sc, d_sc = self._tp_keep            # scatter targets (every rank's buffer) for o / down
@@ -256,11 +260,17 @@ class DecodeModel:
                 ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc))
                 # the next two kernels take everything the preceding kernel produces as tagged words: they skip the
                 # programmatic-dependency wait and start streaming their weights under its tail
-                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                            tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait))
-                h_cur, h_nxt = h_nxt, h_cur
-                ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
-                                            tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait))
+                if self.chain_all:
+                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
+                                                tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait))
+                    h_cur, h_nxt = h_nxt, h_cur
+                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
+                                                tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait))
+                else:
+                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
+                                                tpx=self._tpx(bi, red_data=o_loc))
+                    h_cur, h_nxt = h_nxt, h_cur
+                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc))
             else:
                 ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
                 if self.tp > 1:
@@ -295,7 +305,7 @@ class DecodeModel:
         fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
-        if fused and self.fused == 5 and self.tp_mode == "p2p" and not hasattr(self, "_xbuf"):
+        if fused and self.fused == 5 and self.tp_mode == "p2p" and (self.tp > 1 or self.chain_all) and not hasattr(self, "_xbuf"):
             try:
                 self._setup_exchange()
             except Exception as e:  # symmetric memory unavailable -> plain buffers (+ NCCL all-reduce when tp > 1)

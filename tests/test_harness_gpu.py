@@ -61,8 +61,11 @@ def test_decode_graph_fused_equals_framework_ops():
     """A tiny 2-block model: the captured fused step (8 launches/block) and the PyTorch-op step produce the same tokens."""
     torch.manual_seed(0)
     shape = harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)
-    models = [harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3, tp_mode=m)
-              for f, m in ((5, "p2p"), (5, "nccl"), (True, None), (False, None))]
+    models = []
+    for f, m, chain in ((5, "p2p", True), (5, "nccl", False), (True, None, False), (False, None, False)):
+        mdl = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3, tp_mode=m)
+        mdl.chain_all = chain  # experimental single-GPU chaining through tagged words (skipped dependency waits)
+        models.append(mdl)
     toks = []
     for m in models:
         m.capture()
