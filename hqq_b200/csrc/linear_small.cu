@@ -635,10 +635,12 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   };
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue(s);
-  // Order matters: our dependents may skip THEIR wait (tagged inputs), so they must not be released before everything
-  // older than us has completed -- i.e. not before our own wait has returned.
-  if (!a.skip_wait) pdl_wait();  // x is produced by the previous kernel; the weight prefetch above is already in flight
-  pdl_launch_dependents();
+  // skip_wait 0: release our dependents early (their launch latency hides under our main loop), then wait for x.
+  //           1: every input from the preceding kernel is tagged -> no wait at all.
+  //           2: our dependents skip THEIR wait, so they must not be released before everything older than us has completed,
+  //              i.e. not before our own wait has returned.
+  if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
+  else { pdl_launch_dependents(); if (a.skip_wait == 0) pdl_wait(); }
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
   if (a.step_ctr) {
     const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
@@ -1056,7 +1058,7 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     HQQ_REQUIRE(tpx->tp >= 1 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,
                 "hqq_b200_decode_linear_fwd_desc: bad tp/rank/step counter");
     a.tp = tpx->tp; a.rank = tpx->rank; a.step_ctr = tpx->step_ctr; a.x_index = tpx->x_index; a.x_per_step = tpx->x_per_step;
-    a.skip_wait = tpx->skip_wait ? 1 : 0;
+    a.skip_wait = tpx->skip_wait;
     if (tpx->peer_data) {
       HQQ_REQUIRE(nprob == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: the scatter side takes exactly one matrix");
       for (int i = 0; i < tpx->tp; ++i) a.peer_data[i] = reinterpret_cast<uint32_t*>(tpx->peer_data[i]);

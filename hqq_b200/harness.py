@@ -257,7 +257,7 @@ class DecodeModel:
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
             if chain:
-                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc))
+                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc, skip_wait=2 if (self.chain_all and self.skip_wait) else 0))
                 # the next two kernels take everything the preceding kernel produces as tagged words: they skip the
                 # programmatic-dependency wait and start streaming their weights under its tail
                 if self.chain_all:

@@ -165,7 +165,8 @@ int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const vo
  *     partials into the residual delta.  This IS the all-reduce, fused into the kernels that produce and consume it.
  *   - on one GPU the same words chain kernels: y_tagged[i] keeps a tagged copy [2][N_i] of output i, x_tagged / x2_tagged feed
  *     the SiLU*mul prologue, red_data with tp == 1 feeds the residual delta.  A consumer whose only inputs from the preceding
- *     kernel are tagged may set skip_wait and overlap that kernel's tail (no griddepcontrol.wait).
+ *     kernel are tagged may set skip_wait = 1 and overlap that kernel's tail (no griddepcontrol.wait); the kernel launched
+ *     BEFORE such a consumer sets skip_wait = 2 (wait first, release dependents afterwards).
  * tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0.  step_ctr is an int in local
  * device memory that hqq_b200_glue_add_rmsnorm_tp bumps once per token, so a captured CUDA graph can be replayed.  Buffers
  * start filled with 0xFF.  All other fields as in hqq_b200_decode_linear_fwd.                                                  */
