@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restri
                                                                const T* __restrict__ cos_t, const T* __restrict__ sin_t,
                                                                T* __restrict__ k_cache, T* __restrict__ v_cache, const long long* __restrict__ pos_p,
                                                                T* __restrict__ out, int n_q, int n_kv, int L, int hd, float scale) {
-  extern __shared__ float sm[];  // q[hd] | knew[hd] | p[L] | red[32]
+  extern __shared__ float sm[];  // q[hd] | knew[hd] | p[L]  (later reused as [4][hd] partial outputs) | red[32]
   float* qs = sm;
   float* ks = sm + hd;
   float* ps = sm + 2 * hd;
-  float* red = ps + L;
+  float* red = sm + max(2 * hd + L, 4 * hd);
   pdl_launch_g();
   pdl_wait_g();
   const int h = blockIdx.x, kvh = h / (n_q / n_kv), d = threadIdx.x;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restri
       for (int i = 0; i < hd; ++i) acc += qs[i] * ks[i];
     } else {
       const T* kr = k_cache + ((long long)kvh * L + t) * hd;
+#pragma unroll 4
       for (int i = 0; i < hd; i += 8) {
         const Vec<T, 8> kv = *reinterpret_cast<const Vec<T, 8>*>(kr + i);
 #pragma unroll
@@ -164,11 +165,28 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restri
     sum += e;
   }
   const float tot = block_sum(sum, red);
-  // output: thread d owns dimension d
-  float o = 0.f;
-  for (int t = 0; t < pos; ++t) o += ps[t] * to_f32<T>(v_cache[((long long)kvh * L + t) * hd + d]);
-  o += ps[pos] * to_f32<T>(v_in[kvh * hd + d]);
-  out[h * hd + d] = from_f32<T>(o / tot);
+  const float ps_last = ps[pos];
+  // output: warp w takes positions w, w+4, ... and each lane four consecutive dimensions (one 8-byte load per position),
+  // so the position loop is 4x shorter and its loads are independent; the four partial outputs meet in shared memory.
+  {
+    const int w = d >> 5, l = d & 31;
+    float o4[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* vbase = v_cache + (long long)kvh * L * hd + 4 * l;
+    for (int t = w; t < pos; t += 4) {
+      const Vec<T, 4> vv = *reinterpret_cast<const Vec<T, 4>*>(vbase + (long long)t * hd);
+      const float pt = ps[t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] += pt * to_f32<T>(vv.v[j]);
+    }
+    __syncthreads();  // q, k and the probabilities are dead now: reuse the front of the buffer for the cross-warp reduction
+    float* part = sm;  // [4][hd] floats (the launcher sizes the buffer for max(2*hd + L, 4*hd) + 32)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[w * hd + 4 * l + j] = o4[j];
+    __syncthreads();
+    float o = part[d] + part[hd + d] + part[2 * hd + d] + part[3 * hd + d];
+    o += ps_last * to_f32<T>(v_in[kvh * hd + d]);
+    out[h * hd + d] = from_f32<T>(o / tot);
+  }
 }
 
 // argmax over n logits -> int64 index (two-stage in one launch via last-block pattern is overkill: one CTA, n ~ 128K)
@@ -261,7 +279,8 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
   HQQ_REQUIRE(head_dim == 128 && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && cache_len > 0 && cache_len <= 8192, HQQ_E_UNSUPPORTED,
               "hqq_b200_glue_rope_attn_decode: needs head_dim 128, cache_len <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (2 * head_dim + cache_len + 32) * sizeof(float);
+  const int body = 2 * head_dim + cache_len > 4 * head_dim ? 2 * head_dim + cache_len : 4 * head_dim;
+  const size_t smem = (size_t)(body + 32) * sizeof(float);
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (dtype == HQQ_F16)
     return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads), dim3(head_dim), smem, st, (const __half*)q, (const __half*)k,
