@@ -93,24 +93,32 @@ __device__ __forceinline__ void load8_group<float>(const float* base, int l, int
   w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
   w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
+// 16-bit sources use the SAME element-to-lane assignment as float32 (chunk c of lane l = elements (c*L + l)*4 .. +3), so that
+// quantising a half tensor is bit-identical to quantising its float32 copy (tensor.float() is exact, quantize.py:102).
 template <>
 __device__ __forceinline__ void load8_group<__half>(const __half* base, int l, int L, float (&w)[8]) {
-  uint4 r = __ldg(reinterpret_cast<const uint4*>(base) + l);
-  const __half2* h = reinterpret_cast<const __half2*>(&r);
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(base) + l);
+  const uint2 b = __ldg(reinterpret_cast<const uint2*>(base) + L + l);
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f = __half22float2(h[j]);
-    w[2 * j] = f.x; w[2 * j + 1] = f.y;
+  for (int j = 0; j < 2; ++j) {
+    const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+    w[2 * j] = fa.x; w[2 * j + 1] = fa.y;
+    w[4 + 2 * j] = fb.x; w[4 + 2 * j + 1] = fb.y;
   }
 }
 template <>
 __device__ __forceinline__ void load8_group<__nv_bfloat16>(const __nv_bfloat16* base, int l, int L, float (&w)[8]) {
-  uint4 r = __ldg(reinterpret_cast<const uint4*>(base) + l);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(base) + l);
+  const uint2 b = __ldg(reinterpret_cast<const uint2*>(base) + L + l);
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f = __bfloat1622float2(h[j]);
-    w[2 * j] = f.x; w[2 * j + 1] = f.y;
+  for (int j = 0; j < 2; ++j) {
+    const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]);
+    w[2 * j] = fa.x; w[2 * j + 1] = fa.y;
+    w[4 + 2 * j] = fb.x; w[4 + 2 * j + 1] = fb.y;
   }
 }
 
