@@ -100,24 +100,40 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const T* __restrict__ g, 
 }
 
 // RoPE (rotate-half, cos/sin tables [L, hd]) + KV-cache append + single-token GQA attention over cache[0..pos].
-// grid = n_q_heads, block = hd (= 128) threads.  caches are [n_kv_heads, L, hd].
+// grid = n_q_heads, block = 256 threads (8 warps).  caches are [n_kv_heads, L, hd], hd = 128.
+// The step streams ~5 GB of weights between two visits of a layer's cache, so the rows are cold in DRAM and the kernel is
+// bound by load latency, not bandwidth: (1) rows 0..pos-1 were written by earlier steps, so they are prefetched into L2
+// BEFORE griddepcontrol.wait, under the tail of the q/k/v kernel (pos itself is only written by the non-PDL kernel that ends
+// a step, a full barrier); (2) both position loops keep 8-16 independent loads in flight per thread.
+constexpr int kAttnThreads = 256;
 template <typename T>
-__global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in, const T* __restrict__ v_in,
-                                                               const T* __restrict__ cos_t, const T* __restrict__ sin_t,
-                                                               T* __restrict__ k_cache, T* __restrict__ v_cache, const long long* __restrict__ pos_p,
-                                                               T* __restrict__ out, int n_q, int n_kv, int L, int hd, float scale) {
-  extern __shared__ float sm[];  // q[hd] | knew[hd] | p[L]  (later reused as [4][hd] partial outputs) | red[32]
+__global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in, const T* __restrict__ v_in,
+                                                                        const T* __restrict__ cos_t, const T* __restrict__ sin_t,
+                                                                        T* __restrict__ k_cache, T* __restrict__ v_cache, const long long* __restrict__ pos_p,
+                                                                        T* __restrict__ out, int n_q, int n_kv, int L, int hd, float scale) {
+  extern __shared__ float sm[];  // q[hd] | knew[hd] | p[L]  (later reused as [8][hd] partial outputs) | red[32]
+  constexpr int NW = kAttnThreads / 32;
   float* qs = sm;
   float* ks = sm + hd;
   float* ps = sm + 2 * hd;
-  float* red = sm + max(2 * hd + L, 4 * hd);
-  pdl_launch_g();
-  pdl_wait_g();
+  float* red = sm + max(2 * hd + L, NW * hd);
   const int h = blockIdx.x, kvh = h / (n_q / n_kv), d = threadIdx.x;
   const int pos = (int)pos_p[0];
+  pdl_launch_g();
+  {
+    // one 128-byte line per prefetch; pos rows of hd * sizeof(T) bytes each in both caches
+    const char* kb = reinterpret_cast<const char*>(k_cache + (long long)kvh * L * hd);
+    const char* vb = reinterpret_cast<const char*>(v_cache + (long long)kvh * L * hd);
+    const int lines = (int)(((long long)pos * hd * (int)sizeof(T)) >> 7);
+    for (int i = d; i < lines; i += kAttnThreads) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + ((long long)i << 7)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + ((long long)i << 7)));
+    }
+  }
+  pdl_wait_g();
   const int half = hd / 2;
   // rope: x*cos + rotate_half(x)*sin, computed in T like the framework ops
-  {
+  if (d < hd) {
     const float c = to_f32<T>(cos_t[(long long)pos * hd + d]), s = to_f32<T>(sin_t[(long long)pos * hd + d]);
     const float qx = to_f32<T>(q_in[h * hd + d]);
     const float qr = (d < half) ? -to_f32<T>(q_in[h * hd + d + half]) : to_f32<T>(q_in[h * hd + d - half]);
@@ -132,19 +148,22 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restri
     }
   }
   __syncthreads();
-  // scores: thread t handles positions t, t+blockDim, ... ; the current position uses the freshly rotated k
+  // scores: thread t handles positions t, t+blockDim, ... (a whole 256-byte row each, all 16 loads in flight at once);
+  // the current position uses the freshly rotated k
   float mx = -INFINITY;
-  for (int t = d; t <= pos; t += blockDim.x) {
+  for (int t = d; t <= pos; t += kAttnThreads) {
     float acc = 0.f;
     if (t == pos) {
       for (int i = 0; i < hd; ++i) acc += qs[i] * ks[i];
     } else {
       const T* kr = k_cache + ((long long)kvh * L + t) * hd;
-#pragma unroll 4
-      for (int i = 0; i < hd; i += 8) {
-        const Vec<T, 8> kv = *reinterpret_cast<const Vec<T, 8>*>(kr + i);
+      Vec<T, 8> kv[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += qs[i + j] * to_f32<T>(kv.v[j]);
+      for (int i = 0; i < 16; ++i) kv[i] = *reinterpret_cast<const Vec<T, 8>*>(kr + i * 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += qs[i * 8 + j] * to_f32<T>(kv[i].v[j]);
       }
     }
     acc *= scale;
@@ -156,36 +175,53 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const T* __restri
   if ((d & 31) == 0) red[d >> 5] = mx;
   __syncthreads();
   mx = red[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+#pragma unroll
+  for (int i = 1; i < NW; ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int t = d; t <= pos; t += blockDim.x) {
+  for (int t = d; t <= pos; t += kAttnThreads) {
     const float e = __expf(ps[t] - mx);
     ps[t] = e;
     sum += e;
   }
   const float tot = block_sum(sum, red);
   const float ps_last = ps[pos];
-  // output: warp w takes positions w, w+4, ... and each lane four consecutive dimensions (one 8-byte load per position),
-  // so the position loop is 4x shorter and its loads are independent; the four partial outputs meet in shared memory.
+  // output: warp w takes positions w, w+8, ... and each lane four consecutive dimensions (one 8-byte load per position);
+  // eight positions per warp are loaded before any is consumed.  The eight partial outputs meet in shared memory.
   {
     const int w = d >> 5, l = d & 31;
     float o4[4] = {0.f, 0.f, 0.f, 0.f};
     const T* vbase = v_cache + (long long)kvh * L * hd + 4 * l;
-    for (int t = w; t < pos; t += 4) {
+    int t = w;
+    for (; t + 7 * NW < pos; t += 8 * NW) {
+      Vec<T, 4> vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) vv[u] = *reinterpret_cast<const Vec<T, 4>*>(vbase + (long long)(t + u * NW) * hd);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float pt = ps[t + u * NW];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o4[j] += pt * to_f32<T>(vv[u].v[j]);
+      }
+    }
+    for (; t < pos; t += NW) {
       const Vec<T, 4> vv = *reinterpret_cast<const Vec<T, 4>*>(vbase + (long long)t * hd);
       const float pt = ps[t];
 #pragma unroll
       for (int j = 0; j < 4; ++j) o4[j] += pt * to_f32<T>(vv.v[j]);
     }
     __syncthreads();  // q, k and the probabilities are dead now: reuse the front of the buffer for the cross-warp reduction
-    float* part = sm;  // [4][hd] floats (the launcher sizes the buffer for max(2*hd + L, 4*hd) + 32)
+    float* part = sm;  // [NW][hd] floats (the launcher sizes the buffer for max(2*hd + L, NW*hd) + 32)
 #pragma unroll
     for (int j = 0; j < 4; ++j) part[w * hd + 4 * l + j] = o4[j];
     __syncthreads();
-    float o = part[d] + part[hd + d] + part[2 * hd + d] + part[3 * hd + d];
-    o += ps_last * to_f32<T>(v_in[kvh * hd + d]);
-    out[h * hd + d] = from_f32<T>(o / tot);
+    if (d < hd) {
+      float o = 0.f;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) o += part[i * hd + d];
+      o += ps_last * to_f32<T>(v_in[kvh * hd + d]);
+      out[h * hd + d] = from_f32<T>(o / tot);
+    }
   }
 }
 
@@ -279,15 +315,15 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
   HQQ_REQUIRE(head_dim == 128 && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && cache_len > 0 && cache_len <= 8192, HQQ_E_UNSUPPORTED,
               "hqq_b200_glue_rope_attn_decode: needs head_dim 128, cache_len <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
-  const int body = 2 * head_dim + cache_len > 4 * head_dim ? 2 * head_dim + cache_len : 4 * head_dim;
+  const int body = 2 * head_dim + cache_len > 8 * head_dim ? 2 * head_dim + cache_len : 8 * head_dim;
   const size_t smem = (size_t)(body + 32) * sizeof(float);
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (dtype == HQQ_F16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads), dim3(head_dim), smem, st, (const __half*)q, (const __half*)k,
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads), dim3(kAttnThreads), smem, st, (const __half*)q, (const __half*)k,
                       (const __half*)v, (const __half*)cos_table, (const __half*)sin_table, (__half*)k_cache, (__half*)v_cache, (const long long*)pos,
                       (__half*)out, n_q_heads, n_kv_heads, cache_len, head_dim, scale);
   if (dtype == HQQ_BF16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads), dim3(head_dim), smem, st, (const __nv_bfloat16*)q,
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads), dim3(kAttnThreads), smem, st, (const __nv_bfloat16*)q,
                       (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
                       (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, (const long long*)pos, (__nv_bfloat16*)out, n_q_heads, n_kv_heads, cache_len,
                       head_dim, scale);

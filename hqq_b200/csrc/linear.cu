@@ -86,7 +86,9 @@ extern "C" int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x
   int rc = check_common(x, 1, K, group_size, nbits, 1);
   if (rc) return rc;
   HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: 1..4 matrices, non-null arrays");
-  HQQ_REQUIRE(x_op >= 0 && x_op <= 2, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: x_op must be 0 (none), 1 (add+rmsnorm) or 2 (silu*mul)");
+  HQQ_REQUIRE(x_op >= 0 && (x_op & 15) <= 2 && (x_op >> 4) <= 1, HQQ_E_INVALID,
+              "hqq_b200_decode_linear_fwd: x_op must be 0 (none), 1 (add+rmsnorm) or 2 (silu*mul), optionally | HQQ_YOP_SILU_MUL_PAIR");
+  (void)0;
   for (int i = 0; i < count; ++i) {
     if (!small_route_ok(1, N[i], K, group_size, nbits, 1, dtype) || (x_op != 0 && !small_xop_ok(1, K))) {
       set_error("hqq_b200_decode_linear_fwd: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i, (long long)N[i],
@@ -104,8 +106,9 @@ extern "C" int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* d, vo
   if (rc) return rc;
   HQQ_REQUIRE(d->count >= 1 && d->count <= 4 && d->W_q && d->scale && d->zero && d->y && d->N, HQQ_E_INVALID,
               "hqq_b200_decode_linear_fwd_desc: 1..4 matrices, non-null arrays");
-  HQQ_REQUIRE(d->x_op >= 0 && d->x_op <= 2, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: x_op must be 0, 1 or 2");
-  HQQ_REQUIRE(d->x || (d->x_op == 2 && d->x_tagged), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: no activation given");
+  HQQ_REQUIRE(d->x_op >= 0 && (d->x_op & 15) <= 2 && (d->x_op >> 4) <= 1, HQQ_E_INVALID,
+              "hqq_b200_decode_linear_fwd_desc: x_op must be 0, 1 or 2, optionally | HQQ_YOP_SILU_MUL_PAIR");
+  HQQ_REQUIRE(d->x || ((d->x_op & 15) == 2 && d->x_tagged), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: no activation given");
   for (int i = 0; i < d->count; ++i) {
     if (!small_route_ok(1, d->N[i], d->K, d->group_size, d->nbits, 1, d->dtype) || !small_xop_ok(1, d->K)) {
       set_error("hqq_b200_decode_linear_fwd_desc: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i,

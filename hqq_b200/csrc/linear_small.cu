@@ -64,6 +64,10 @@ struct SKArgs {
   //   xop 0: x as is;  1: x = rmsnorm(x + x2) * xw, and h_out = x + x2 is written by CTA 0 (x2 may be null);
   //   xop 2: x = silu(x) * x2
   int xop;
+  // optional epilogue (M == 1 decode kernel, nbits < 8, exactly two matrices of equal N -- the MLP's gate and up):
+  //   yop 1: y[0][n] = silu(W0 x)[n] * (W1 x)[n]; every 16-row tile then holds P/2 packed rows of EACH matrix, so both
+  //   operands of an output meet in one CTA and the activation is computed once instead of by every consumer CTA.
+  int yop;
   const void* x2;
   const void* xw;
   void* h_out;
@@ -105,11 +109,12 @@ template <> struct MT16<__half> {
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.0f));
   }
   __device__ __forceinline__ static float ld(const void* p, long long i) { return __half2float(reinterpret_cast<const __half*>(p)[i]); }
-  __device__ __forceinline__ static void st(void* p, long long i, float v, const void* bias, int n) {
+  __device__ __forceinline__ static __half cvt(float v, const void* bias, int n) {
     __half o = __float2half_rn(v);
     if (bias) o = __hadd(o, reinterpret_cast<const __half*>(bias)[n]);  // out += bias, second rounding as in the reference
-    reinterpret_cast<__half*>(p)[i] = o;
+    return o;
   }
+  __device__ __forceinline__ static void st(void* p, long long i, float v, const void* bias, int n) { reinterpret_cast<__half*>(p)[i] = cvt(v, bias, n); }
 };
 template <> struct MT16<__nv_bfloat16> {
   static constexpr uint32_t ONE2 = 0x3F803F80u;
@@ -124,11 +129,12 @@ template <> struct MT16<__nv_bfloat16> {
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.0f));
   }
   __device__ __forceinline__ static float ld(const void* p, long long i) { return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]); }
-  __device__ __forceinline__ static void st(void* p, long long i, float v, const void* bias, int n) {
+  __device__ __forceinline__ static __nv_bfloat16 cvt(float v, const void* bias, int n) {
     __nv_bfloat16 o = __float2bfloat16_rn(v);
     if (bias) o = __hadd(o, reinterpret_cast<const __nv_bfloat16*>(bias)[n]);
-    reinterpret_cast<__nv_bfloat16*>(p)[i] = o;
+    return o;
   }
+  __device__ __forceinline__ static void st(void* p, long long i, float v, const void* bias, int n) { reinterpret_cast<__nv_bfloat16*>(p)[i] = cvt(v, bias, n); }
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
@@ -560,11 +566,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   if (n_tiles <= 0) return;
 
   struct Tile { const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y; uint32_t* ytag; int N, step, tile0; };
-  auto locate = [&](int gt, Tile& t) {
-    int pi = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxProb; ++i)
-      if (i < a.nprob && gt >= a.p[i].tile0) pi = i;
+  auto pick = [&](int pi, Tile& t) {
     const uint8_t* Wq = a.p[0].Wq; const void* sc = a.p[0].scale; const void* ze = a.p[0].zero; const void* bi = a.p[0].bias;
     void* y = a.p[0].y; uint32_t* yt = a.p[0].ytag; int N = a.p[0].N, step = a.p[0].step, tile0 = a.p[0].tile0;
 #pragma unroll
@@ -573,13 +575,33 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     t.Wq = Wq; t.scale = reinterpret_cast<const T*>(sc); t.zero = reinterpret_cast<const T*>(ze);
     t.bias = reinterpret_cast<const T*>(bi); t.y = reinterpret_cast<T*>(y); t.ytag = yt; t.N = N; t.step = step; t.tile0 = tile0;
   };
+  auto locate = [&](int gt, Tile& t) {
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProb; ++i)
+      if (i < a.nprob && gt >= a.p[i].tile0) pi = i;
+    pick(pi, t);
+  };
+  // paired epilogue (yop 1, F > 1): tile gt = packed rows [gt*PH, gt*PH + PH) of matrix 0 (fragment rows p < PH) and of matrix 1
+  constexpr int PH = (P >= 2) ? P / 2 : 1;
+  const bool paired = (F > 1) && a.yop == 1;
+  auto my_rows = [&](int gt, Tile& t, int& prow_a, int& prow_b) {
+    if (paired) {
+      pick(p >= PH ? 1 : 0, t);
+      prow_a = prow_b = gt * PH + (p % PH);
+    } else {
+      locate(gt, t);
+      prow_a = (gt - t.tile0) * P + p;
+      prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    }
+  };
 
   int i_tile = 0, i_k = 0;
   const uint8_t *iw_a, *iw_b;
   auto issue_setup = [&]() {
     const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
-    Tile t; locate(gt, t);
-    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    Tile t; int prow_a, prow_b;
+    my_rows(gt, t, prow_a, prow_b);
     const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
     iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
     iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
@@ -593,8 +615,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   const T *ms_a = nullptr, *mz_a = nullptr, *ms_b = nullptr, *mz_b = nullptr;
   auto meta_setup = [&]() {
     const int gt = (int)blockIdx.x + m_tile * (int)gridDim.x;
-    Tile t; locate(gt, t);
-    const int prow_a = (gt - t.tile0) * P + p, prow_b = (F == 1) ? prow_a + 8 : prow_a;
+    Tile t; int prow_a, prow_b;
+    my_rows(gt, t, prow_a, prow_b);
     const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
     ms_a = t.scale + na * a.Gk + kb0 * GPB; mz_a = t.zero + na * a.Gk + kb0 * GPB;
     ms_b = t.scale + nb * a.Gk + kb0 * GPB; mz_b = t.zero + nb * a.Gk + kb0 * GPB;
@@ -812,10 +834,25 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     __syncthreads();
     if (warp == (ti & 7) && lane < 16) {
       const int gt = (int)blockIdx.x + ti * (int)gridDim.x;
-      Tile t; locate(gt, t);
       const int rr = lane & 7, hi = lane >> 3;  // fragment row lane = rr + 8*hi
       const int pp = (F == 1) ? rr : (rr % P);
       const int ff = (F == 1) ? 0 : (hi ? F / 2 + rr / P : rr / P);
+      if (paired) {
+        // lane (pp < PH) holds matrix 0's row, lane + PH the same row of matrix 1: activation computed once, here
+        Tile tg, tu; pick(0, tg); pick(1, tu);
+        const int prow = gt * PH + pp;
+        if (pp < PH && prow < tg.step) {
+          float ag = 0.0f, au = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { ag += buf[w * 16 + lane]; au += buf[w * 16 + lane + PH]; }
+          const int n = ff * tg.step + prow;
+          const float f = to_f32<T>(MM::cvt(ag, tg.bias, n));
+          const float u = to_f32<T>(MM::cvt(au, tu.bias, n));
+          tg.y[n] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(f / (1.0f + __expf(-f)))) * u);
+        }
+        continue;
+      }
+      Tile t; locate(gt, t);
       const int prow = (gt - t.tile0) * P + pp + ((F == 1 && hi) ? 8 : 0);
       if (prow < t.step) {
         float acc = 0.0f;
@@ -1049,7 +1086,17 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
   const int F = 8 / nbits, P = 16 / F;
   SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
-  a.xop = xop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
+  const int yop = xop >> 4;  // HQQ_YOP_* travel in the high bits of x_op
+  xop &= 15;
+  a.xop = xop; a.yop = yop; a.x2 = x2; a.xw = xw; a.h_out = h_out; a.eps = eps;
+  if (yop) {
+    HQQ_REQUIRE(yop == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: unknown epilogue %d", yop);
+    HQQ_REQUIRE(nprob == 2 && N[0] == N[1], HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: the silu*mul epilogue pairs exactly two matrices of equal N");
+    if (!(small_xop_ok(M, K) && nbits < 8) || (tpx && (tpx->peer_data || tpx->y_tagged))) {
+      set_error("hqq_b200_decode_linear_fwd: the silu*mul epilogue needs the M == 1 kernel, nbits < 8 and plain outputs");
+      return HQQ_E_UNSUPPORTED;
+    }
+  }
   a.tp = 1; a.rank = 0; a.red_data = nullptr; a.xtag = nullptr; a.x2tag = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
   a.skip_wait = 0;
   for (int i = 0; i < 8; ++i) a.peer_data[i] = nullptr;
@@ -1082,7 +1129,7 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     a.p[i].y = y[j]; a.p[i].ytag = (tpx && tpx->y_tagged) ? reinterpret_cast<uint32_t*>(tpx->y_tagged[j]) : nullptr; a.p[i].N = (int)N[j]; a.p[i].step = (int)(N[j] / F); a.p[i].tile0 = tiles;
     if (i < nprob) tiles += (int)cdiv(a.p[i].step, P);
   }
-  a.total_tiles = tiles;
+  a.total_tiles = yop ? (int)cdiv(a.p[0].step, P / 2) : tiles;
   if (dtype == HQQ_F16) return sk_bits<__half>(a, gs, nbits, st);
   return sk_bits<__nv_bfloat16>(a, gs, nbits, st);
 }

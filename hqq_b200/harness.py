@@ -66,6 +66,8 @@ class DecodeModel:
         self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")  # "p2p": tagged-word chaining / fused exchange; "nccl": plain
         self.chain_all = os.environ.get("HQQ_B200_CHAIN", "0") == "1"
         self.skip_wait = int(os.environ.get("HQQ_B200_SKIP_WAIT", "1"))
+        self.pair_silu = os.environ.get("HQQ_B200_PAIR_SILU", "1") != "0"
+        self.nbits = nbits
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
         self.n_layers = n_layers if n_layers is not None else shape.n_layers
@@ -242,6 +244,8 @@ class DecodeModel:
         # more than the kernel boundary it removes (measured 414 vs 468 tok/s)
         chain = self.tp_mode == "p2p" and (self.tp > 1 or self.chain_all)
         nb = len(self.blocks)
+        # SiLU(gate) * up in the gate/up launch's epilogue (4/2/1-bit): computed once instead of by each of down's CTAs
+        pair = self.pair_silu and self.nbits < 8
         if chain:
             o_sc, d_sc = self._tp_keep            # scatter targets (every rank's buffer) for o / down
             o_loc, d_loc = self._tp_local         # this rank's buffers
@@ -267,17 +271,29 @@ class DecodeModel:
                     ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
                                                 tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait))
                 else:
-                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                                tpx=self._tpx(bi, red_data=o_loc))
-                    h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc))
+                    if pair:  # act = silu(gate) * up leaves the gate/up launch's epilogue; down takes it as is
+                        ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, None, blk["norm2"],
+                                                    h_nxt, s.rms_eps, tpx=self._tpx(bi, red_data=o_loc))
+                        h_cur, h_nxt = h_nxt, h_cur
+                        ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], tpx=self._tpx(bi, peer_data=d_sc))
+                    else:
+                        ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
+                                                    tpx=self._tpx(bi, red_data=o_loc))
+                        h_cur, h_nxt = h_nxt, h_cur
+                        ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc))
             else:
                 ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
                 if self.tp > 1:
                     torch.distributed.all_reduce(b["o"], group=self.pg)
-                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
-                h_cur, h_nxt = h_nxt, h_cur
-                ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
+                if pair:
+                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, b["o"], blk["norm2"],
+                                                h_nxt, s.rms_eps)
+                    h_cur, h_nxt = h_nxt, h_cur
+                    ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]])
+                else:
+                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
+                    h_cur, h_nxt = h_nxt, h_cur
+                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
                 if self.tp > 1:
                     torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]

@@ -153,7 +153,10 @@ int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, i
  *   x_op 0: y_i = x @ W_i^T                               (== hqq_b200_linear_fwd_multi at M = 1)
  *   x_op 1: t = x + x2 (x2 may be NULL); h_out = t (may be NULL); y_i = (rmsnorm(t, eps) * x_weight) @ W_i^T
  *   x_op 2: y_i = (silu(x) * x2) @ W_i^T
+ *   x_op | HQQ_YOP_SILU_MUL_PAIR (count == 2, N[0] == N[1], nbits < 8): y[0] = silu(x' @ W_0^T) * (x' @ W_1^T) with both
+ *     products rounded to `dtype` first (the MLP's act(gate) * up, models/llama semantics); y[1] is not written.
  * Roundings follow the stand-alone glue kernels (every intermediate is rounded to `dtype`).  h_out must not alias x. */
+#define HQQ_YOP_SILU_MUL_PAIR 16
 int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const void* x_weight, void* h_out, float eps,
                                int count, const void* const* W_q, const void* const* scale, const void* const* zero,
                                const void* const* bias, void* const* y, const int64_t* N, int64_t K,

@@ -37,11 +37,11 @@ def test_rope_attention_kernel(dt):
     lib = load()
     st, code = stream_ptr(DEV), DTYPE_CODE[dt]
     torch.manual_seed(1)
-    hq, hkv, hd, L = 8, 2, 128, 64
+    hq, hkv, hd, L = 8, 2, 128, 512
     m = harness.DecodeModel(harness.LlamaShape(hidden=hq * hd, inter=1024, n_layers=0, n_heads=hq, n_kv_heads=hkv, vocab=256), dtype=dt, device=DEV,
                             cache_len=L)
     kc = torch.randn(hkv, L, hd, device=DEV).to(dt); vc = torch.randn(hkv, L, hd, device=DEV).to(dt)
-    for pos in (0, 1, 37, 63):
+    for pos in (0, 1, 37, 63, 64, 200, 511):
         q = torch.randn(1, hq * hd, device=DEV).to(dt); k = torch.randn(1, hkv * hd, device=DEV).to(dt); v = torch.randn(1, hkv * hd, device=DEV).to(dt)
         kc1, vc1 = kc.clone(), vc.clone()
         p = torch.tensor([pos], device=DEV)
@@ -55,6 +55,45 @@ def test_rope_attention_kernel(dt):
         mask = (torch.arange(L, device=DEV) <= pos).view(1, 1, 1, L)
         ref = F.scaled_dot_product_attention(qr.view(1, hq, 1, hd).float(), kc2[None].float(), vc2[None].float(), attn_mask=mask, enable_gqa=True)
         assert torch.allclose(out.float().view(hq, hd), ref.view(hq, hd), rtol=3e-2, atol=3e-2), pos
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("nbits,N", [(4, 1024), (4, 1048), (2, 512), (1, 256)])
+def test_paired_silu_mul_epilogue_is_bit_identical(dt, nbits, N):
+    """x_op | HQQ_YOP_SILU_MUL_PAIR: y[0] = silu(gate) * up out of ONE launch == the two plain products + the glue kernel."""
+    from hqq_b200 import ops
+    from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
+    torch.manual_seed(nbits + N)
+    K = 1024
+    cfg = BaseQuantizeConfig(nbits=nbits, group_size=64, axis=1)
+    gate, up = (HQQLinear.from_weights((torch.randn(N, K, device=DEV) * 0.05).to(dt), None, cfg, compute_dtype=dt, device=DEV) for _ in range(2))
+    x = torch.randn(1, K, device=DEV).to(dt)
+    g, u, act = (torch.empty(1, N, device=DEV, dtype=dt) for _ in range(3))
+    assert ops.decode_linear_fwd(x, (gate, up), [g, u])
+    ref = torch.empty_like(g)
+    check(load().hqq_b200_glue_silu_mul(ptr(g), ptr(u), ptr(ref), N, DTYPE_CODE[dt], stream_ptr(DEV)))
+    u2 = torch.full_like(u, 7.0)
+    assert ops.decode_linear_fwd(x, (gate, up), [act, u2], ops.YOP_SILU_MUL_PAIR)
+    assert torch.equal(act, ref)
+    assert bool((u2 == 7.0).all())  # y[1] is not written
+    # with the add + RMSNorm prologue in front (the MLP launch of the decode step)
+    h, w, hout = torch.randn(1, K, device=DEV).to(dt), torch.rand(K, device=DEV).to(dt), torch.empty(1, K, device=DEV, dtype=dt)
+    assert ops.decode_linear_fwd(x, (gate, up), [g, u], 1, h, w, hout, 1e-5)
+    check(load().hqq_b200_glue_silu_mul(ptr(g), ptr(u), ptr(ref), N, DTYPE_CODE[dt], stream_ptr(DEV)))
+    assert ops.decode_linear_fwd(x, (gate, up), [act, u2], 1 | ops.YOP_SILU_MUL_PAIR, h, w, hout, 1e-5)
+    assert torch.equal(act, ref)
+
+
+def test_paired_epilogue_rejects_what_it_cannot_pair():
+    from hqq_b200 import ops
+    from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
+    mk = lambda n, b: HQQLinear.from_weights((torch.randn(n, 512, device=DEV) * 0.05).half(), None, BaseQuantizeConfig(nbits=b, group_size=64, axis=1),
+                                             compute_dtype=torch.float16, device=DEV)
+    x = torch.randn(1, 512, device=DEV).half()
+    o = lambda n: torch.empty(1, n, device=DEV, dtype=torch.float16)
+    with pytest.raises(Exception):  # unequal N
+        ops.decode_linear_fwd(x, (mk(256, 4), mk(512, 4)), [o(256), o(512)], ops.YOP_SILU_MUL_PAIR)
+    assert not ops.decode_linear_fwd(x, (mk(256, 8), mk(256, 8)), [o(256), o(256)], ops.YOP_SILU_MUL_PAIR)  # 8-bit: unsupported -> caller falls back
 
 
 def test_decode_graph_fused_equals_framework_ops():
