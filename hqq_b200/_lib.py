@@ -61,7 +61,9 @@ class DecodeDesc(ctypes.Structure):
                 ("count", c_int), ("W_q", c_void_p), ("scale", c_void_p), ("zero", c_void_p), ("bias", c_void_p), ("y", c_void_p),
                 ("N", c_void_p), ("K", c_int64), ("group_size", c_int), ("nbits", c_int), ("dtype", c_int), ("tp", c_int), ("rank", c_int),
                 ("peer_data", c_void_p), ("red_data", c_void_p), ("y_tagged", c_void_p), ("x_tagged", c_void_p), ("x2_tagged", c_void_p),
-                ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int), ("skip_wait", c_int)]
+                ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int), ("skip_wait", c_int),
+                ("l2_hint", c_void_p * 2), ("l2_hint_rows", c_void_p), ("l2_hint_chunks", c_int), ("l2_hint_row_bytes", c_int),
+                ("l2_hint_chunk_stride", c_int64)]
 
 
 class HQQB200Error(RuntimeError):

@@ -36,6 +36,10 @@ struct TpExchange {  // host-side view of the optional tagged-word exchange (see
   const void* x2_tagged;
   const int* step_ctr;
   int x_index, x_per_step, skip_wait;
+  const void* l2_hint[2];
+  const int64_t* l2_hint_rows;
+  int l2_hint_chunks, l2_hint_row_bytes;
+  int64_t l2_hint_chunk_stride;
 };
 
 constexpr int kMaxProb = 4;   // weight matrices sharing one activation in a single launch (q/k/v, gate/up)
@@ -92,6 +96,11 @@ struct SKArgs {
   const int* step_ctr;
   int x_index, x_per_step;
   int skip_wait;
+  // optional L2 warm-up for the next kernel (hqq_b200_decode_desc::l2_hint*): rows [0, *hint_rows) of hint_chunks chunks
+  const char* hint[2];
+  const long long* hint_rows;
+  int hint_chunks, hint_row_lines;  // 128-byte lines per row
+  long long hint_stride;
 };
 
 template <typename T> struct MT16;
@@ -661,6 +670,15 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   //           1: every input from the preceding kernel is tagged -> no wait at all.
   //           2: our dependents skip THEIR wait, so they must not be released before everything older than us has completed,
   //              i.e. not before our own wait has returned.
+  if (a.hint_rows) {
+    // warm L2 with what the NEXT kernel will read and nobody in this step writes (KV-cache rows below the current position)
+    const long long per_chunk = *a.hint_rows * a.hint_row_lines, total = per_chunk * a.hint_chunks;
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < total; i += (long long)gridDim.x * 256) {
+      const long long ch = i / per_chunk, off = ch * a.hint_stride + ((i - ch * per_chunk) << 7);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.hint[0] + off));
+      if (a.hint[1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.hint[1] + off));
+    }
+  }
   if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
   else { pdl_launch_dependents(); if (a.skip_wait == 0) pdl_wait(); }
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
@@ -715,59 +733,86 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       if (x2) { d = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8); return true; }
       return false;
     };
+    auto put_permuted = [&](int k8, const Vec<T, 8>& v) {
+      Vec<T, 8> w;
+      w.v[0] = v.v[0]; w.v[1] = v.v[2]; w.v[2] = v.v[1]; w.v[3] = v.v[3];
+      w.v[4] = v.v[4]; w.v[5] = v.v[6]; w.v[6] = v.v[5]; w.v[7] = v.v[7];
+      *reinterpret_cast<Vec<T, 8>*>(xs + k8) = w;
+    };
     if (a.xop == 1) {
-      // fused residual add + RMSNorm: every CTA needs the sum of squares of the whole vector (K elements, L2-resident)
-      float ss = 0.0f;
+      // fused residual add + RMSNorm: every CTA needs the sum of squares of the whole vector (K elements, L2-resident).
+      // One pass over global memory: t = x + delta is parked (unpermuted) in xs while its squares are summed, two vectors
+      // per thread in flight; the norm weights of this lane's first two staging vectors are requested up front, so
+      // after the reduction only shared memory is touched.
+      const T* xw = reinterpret_cast<const T*>(a.xw);
       T* hout = reinterpret_cast<T*>(a.h_out);
-      for (int k8 = tid * 8; k8 < a.K; k8 += 256 * 8) {
-        Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
-        Vec<T, 8> d;
-        if (delta8(k8, d)) {
+      const int kg0 = k_lo + lane * 8;
+      Vec<T, 8> g0, g1;
+      if (kg0 < k_hi) g0 = *reinterpret_cast<const Vec<T, 8>*>(xw + kg0);
+      if (kg0 + 256 < k_hi) g1 = *reinterpret_cast<const Vec<T, 8>*>(xw + kg0 + 256);
+      float ss = 0.0f;
+      for (int ka = tid * 8; ka < a.K; ka += 2 * 256 * 8) {
+        const int kb = ka + 256 * 8;
+        const bool has_b = kb < a.K;
+        Vec<T, 8> va = *reinterpret_cast<const Vec<T, 8>*>(x + ka), vb, da, db;
+        if (has_b) vb = *reinterpret_cast<const Vec<T, 8>*>(x + kb);
+        const bool add_a = delta8(ka, da);
+        const bool add_b = has_b && delta8(kb, db);
+        if (add_a) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
+          for (int j = 0; j < 8; ++j) va.v[j] = from_f32_t<T>(to_f32<T>(va.v[j]) + to_f32<T>(da.v[j]));
         }
-        if (hout && blockIdx.x == 0) *reinterpret_cast<Vec<T, 8>*>(hout + k8) = v;  // the residual stream, written once
+        if (add_b) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float f = to_f32<T>(v.v[j]); ss += f * f; }
+          for (int j = 0; j < 8; ++j) vb.v[j] = from_f32_t<T>(to_f32<T>(vb.v[j]) + to_f32<T>(db.v[j]));
+        }
+        *reinterpret_cast<Vec<T, 8>*>(xs + ka) = va;
+        if (has_b) *reinterpret_cast<Vec<T, 8>*>(xs + kb) = vb;
+        if (hout && blockIdx.x == 0) {  // the residual stream, written once
+          *reinterpret_cast<Vec<T, 8>*>(hout + ka) = va;
+          if (has_b) *reinterpret_cast<Vec<T, 8>*>(hout + kb) = vb;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float f = to_f32<T>(va.v[j]); ss += f * f; }
+        if (has_b) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float f = to_f32<T>(vb.v[j]); ss += f * f; }
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       if (lane == 0) part_s[warp] = ss;
-      __syncthreads();  // all 8 warps are still here (CTAs without tiles returned as a whole)
+      __syncthreads();  // all 8 warps are still here (CTAs without tiles returned as a whole); also publishes xs
       float tot = 0.0f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) tot += part_s[w];
       inv = rsqrtf(tot / (float)a.K + a.eps);
       __syncthreads();  // part_s is reused by the tile reduction below
-    }
-    const T* xw = reinterpret_cast<const T*>(a.xw);
-    for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
-      Vec<T, 8> v;
-      if (a.xop == 2 && a.xtag) poll8(a.xtag + (size_t)send_par * a.K + k8, v);
-      else v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
-      if (a.xop == 1) {
-        Vec<T, 8> d;
-        if (delta8(k8, d)) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(v.v[j]) + to_f32<T>(d.v[j]));
-        }
-        const Vec<T, 8> g = *reinterpret_cast<const Vec<T, 8>*>(xw + k8);
+      int i = 0;
+      for (int k8 = kg0; k8 < k_hi; k8 += 256, ++i) {
+        Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(xs + k8);
+        const Vec<T, 8> g = (i == 0) ? g0 : (i == 1) ? g1 : *reinterpret_cast<const Vec<T, 8>*>(xw + k8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(to_f32<T>(v.v[j]) * inv)) * to_f32<T>(g.v[j]));
-      } else if (a.xop == 2) {
-        Vec<T, 8> u;
-        if (a.x2tag) poll8(a.x2tag + (size_t)send_par * a.K + k8, u);
-        else u = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float f = to_f32<T>(v.v[j]);
-          v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(f / (1.0f + __expf(-f)))) * to_f32<T>(u.v[j]));
-        }
+        put_permuted(k8, v);  // in place: every lane rewrites exactly the eight elements it read
       }
-      Vec<T, 8> w;
-      w.v[0] = v.v[0]; w.v[1] = v.v[2]; w.v[2] = v.v[1]; w.v[3] = v.v[3];
-      w.v[4] = v.v[4]; w.v[5] = v.v[6]; w.v[6] = v.v[5]; w.v[7] = v.v[7];
-      *reinterpret_cast<Vec<T, 8>*>(xs + k8) = w;
+    } else {
+      for (int k8 = k_lo + lane * 8; k8 < k_hi; k8 += 256) {
+        Vec<T, 8> v;
+        if (a.xop == 2 && a.xtag) poll8(a.xtag + (size_t)send_par * a.K + k8, v);
+        else v = *reinterpret_cast<const Vec<T, 8>*>(x + k8);
+        if (a.xop == 2) {
+          Vec<T, 8> u;
+          if (a.x2tag) poll8(a.x2tag + (size_t)send_par * a.K + k8, u);
+          else u = *reinterpret_cast<const Vec<T, 8>*>(x2 + k8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float f = to_f32<T>(v.v[j]);
+            v.v[j] = from_f32_t<T>(to_f32<T>(from_f32_t<T>(f / (1.0f + __expf(-f)))) * to_f32<T>(u.v[j]));
+          }
+        }
+        put_permuted(k8, v);
+      }
     }
     __syncwarp();
     for (int g = k_lo / GS + lane; g < k_hi / GS; g += 32) {
@@ -1100,6 +1145,14 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
   a.tp = 1; a.rank = 0; a.red_data = nullptr; a.xtag = nullptr; a.x2tag = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
   a.skip_wait = 0;
   for (int i = 0; i < 8; ++i) a.peer_data[i] = nullptr;
+  a.hint[0] = a.hint[1] = nullptr; a.hint_rows = nullptr; a.hint_chunks = 0; a.hint_row_lines = 0; a.hint_stride = 0;
+  if (tpx && tpx->l2_hint_rows) {
+    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
+    a.hint[0] = reinterpret_cast<const char*>(tpx->l2_hint[0]); a.hint[1] = reinterpret_cast<const char*>(tpx->l2_hint[1]);
+    a.hint_rows = reinterpret_cast<const long long*>(tpx->l2_hint_rows); a.hint_chunks = tpx->l2_hint_chunks;
+    a.hint_row_lines = tpx->l2_hint_row_bytes >> 7; a.hint_stride = tpx->l2_hint_chunk_stride;
+  }
+  if (tpx && !tpx->step_ctr) tpx = nullptr;  // hint only
   if (tpx) {
     HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
     HQQ_REQUIRE(tpx->tp >= 1 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,

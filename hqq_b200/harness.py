@@ -67,6 +67,8 @@ class DecodeModel:
         self.chain_all = os.environ.get("HQQ_B200_CHAIN", "0") == "1"
         self.skip_wait = int(os.environ.get("HQQ_B200_SKIP_WAIT", "1"))
         self.pair_silu = os.environ.get("HQQ_B200_PAIR_SILU", "1") != "0"
+        # measured neutral at cache_len 256 (the attention kernel already prefetches under the q/k/v tail): opt-in
+        self.kv_hint = os.environ.get("HQQ_B200_KV_HINT", "0") == "1"
         self.nbits = nbits
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -254,9 +256,10 @@ class DecodeModel:
             if chain:
                 # [residual add + RMSNorm] -> q/k/v; the delta is the sum of the ranks' down-proj partials of block bi-1
                 ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None, blk["norm1"], h_nxt, s.rms_eps,
-                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None))
+                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None), l2_hint=self._kv_hint(blk))
             else:
-                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps)
+                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps,
+                                            l2_hint=self._kv_hint(blk))
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
@@ -307,6 +310,15 @@ class DecodeModel:
         torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
         check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
         self.pos.add_(1).remainder_(self.cache_len)
+
+    def _kv_hint(self, blk):
+        """The q/k/v launch warms L2 with the cache rows the attention kernel behind it reads (they are evicted by the ~5 GB
+        of weights streamed between two visits of a layer); `pos` is only written by the non-PDL kernel that ends a step."""
+        if not self.kv_hint:
+            return None
+        kc, vc = blk["k_cache"], blk["v_cache"]
+        return {"ptrs": (kc.data_ptr(), vc.data_ptr()), "rows": self.pos.data_ptr(), "chunks": kc.shape[-3],
+                "row_bytes": kc.shape[-1] * kc.element_size(), "chunk_stride": kc.stride(-3) * kc.element_size()}
 
     def _alloc_bufs(self):
         s, dev, dt = self.shape, self.device, self.dtype

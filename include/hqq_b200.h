@@ -184,6 +184,11 @@ typedef struct hqq_b200_decode_desc {
   const void* x_tagged;     /* local [2][K] uint32 (x_op 2), or NULL */
   const void* x2_tagged;
   const int* step_ctr; int x_index; int x_per_step; int skip_wait;
+  /* optional L2 warm-up for the NEXT kernel's read-only inputs (the decode step's KV cache, which the ~5 GB of weights streamed
+   * per token evict between two visits): rows [0, *l2_hint_rows) of `l2_hint_chunks` chunks (kv heads) of both regions are
+   * prefetched into L2 by the whole grid before it waits for its own inputs.  *l2_hint_rows must not be written by a kernel
+   * launched with programmatic dependent launch in the same step.  All zero / NULL = off. */
+  const void* l2_hint[2]; const int64_t* l2_hint_rows; int l2_hint_chunks; int l2_hint_row_bytes; int64_t l2_hint_chunk_stride;
 } hqq_b200_decode_desc;
 int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* desc, void* stream);
 /* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */

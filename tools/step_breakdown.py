@@ -16,14 +16,15 @@ code = DTYPE_CODE[model.dtype]
 hd, hq, hkv = s.head_dim, s.n_heads, s.n_kv_heads
 
 
-def variant(qkv=True, attn=True, o=True, gu=True, down=True, prolog=True, head=False, pair=False):
+def variant(qkv=True, attn=True, o=True, gu=True, down=True, prolog=True, head=False, pair=False, hint=False):
     st = stream_ptr(dev)
     h_cur, h_nxt = b["h"], b["h2"]
     delta = None
     for blk in model.blocks:
         if qkv:
             if prolog:
-                ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps)
+                ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps,
+                                      l2_hint=(model._kv_hint(blk) if hint else None))
                 h_cur, h_nxt = h_nxt, h_cur
             else:
                 ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]])
@@ -82,6 +83,8 @@ def time_variant(name, **kw):
 model.pos.fill_(128)
 time_variant("full step, unpaired silu", head=True, pair=False)
 time_variant("full step, paired silu", head=True, pair=True)
+time_variant("full step, paired silu + kv L2 hint", head=True, pair=True, hint=True)
+time_variant("qkv+attn + kv L2 hint", o=False, gu=False, down=False, hint=True)
 time_variant("blocks only")
 time_variant("gate_up paired only", qkv=False, attn=False, o=False, down=False, pair=True)
 time_variant("gate_up+down paired", qkv=False, attn=False, o=False, pair=True)
