@@ -160,9 +160,12 @@ def kernel_roofline(model, torch, peaks, reps=4):
         x = torch.randn(1, K, device=dev).to(model.dtype)
         outs = [torch.empty(1, N, device=dev, dtype=model.dtype) for N in Ns]
 
+        # the MLP launch ships with the silu*mul epilogue (gate and up rows paired per tile, one output vector)
+        x_op = ops.YOP_SILU_MUL_PAIR if (gname == "gate_up" and model.pair_silu and model.nbits < 8) else 0
+
         def run_all():
             for ls in sets:
-                if not ops.decode_linear_fwd(x, ls, outs):
+                if not ops.decode_linear_fwd(x, ls, outs, x_op):
                     ops.linear_fwd_multi(x, ls, outs)
 
         side = torch.cuda.Stream(device=dev)
@@ -184,7 +187,7 @@ def kernel_roofline(model, torch, peaks, reps=4):
         e1.record(stream)
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / (reps * len(sets))
-        nbytes = sum(N * K * 0.5 + 2 * (N * K // 64) * 2 + N * 2 for N in Ns) + K * 2
+        nbytes = sum(N * K * 0.5 + 2 * (N * K // 64) * 2 for N in Ns) + (Ns[0] if x_op else sum(Ns)) * 2 + K * 2
         per[gname] = {"N": Ns, "K": K, "us": round(ms * 1e3, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         tot_bytes += nbytes
         tot_ms += ms

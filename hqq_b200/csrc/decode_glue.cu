@@ -2,6 +2,8 @@
 // between the fused linears of a Llama-style block at batch 1, written so a decode step is 8 launches per block
 // instead of ~25 framework kernels.  fp16/bf16, one token.  All kernels are PDL-aware (griddepcontrol) so their
 // launch latency overlaps the tail of the previous kernel inside a CUDA graph.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace hqq {
@@ -225,16 +227,23 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
   }
 }
 
-// argmax over n logits -> int64 index (two-stage in one launch via last-block pattern is overkill: one CTA, n ~ 128K)
+// argmax over n logits -> int64 index (first index on ties).  One thread-block cluster of 8 CTAs: each scans an
+// interleaved eighth of the row, the eight candidates meet in CTA 0's shared memory over DSMEM (no workspace, one launch).
+constexpr int kArgmaxCtas = 8;
 template <typename T>
-__global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out) {
+__global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out) {
+  namespace cg = cooperative_groups;
   __shared__ float bv[32];
   __shared__ int bi[32];
+  __shared__ float cv[kArgmaxCtas];
+  __shared__ int ci[kArgmaxCtas];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   pdl_launch_g();
   pdl_wait_g();
   float best = -INFINITY;
   int idx = 0;
-  for (int i = threadIdx.x * 8; i < n; i += blockDim.x * 8) {
+  for (int i = (rank * 1024 + (int)threadIdx.x) * 8; i < n; i += kArgmaxCtas * 1024 * 8) {
     if (i + 8 <= n) {
       const Vec<T, 8> v = *reinterpret_cast<const Vec<T, 8>*>(x + i);
 #pragma unroll
@@ -254,6 +263,14 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, i
   if (threadIdx.x == 0) {
     for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
       if (bv[i] > best || (bv[i] == best && bi[i] < idx)) { best = bv[i]; idx = bi[i]; }
+    cluster.map_shared_rank(cv, 0)[rank] = best;
+    cluster.map_shared_rank(ci, 0)[rank] = idx;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    best = cv[0]; idx = ci[0];
+    for (int i = 1; i < kArgmaxCtas; ++i)
+      if (cv[i] > best || (cv[i] == best && ci[i] < idx)) { best = cv[i]; idx = ci[i]; }
     out[0] = idx;
   }
 }
@@ -334,8 +351,8 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
 extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {
   HQQ_REQUIRE(logits && out && n > 0, HQQ_E_INVALID, "hqq_b200_glue_argmax: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(1), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out);
-  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(1), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out);
+  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out);
   set_error("hqq_b200_glue_argmax: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }

@@ -30,6 +30,12 @@ def test_glue_kernels_match_torch_ops(dt):
     lg = torch.randn(1, 128256, device=DEV).to(dt); out = torch.zeros(1, dtype=torch.long, device=DEV)
     check(lib.hqq_b200_glue_argmax(ptr(lg), 128256, ptr(out), code, st))
     assert int(out) == int(torch.argmax(lg.float(), dim=-1))
+    for n, hot in ((5000, (4097, 77)), (13, (12,)), (8 * 8192 + 3, (8 * 8192 + 2, 8 * 8192 + 1))):  # ties -> first index; ragged tails
+        lg = torch.zeros(1, n, device=DEV).to(dt)
+        for i in hot:
+            lg[0, i] = 3.0
+        check(lib.hqq_b200_glue_argmax(ptr(lg), n, ptr(out), code, st))
+        assert int(out) == min(hot), (n, int(out))
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])

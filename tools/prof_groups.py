@@ -23,7 +23,7 @@ for name, K, Ns in groups:
     outs = [torch.empty(1, N, device="cuda", dtype=torch.float16) for N in Ns]
     flush.fill_(1)  # evict the freshly written weights from the 126 MB L2
     torch.cuda.synchronize()
-    assert ops.decode_linear_fwd(x, layers, outs)
+    assert ops.decode_linear_fwd(x, layers, outs, ops.YOP_SILU_MUL_PAIR if name == "gate_up" else 0)  # the MLP launch ships paired
     torch.cuda.synchronize()
-    nbytes = sum(N * K // 2 + 2 * (N * K // 64) * 2 + N * 2 for N in Ns) + K * 2
+    nbytes = sum(N * K // 2 + 2 * (N * K // 64) * 2 for N in Ns) + (Ns[0] if name == "gate_up" else sum(Ns)) * 2 + K * 2
     print(f"{name}: K={K} N={Ns} algorithmic_bytes={nbytes}", flush=True)
