@@ -192,10 +192,17 @@ def kernel_roofline(model, torch, peaks, reps=4):
         tot_bytes += nbytes
         tot_ms += ms
     achieved = tot_bytes / tot_ms / 1e6
+    # dram bytes per launch (average over the four launch groups) from the committed `ncu --set full` capture of these kernels
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_decode1_traffic.json")) as fh:
+            traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
+    except (OSError, KeyError, ValueError):
+        pass
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "kernel": "hqq::linear_decode1_kernel<half,4,64> (4 launches/block, 128/step)", "peak_source": peaks["source"],
+            "traffic": traffic, "algorithmic_bytes_per_launch": tot_bytes / len(groups), "kernel": "hqq::linear_decode1_kernel<half,4,64> (4 launches/block, 128/step)", "peak_source": peaks["source"],
             "per_launch_group": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
-            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: see profiles/"}
+            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: profiles/r1_decode1_traffic.json (ncu dram bytes)"}
 
 
 def run_gpu(args, rank, world, local_rank):
