@@ -92,7 +92,6 @@ extern "C" int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x
   HQQ_REQUIRE(count >= 1 && count <= 4 && W_q && scale && zero && y && N, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd: 1..4 matrices, non-null arrays");
   HQQ_REQUIRE(x_op >= 0 && (x_op & 15) <= 2 && (x_op >> 4) <= 1, HQQ_E_INVALID,
               "hqq_b200_decode_linear_fwd: x_op must be 0 (none), 1 (add+rmsnorm) or 2 (silu*mul), optionally | HQQ_YOP_SILU_MUL_PAIR");
-  (void)0;
   for (int i = 0; i < count; ++i) {
     if (!small_route_ok(1, N[i], K, group_size, nbits, 1, dtype) || (x_op != 0 && !small_xop_ok(1, K))) {
       set_error("hqq_b200_decode_linear_fwd: matrix %d (N=%lld K=%lld gs=%d nbits=%d dtype=%d) is outside the fused M=1 kernel", i, (long long)N[i],

@@ -200,7 +200,9 @@ int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, vo
 /* y = silu(gate) * up */
 int hqq_b200_glue_silu_mul(const void* gate, const void* up, void* y, int n, int dtype, void* stream);
 /* RoPE(q,k at *pos) + KV-cache append + one-token GQA attention over cache[0..*pos];
- * caches [n_kv_heads, cache_len, head_dim], cos/sin tables [cache_len, head_dim], pos on device */
+ * caches [n_kv_heads, cache_len, head_dim], cos/sin tables [cache_len, head_dim], pos on device.
+ * *pos and cache rows [0, *pos) are read BEFORE the programmatic-dependency wait (L2 prefetch under the previous kernel's
+ * tail): they must have been written by an earlier, completed launch, not by the kernel directly in front of this one. */
 int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v,
                                    const void* cos_table, const void* sin_table,
                                    void* k_cache, void* v_cache, const int64_t* pos, void* out,
