@@ -21,14 +21,22 @@ def install_as_hqq() -> None:
     import types
 
     from .core import bitpack, optimize, quantize, utils
+    from .models import base as models_base
+    from .models import hf as models_hf
+    from .models.hf import base as models_hf_base
 
-    root = types.ModuleType("hqq")
-    core = types.ModuleType("hqq.core")
-    root.core = core
-    root.__path__ = []
-    core.__path__ = []
+    def package(name):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        sys.modules[name] = mod
+        return mod
+
+    root, core, models = package("hqq"), package("hqq.core"), package("hqq.models")
+    root.core, root.models = core, models
     for name, mod in (("quantize", quantize), ("bitpack", bitpack), ("optimize", optimize), ("utils", utils)):
         setattr(core, name, mod)
         sys.modules["hqq.core." + name] = mod
-    sys.modules["hqq"] = root
-    sys.modules["hqq.core"] = core
+    models.base, models.hf = models_base, models_hf
+    sys.modules["hqq.models.base"] = models_base
+    sys.modules["hqq.models.hf"] = models_hf
+    sys.modules["hqq.models.hf.base"] = models_hf_base
