@@ -541,23 +541,27 @@ __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS)
 // depends only on the activation is hoisted out of the per-tile loop: each warp stages ITS k-chunk of x once in shared
 // memory, already permuted to the lane pairing the bit-tricks produce ({k0,k2},{k1,k3}: no PRMT on the weights), and
 // sums it per quantisation group once (no all-ones MMA); the affine correction is applied to the single real column.
-template <typename T, int NBITS, int GS, int MAGIC, int ST>
+// MR = 1 (experimental, HQQ_B200_D1_VARIANT=1042): scale/zero ride the cp.async ring at the same distance as the weights
+// (16-byte copies of the aligned block that holds this unit's 8 bytes) instead of register loads one unit ahead -- ncu showed
+// 18 % of all stall samples on the first use of those registers (DRAM latency under load exceeds one unit of work).
+template <typename T, int NBITS, int GS, int MAGIC, int ST, int MR = 0>
 struct D1Cfg {
   static constexpr int F = 8 / NBITS, P = 16 / F, MPG = GS / 16, GPB = 256 / GS, MB = GPB * 2;
   static constexpr int NWV = (F == 1) ? 8 : 4;
   static constexpr int W_BYTES = ST * NWV * 256 * 16;
-  static constexpr int M_BYTES = 0;               // scale/zero travel through registers
+  static constexpr int M_BYTES = MR ? ST * 8 * 4 * 8 * 16 : 0;  // MR: [stage][warp][vector][row] 16-byte blocks; else registers
   static constexpr int P_BYTES = 2 * 8 * 16 * 4;  // double-buffered: 8 warps x 16 rows
   static int smem(int K) { return W_BYTES + M_BYTES + P_BYTES + K * 2 + (K / GS) * 4; }
 };
 
-template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC>
+template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC, int MR = 0>
 __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
-  using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
+  using C = D1Cfg<T, NBITS, GS, MAGIC, ST, MR>;
   constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, NWV = C::NWV;
   using MM = MT16<T>;
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* wring = reinterpret_cast<uint4*>(smem);
+  uint4* mring = reinterpret_cast<uint4*>(smem + C::W_BYTES);  // MR only
   float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);       // [2][8][16]
   T* xs = reinterpret_cast<T*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES);      // [K] permuted activations
   float* xsum = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES + a.K * 2);  // [K/GS]
@@ -607,6 +611,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 
   int i_tile = 0, i_k = 0;
   const uint8_t *iw_a, *iw_b;
+  const T* im = nullptr;  // MR: this lane's meta vector (c = 0: scale of row a, 1: zero of row a, 2: scale of row b, 3: zero of row b)
   auto issue_setup = [&]() {
     const int gt = (int)blockIdx.x + i_tile * (int)gridDim.x;
     Tile t; int prow_a, prow_b;
@@ -614,13 +619,17 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
     iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
     iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
+    if constexpr (MR != 0) {
+      const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
+      im = ((c & 1) ? t.zero : t.scale) + ((c & 2) ? nb : na) * a.Gk + kb0 * GPB;
+    }
   };
   int to_issue = n_tiles * upt;
   if (to_issue > 0) issue_setup();
   // ---- meta cursor: scale/zero of the NEXT unit travel through registers (plain cached loads, one unit ahead).  They
   // used to ride the cp.async ring, but 8-byte cp.async costs one shared-memory wavefront per lane (ncu: 60 % of all
   // shared wavefronts of the kernel).
-  int m_tile = 0, m_k = 0, m_left = n_tiles * upt;
+  int m_tile = 0, m_k = 0, m_left = (MR != 0) ? 0 : n_tiles * upt;
   const T *ms_a = nullptr, *mz_a = nullptr, *ms_b = nullptr, *mz_b = nullptr;
   auto meta_setup = [&]() {
     const int gt = (int)blockIdx.x + m_tile * (int)gridDim.x;
@@ -654,12 +663,15 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
       }
+      if constexpr (MR != 0)  // the aligned 16 bytes holding this unit's GPB values (rows are 16-byte aligned: host check)
+        cp_async16(&mring[((stage * 8 + warp) * 4 + c) * 8 + r], reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(im) & ~uintptr_t(15)));
       --to_issue;
       if (++i_k == upt) {
         i_k = 0; ++i_tile;
         if (to_issue > 0) issue_setup();
       } else {
         iw_a += 256; iw_b += 256;
+        if constexpr (MR != 0) im += GPB;
       }
     }
     cp_async_commit();
@@ -838,11 +850,20 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
         issue(is);
       }
       cp_async_wait<ST - 1>();
+      const int kb = kb0 + ku;
       float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
+      if constexpr (MR != 0) {
+        // this unit's scale/zero arrived with its weights, copied by OTHER lanes of this warp: every lane has waited for its own
+        // copies, the warp barrier makes them visible to the whole quad (and fences the slot against the next overwrite)
+        __syncwarp();
+        // lanes of a quad read the same 8 bytes (broadcast, conflict-free)
+        const char* mr = reinterpret_cast<const char*>(mring + ((stage * 8 + warp) * 4) * 8) + r * 16 + ((kb * GPB * 2) & 15);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) mv[v] = *reinterpret_cast<const Vec<T, GPB>*>(mr + v * 128);
+      }
 #pragma unroll
       for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(mv[0].v[i]); zA[i] = to_f32<T>(mv[1].v[i]); sB[i] = to_f32<T>(mv[2].v[i]); zB[i] = to_f32<T>(mv[3].v[i]); }
-      meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
-      const int kb = kb0 + ku;
+      if constexpr (MR == 0) meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
       const T* xk = xs + kb * 256 + 16 * c;
       float Sg[4];
 #pragma unroll
@@ -1012,12 +1033,12 @@ static int launch_sk(SKArgs& a, cudaStream_t st) {
   return HQQ_OK;
 }
 
-template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC>
+template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC, int MR = 0>
 static int launch_d1(SKArgs& a, cudaStream_t st) {
-  using C = D1Cfg<T, NBITS, GS, MAGIC, ST>;
+  using C = D1Cfg<T, NBITS, GS, MAGIC, ST, MR>;
   static int max_smem = 0;
   const int smem = C::smem(a.K);
-  auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST, MC>;
+  auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST, MC, MR>;
   if (smem > max_smem) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -1055,20 +1076,25 @@ template <typename T, int NBITS, int GS, int MAGIC>
 static int sk_mt(SKArgs& a, cudaStream_t st) {
   if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
     if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
-    static int variant = -1;  // HQQ_B200_D1_VARIANT = <stages><ctas per SM>, e.g. 42 (default), 43, 33, 23
+    // HQQ_B200_D1_VARIANT (tuning knob): 42 = 4 stages, 2 CTAs per SM (default; 43/33/23/62/41/61/81 were measured and are not
+    // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 1033 = that with 3 stages and 3 CTAs per SM
+    // (both experimental: written after round 1's GPU budget was spent, see D1Cfg)
+    static int variant = -1;
     if (variant < 0) { const char* e = getenv("HQQ_B200_D1_VARIANT"); variant = e ? atoi(e) : 0; }
-    switch (variant) {
-      case 43: return launch_d1<T, NBITS, GS, MAGIC, 4, 3>(a, st);
-      case 33: return launch_d1<T, NBITS, GS, MAGIC, 3, 3>(a, st);
-      case 23: return launch_d1<T, NBITS, GS, MAGIC, 2, 3>(a, st);
-      case 62: return launch_d1<T, NBITS, GS, MAGIC, 6, 2>(a, st);
-      case 41: return launch_d1<T, NBITS, GS, MAGIC, 4, 1>(a, st);
-      case 61: return launch_d1<T, NBITS, GS, MAGIC, 6, 1>(a, st);
-      case 81: return launch_d1<T, NBITS, GS, MAGIC, 8, 1>(a, st);
-      case 32: return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
-      default: break;
+    if (variant == 32) return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
+    if constexpr (GS == 64 && NBITS != 8) {
+      if (variant == 1042 && a.K % 512 == 0) {
+        bool ok = true;  // the ring copies aligned 16-byte blocks: every group row must start on one
+        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
+        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(a, st);
+      }
+      if (variant == 1033 && a.K % 512 == 0 && a.K <= 8192) {  // + 3 stages, 3 CTAs per SM (24 warps): fits while K <= 8192
+        bool ok = true;
+        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
+        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 3, 3, 1>(a, st);
+      }
     }
-    return (a.K > 8192) ? launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);
+    return launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);
   }
   if (a.M <= 8) return launch_sk<T, NBITS, GS, 1, MAGIC>(a, st);
   if (a.M <= 16) return launch_sk<T, NBITS, GS, 2, MAGIC>(a, st);

@@ -1,0 +1,56 @@
+"""GPU: experimental M = 1 kernel variants (HQQ_B200_D1_VARIANT) must be bit-identical to the default kernel -- they only change
+how scale/zero travel (cp.async ring instead of registers) and how many CTAs share an SM.  The knob is read once per process,
+so each variant runs in a subprocess."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %(root)r)
+from hqq_b200 import ops
+from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
+dev = torch.device("cuda", 0)
+out = {}
+for dt in (torch.float16, torch.bfloat16):
+    for nbits in (4, 2, 1):
+        for N, K in ((1024, 1024), (1048, 2048), (512, 3584)):
+            torch.manual_seed(nbits * 1000 + N + K)
+            cfg = BaseQuantizeConfig(nbits=nbits, group_size=64, axis=1)
+            a, b = (HQQLinear.from_weights((torch.randn(N, K, device=dev) * 0.05).to(dt), None, cfg, compute_dtype=dt, device=dev) for _ in range(2))
+            x = torch.randn(1, K, device=dev).to(dt)
+            h, w = torch.randn(1, K, device=dev).to(dt), torch.rand(K, device=dev).to(dt)
+            ya, yb, act, hout = (torch.empty(1, n, device=dev, dtype=dt) for n in (N, N, N, K))
+            assert ops.decode_linear_fwd(x, (a, b), [ya, yb])
+            key = f"{dt}-{nbits}-{N}-{K}"
+            out[key + "-plain"] = torch.cat([ya, yb]).cpu()
+            assert ops.decode_linear_fwd(x, (a, b), [act, yb], 1 | ops.YOP_SILU_MUL_PAIR, h, w, hout, 1e-5)
+            out[key + "-paired"] = act.cpu()
+torch.save(out, sys.argv[1])
+"""
+
+
+def run_variant(variant, path):
+    env = dict(os.environ)
+    env.pop("HQQ_B200_D1_VARIANT", None)
+    if variant:
+        env["HQQ_B200_D1_VARIANT"] = str(variant)
+    subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=600)
+    return torch.load(path, weights_only=True)
+
+
+# Written after round 1's GPU budget was spent: first execution is the driver's round-end run (non-strict: reports XPASS when green).
+@pytest.mark.xfail(strict=False, reason="experimental kernel variants, first GPU execution pending")
+@pytest.mark.parametrize("variant", [1042, 1033])
+def test_experimental_decode_variants_are_bit_identical(tmp_path, variant):
+    ref = run_variant(0, str(tmp_path / "default.pt"))
+    got = run_variant(variant, str(tmp_path / f"v{variant}.pt"))
+    assert ref.keys() == got.keys()
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
