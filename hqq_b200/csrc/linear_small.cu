@@ -258,6 +258,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
 }
+// the same copy, marked evict-first in L2: a stream that is read once should not push the step's reusable lines (KV cache,
+// activations, norm weights) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* g, uint64_t pol) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "l"(pol) : "memory");
+}
 template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* smem, const void* g) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -549,7 +560,7 @@ struct D1Cfg {
   static constexpr int F = 8 / NBITS, P = 16 / F, MPG = GS / 16, GPB = 256 / GS, MB = GPB * 2;
   static constexpr int NWV = (F == 1) ? 8 : 4;
   static constexpr int W_BYTES = ST * NWV * 256 * 16;
-  static constexpr int M_BYTES = MR ? ST * 8 * 4 * 8 * 16 : 0;  // MR: [stage][warp][vector][row] 16-byte blocks; else registers
+  static constexpr int M_BYTES = (MR & 1) ? ST * 8 * 4 * 8 * 16 : 0;  // MR: [stage][warp][vector][row] 16-byte blocks; else registers
   static constexpr int P_BYTES = 2 * 8 * 16 * 4;  // double-buffered: 8 warps x 16 rows
   static int smem(int K) { return W_BYTES + M_BYTES + P_BYTES + K * 2 + (K / GS) * 4; }
 };
@@ -609,6 +620,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     }
   };
 
+  uint64_t wpol = 0;
+  if constexpr ((MR & 2) != 0) wpol = l2_evict_first_policy();
   int i_tile = 0, i_k = 0;
   const uint8_t *iw_a, *iw_b;
   const T* im = nullptr;  // MR: this lane's meta vector (c = 0: scale of row a, 1: zero of row a, 2: scale of row b, 3: zero of row b)
@@ -619,7 +632,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const long long ra = prow_a < t.step ? prow_a : 0, rb = prow_b < t.step ? prow_b : 0;
     iw_a = t.Wq + ra * a.K + (long long)kb0 * 256 + 16 * c;
     iw_b = t.Wq + rb * a.K + (long long)kb0 * 256 + 16 * c;
-    if constexpr (MR != 0) {
+    if constexpr ((MR & 1) != 0) {
       const long long na = prow_a < t.step ? fa * t.step + prow_a : 0, nb = prow_b < t.step ? fb * t.step + prow_b : 0;
       im = ((c & 1) ? t.zero : t.scale) + ((c & 2) ? nb : na) * a.Gk + kb0 * GPB;
     }
@@ -629,7 +642,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   // ---- meta cursor: scale/zero of the NEXT unit travel through registers (plain cached loads, one unit ahead).  They
   // used to ride the cp.async ring, but 8-byte cp.async costs one shared-memory wavefront per lane (ncu: 60 % of all
   // shared wavefronts of the kernel).
-  int m_tile = 0, m_k = 0, m_left = (MR != 0) ? 0 : n_tiles * upt;
+  int m_tile = 0, m_k = 0, m_left = (MR & 1) ? 0 : n_tiles * upt;
   const T *ms_a = nullptr, *mz_a = nullptr, *ms_b = nullptr, *mz_b = nullptr;
   auto meta_setup = [&]() {
     const int gt = (int)blockIdx.x + m_tile * (int)gridDim.x;
@@ -657,13 +670,22 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   meta_fetch();
   auto issue = [&](int stage) {
     if (to_issue > 0) {
+      if constexpr ((MR & 2) != 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
-      if (F == 1) {
+        for (int i = 0; i < 4; ++i) cp_async16_hint(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64, wpol);
+        if (F == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
+          for (int i = 0; i < 4; ++i) cp_async16_hint(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64, wpol);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
+        if (F == 1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
+        }
       }
-      if constexpr (MR != 0)  // the aligned 16 bytes holding this unit's GPB values (rows are 16-byte aligned: host check)
+      if constexpr ((MR & 1) != 0)  // the aligned 16 bytes holding this unit's GPB values (rows are 16-byte aligned: host check)
         cp_async16(&mring[((stage * 8 + warp) * 4 + c) * 8 + r], reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(im) & ~uintptr_t(15)));
       --to_issue;
       if (++i_k == upt) {
@@ -671,7 +693,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
         if (to_issue > 0) issue_setup();
       } else {
         iw_a += 256; iw_b += 256;
-        if constexpr (MR != 0) im += GPB;
+        if constexpr ((MR & 1) != 0) im += GPB;
       }
     }
     cp_async_commit();
@@ -852,7 +874,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       cp_async_wait<ST - 1>();
       const int kb = kb0 + ku;
       float sA[GPB], zA[GPB], sB[GPB], zB[GPB];
-      if constexpr (MR != 0) {
+      if constexpr ((MR & 1) != 0) {
         // this unit's scale/zero arrived with its weights, copied by OTHER lanes of this warp: every lane has waited for its own
         // copies, the warp barrier makes them visible to the whole quad (and fences the slot against the next overwrite)
         __syncwarp();
@@ -863,7 +885,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       }
 #pragma unroll
       for (int i = 0; i < GPB; ++i) { sA[i] = to_f32<T>(mv[0].v[i]); zA[i] = to_f32<T>(mv[1].v[i]); sB[i] = to_f32<T>(mv[2].v[i]); zB[i] = to_f32<T>(mv[3].v[i]); }
-      if constexpr (MR == 0) meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
+      if constexpr ((MR & 1) == 0) meta_fetch();  // next unit's scale/zero: a full unit of work hides the (mostly L1/L2) latency
       const T* xk = xs + kb * 256 + 16 * c;
       float Sg[4];
 #pragma unroll
@@ -1077,7 +1099,8 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
   if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
     if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
     // HQQ_B200_D1_VARIANT (tuning knob): 42 = 4 stages, 2 CTAs per SM (default; 43/33/23/62/41/61/81 were measured and are not
-    // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 1033 = that with 3 stages and 3 CTAs per SM
+    // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 2042 = evict-first weight
+    // stream, 3042 = both, 1033 = both with 3 stages and 3 CTAs per SM
     // (both experimental: written after round 1's GPU budget was spent, see D1Cfg)
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("HQQ_B200_D1_VARIANT"); variant = e ? atoi(e) : 0; }
@@ -1088,10 +1111,16 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
         for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
         if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(a, st);
       }
+      if (variant == 2042) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 2>(a, st);  // evict-first weight stream only
+      if (variant == 3042 && a.K % 512 == 0) {
+        bool ok = true;
+        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
+        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 3>(a, st);
+      }
       if (variant == 1033 && a.K % 512 == 0 && a.K <= 8192) {  // + 3 stages, 3 CTAs per SM (24 warps): fits while K <= 8192
         bool ok = true;
         for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
-        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 3, 3, 1>(a, st);
+        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 3, 3, 3>(a, st);
       }
     }
     return launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);

@@ -1,5 +1,5 @@
 """GPU: experimental M = 1 kernel variants (HQQ_B200_D1_VARIANT) must be bit-identical to the default kernel -- they only change
-how scale/zero travel (cp.async ring instead of registers) and how many CTAs share an SM.  The knob is read once per process,
+how scale/zero travel (cp.async ring instead of registers), the L2 eviction hint of the weight stream and how many CTAs share an SM.  The knob is read once per process,
 so each variant runs in a subprocess."""
 import os
 import subprocess
@@ -36,6 +36,9 @@ torch.save(out, sys.argv[1])
 """
 
 
+_CACHE = {}
+
+
 def run_variant(variant, path):
     env = dict(os.environ)
     env.pop("HQQ_B200_D1_VARIANT", None)
@@ -47,9 +50,11 @@ def run_variant(variant, path):
 
 # Written after round 1's GPU budget was spent: first execution is the driver's round-end run (non-strict: reports XPASS when green).
 @pytest.mark.xfail(strict=False, reason="experimental kernel variants, first GPU execution pending")
-@pytest.mark.parametrize("variant", [1042, 1033])
+@pytest.mark.parametrize("variant", [1042, 2042, 3042, 1033])
 def test_experimental_decode_variants_are_bit_identical(tmp_path, variant):
-    ref = run_variant(0, str(tmp_path / "default.pt"))
+    if "ref" not in _CACHE:
+        _CACHE["ref"] = run_variant(0, str(tmp_path / "default.pt"))
+    ref = _CACHE["ref"]
     got = run_variant(variant, str(tmp_path / f"v{variant}.pt"))
     assert ref.keys() == got.keys()
     for k in ref:
