@@ -382,6 +382,252 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   }
 }
 
+// =====================================================================================================================
+// Variant "ld" (HQQ_B200_GEMM_VARIANT=ld, experimental -- written after round 1's GPU budget was spent, not yet run):
+// ncu on the kernel above shows the dequant warps, not the tensor pipe, on the critical path (tensor pipe 61 % active), and
+// a third of their stall samples sit on `fence.proxy.async` and on the first use of the register-prefetched bytes: the
+// proxy fence waits for the thread's OWN outstanding global loads, so the one-quad-ahead prefetch is serialised behind DRAM
+// latency at every stage.  Here the dequant warps never touch global memory: a loader warp streams the packed tile and its
+// scale/zero into shared-memory rings with cp.async (completion signalled through an mbarrier by
+// cp.async.mbarrier.arrive.noinc, up to 8 k-blocks ahead), the dequant warps read them with LDS.  Everything downstream
+// (swizzled A stage, tcgen05.mma, TMEM epilogue) is unchanged; B gets 3 stages to make room for the rings.
+constexpr int kStagesB = 3;
+constexpr int kMetaSlots = 4;
+constexpr int kLdThreads = 96 + kDequantThreads;  // warp 0: TMA(B) + TMEM alloc, warp 1: MMA, warp 2: loader, warps 3..10: dequant + epilogue
+
+template <int UN, int NBITS>
+struct SmemLd {
+  static constexpr int PR = kTileRows / (8 / NBITS);
+  static constexpr int A_STAGE = kTileRows * 128;
+  static constexpr int B_STAGE = UN * 128;
+  static constexpr int W_STAGE = PR * kBlockK;                                        // packed bytes of one k-block
+  static constexpr int NW = (32 * 1024 / W_STAGE) < 8 ? (32 * 1024 / W_STAGE) : 8;    // 8 k-blocks ahead (8-bit: 4)
+  static constexpr int M_SLOT = kTileRows * 2 * 8;                                    // {scale, zero} x 128 rows x <= 4 groups x 2 B
+  static constexpr int BYTES = kStages * A_STAGE + kStagesB * B_STAGE + NW * W_STAGE + kMetaSlots * M_SLOT + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(4 * kMetaSlots >= NW + 4, "a meta slot must outlive the W stages of its four k-blocks");
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_b(uint32_t smem_addr, const void* g) {
+  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(g), "n"(BYTES) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed (the count is part of init)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int NBITS, int GS, int UN>
+__global__ void __launch_bounds__(kLdThreads, 1) linear_gemm_ld_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  constexpr int F = 8 / NBITS;
+  constexpr int PR = kTileRows / F;
+  constexpr int BPT = 64 * PR / kDequantThreads;
+  constexpr int TPR = 64 / BPT;
+  constexpr int GPQ = 256 / GS;  // groups per four k-blocks
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = SmemLd<UN, NBITS>;
+  using P2 = Pair<T>;
+  constexpr int NW = S::NW;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kStages * S::A_STAGE;
+  uint8_t* sW = sB + kStagesB * S::B_STAGE;
+  uint8_t* sM = sW + NW * S::W_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sM + kMetaSlots * S::M_SLOT);
+  uint64_t* full_a = bars;                       // [kStages]  dequant warps -> MMA (one arrival per warp)
+  uint64_t* empty_a = full_a + kStages;          // [kStages]  MMA (tcgen05.commit) -> dequant warps
+  uint64_t* full_b = empty_a + kStages;          // [kStagesB] TMA -> MMA
+  uint64_t* empty_b = full_b + kStagesB;         // [kStagesB] MMA -> TMA
+  uint64_t* full_w = empty_b + kStagesB;         // [NW] loader lanes (32 async arrivals) -> dequant warps
+  uint64_t* empty_w = full_w + NW;               // [NW] dequant warps (one arrival per warp) -> loader
+  uint64_t* accum_full = empty_w + NW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int prow0 = tile_n * PR;
+  const int m0 = tile_m * UN;
+  const int num_kb = a.K / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty_a[s], 1); }
+      for (int s = 0; s < kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+      for (int s = 0; s < NW; ++s) { mbar_init(&full_w[s], 32); mbar_init(&empty_w[s], kDequantThreads / 32); }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    __syncwarp();
+    tmem_alloc<UN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: activation tiles =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStagesB;
+        mbar_wait(&empty_b[s], ((kb / kStagesB) & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], S::B_STAGE);
+        tma_load_2d(sB + s * S::B_STAGE, &xmap, &full_b[s], kb * kBlockK, m0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    const uint32_t idesc = make_idesc<T>(UN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sa = kb % kStages, sb = kb % kStagesB;
+      mbar_wait(&full_a[sa], (kb / kStages) & 1);
+      mbar_wait(&full_b[sb], (kb / kStagesB) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_desc_sw128(smem_u32(sA + sa * S::A_STAGE));
+        const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(&empty_a[sa]);
+        tc_commit(&empty_b[sb]);
+        if (kb == num_kb - 1) tc_commit(accum_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ================= loader: packed tile + scale/zero -> shared-memory rings (cp.async, no registers) =================
+    const uint32_t sW_u32 = smem_u32(sW), sM_u32 = smem_u32(sM);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sw = kb % NW;
+      mbar_wait(&empty_w[sw], ((kb / NW) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < PR * 4 / 32; ++i) {  // PR rows x four 16-byte chunks, lanes along the row: coalesced 64-byte rows
+        const int id = i * 32 + lane, row = id >> 2, ch = id & 3;
+        const int prow = prow0 + row;
+        const uint8_t* src = a.Wq + (long long)(prow < a.step ? prow : 0) * a.K + kb * kBlockK + ch * 16;
+        cp_async_b<16>(sW_u32 + sw * S::W_STAGE + row * kBlockK + ch * 16, src);
+      }
+      if ((kb & 3) == 0) {  // the groups of k-blocks kb .. kb+3: GPQ values per row and array
+        const int slot = (kb >> 2) % kMetaSlots;
+#pragma unroll
+        for (int i = 0; i < kTileRows * 2 / 32; ++i) {
+          const int id = i * 32 + lane, arr = id >> 7, t = id & (kTileRows - 1);
+          const int f = t / PR, prow = prow0 + t % PR;
+          const long long mrow = (prow < a.step) ? (long long)f * a.step + prow : 0;
+          const T* src = reinterpret_cast<const T*>(arr ? a.zero : a.scale) + mrow * a.Gk + (kb >> 2) * GPQ;
+          cp_async_b<GPQ * 2>(sM_u32 + slot * S::M_SLOT + (arr * kTileRows + t) * (GPQ * 2), src);
+        }
+      }
+      cp_async_mbar_arrive(&full_w[sw]);
+    }
+  } else {
+    // ================= dequant warps: shared-memory packed bytes -> swizzled fp16/bf16 A tile =================
+    static_assert(kStages == 4, "the dequant loop is unrolled over the 4 A stages");
+    const int td = threadIdx.x - 96;
+    const int pr = td / TPR, c = td % TPR;
+    uint32_t soff[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const int row = f * PR + pr;
+      if constexpr (BPT >= 8) soff[f] = (uint32_t)(row * 128) | ((uint32_t)(row & 7) << 16);
+      else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
+    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router)
+    for (int q = 0; q < num_quads; ++q) {
+      typename P2::T2 s2[4][F], z2[4][F];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int kb = 4 * q + d;
+        const int sw = kb % NW;
+        mbar_wait(&full_w[sw], (kb / NW) & 1);
+        if (d == 0) {  // this quad's scale/zero arrived with its first k-block
+          const uint8_t* slot = sM + (q % kMetaSlots) * S::M_SLOT;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const Vec<T, GPQ> sv = *reinterpret_cast<const Vec<T, GPQ>*>(slot + (0 * kTileRows + f * PR + pr) * (GPQ * 2));
+            const Vec<T, GPQ> zv = *reinterpret_cast<const Vec<T, GPQ>*>(slot + (1 * kTileRows + f * PR + pr) * (GPQ * 2));
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) { s2[dd][f] = P2::bcast(sv.v[(dd * kBlockK) / GS]); z2[dd][f] = P2::bcast(zv.v[(dd * kBlockK) / GS]); }
+          }
+        }
+        uint32_t wq[BPT / 4];
+        {
+          const uint8_t* p = sW + sw * S::W_STAGE + pr * kBlockK + c * BPT;
+          if constexpr (BPT == 32) { const uint4 v0 = *reinterpret_cast<const uint4*>(p), v1 = *reinterpret_cast<const uint4*>(p + 16); wq[0] = v0.x; wq[1] = v0.y; wq[2] = v0.z; wq[3] = v0.w; wq[4] = v1.x; wq[5] = v1.y; wq[6] = v1.z; wq[7] = v1.w; }
+          else if constexpr (BPT == 16) { const uint4 v = *reinterpret_cast<const uint4*>(p); wq[0] = v.x; wq[1] = v.y; wq[2] = v.z; wq[3] = v.w; }
+          else if constexpr (BPT == 8) { const uint2 v = *reinterpret_cast<const uint2*>(p); wq[0] = v.x; wq[1] = v.y; }
+          else { wq[0] = *reinterpret_cast<const uint32_t*>(p); }
+        }
+        mbar_wait(&empty_a[d], (uint32_t)(q & 1) ^ 1u);  // A stage index == d (four stages, four k-blocks per quad)
+        const uint32_t stage = sA_u32 + d * S::A_STAGE;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int sh = 8 - NBITS * (f + 1);
+          uint32_t out[BPT / 2];
+#pragma unroll
+          for (int i = 0; i < BPT / 4; ++i) {
+            const uint32_t t = (wq[i] >> sh) & (MASK * 0x01010101u);
+            P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
+          }
+          if constexpr (BPT >= 8) {
+            const uint32_t rowbase = stage + (soff[f] & 0xFFFFu), rx = soff[f] >> 16;
+#pragma unroll
+            for (int ch = 0; ch < BPT / 8; ++ch) {
+              const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+            }
+          } else {
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&full_a[d]); mbar_arrive(&empty_w[sw]); }  // every lane's packed bytes (and meta) are in registers
+      }
+    }
+
+    // ================= epilogue: TMEM -> registers -> y =================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 3) >> 2;             // two warps share a quarter: split the token columns
+    const int t = quarter * 32 + lane;
+    const int tf = t / PR, tp = t % PR;
+    const bool n_ok = (prow0 + tp) < a.step;
+    const int n = tf * a.step + prow0 + tp;
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const bool has_bias = bias != nullptr;
+    T bn = cvt_out<T>(0.0f);
+    if (has_bias && n_ok) bn = bias[n];
+#pragma unroll 1
+    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + col + j;
+        if (n_ok && m < a.M) {
+          T o = cvt_out<T>(__uint_as_float(v[j]));
+          if (has_bias) o = __hadd(o, bn);
+          y[(long long)m * a.N + n] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<UN>(tmem_base);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -410,6 +656,23 @@ static int launch(const void* x, const Args& a, cudaStream_t st) {
   CUresult r = enc(&xmap, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HQQ_REQUIRE(r == CUDA_SUCCESS, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  constexpr int PR = kTileRows / (8 / NBITS);
+  const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, UN));
+  static int variant = -1;  // HQQ_B200_GEMM_VARIANT=ld: loader-warp kernel (experimental, see linear_gemm_ld_kernel)
+  if (variant < 0) { const char* e = getenv("HQQ_B200_GEMM_VARIANT"); variant = (e && !strcmp(e, "ld")) ? 1 : 0; }
+  if (variant == 1) {
+    auto kl = linear_gemm_ld_kernel<T, NBITS, GS, UN>;
+    using SL = SmemLd<UN, NBITS>;
+    static bool attr_set_ld = false;
+    if (!attr_set_ld) {
+      cudaError_t e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES);
+      HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", SL::BYTES, cudaGetErrorString(e));
+      attr_set_ld = true;
+    }
+    kl<<<grid, kLdThreads, SL::BYTES, st>>>(xmap, a);
+    HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05-ld");
+    return HQQ_OK;
+  }
   auto k = linear_gemm_kernel<T, NBITS, GS, UN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -417,8 +680,6 @@ static int launch(const void* x, const Args& a, cudaStream_t st) {
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem<UN>::BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  constexpr int PR = kTileRows / (8 / NBITS);
-  const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, UN));
   k<<<grid, kThreads, Smem<UN>::BYTES, st>>>(xmap, a);
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   return HQQ_OK;
