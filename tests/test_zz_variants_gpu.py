@@ -8,7 +8,11 @@ import sys
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Opt-in (HQQ_B200_RUN_EXPERIMENTAL=1): these kernels were written after round 1's GPU budget was spent and have never run; a
+# protocol bug in them could hang a subprocess until its timeout, which must not be able to eat the default GPU suite's time.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HQQ_B200_RUN_EXPERIMENTAL", "0") != "1",
+                                 reason="experimental kernel variants: set HQQ_B200_RUN_EXPERIMENTAL=1 to run")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPT = r"""
@@ -44,12 +48,10 @@ def run_variant(variant, path):
     env.pop("HQQ_B200_D1_VARIANT", None)
     if variant:
         env["HQQ_B200_D1_VARIANT"] = str(variant)
-    subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=600)
+    subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=240)
     return torch.load(path, weights_only=True)
 
 
-# Written after round 1's GPU budget was spent: first execution is the driver's round-end run (non-strict: reports XPASS when green).
-@pytest.mark.xfail(strict=False, reason="experimental kernel variants, first GPU execution pending")
 @pytest.mark.parametrize("variant", [1042, 2042, 3042, 1033])
 def test_experimental_decode_variants_are_bit_identical(tmp_path, variant):
     if "ref" not in _CACHE:
@@ -91,11 +93,10 @@ def run_gemm(variant, path):
     env.pop("HQQ_B200_GEMM_VARIANT", None)
     if variant:
         env["HQQ_B200_GEMM_VARIANT"] = variant
-    subprocess.run([sys.executable, "-c", GEMM_SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=600)
+    subprocess.run([sys.executable, "-c", GEMM_SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=240)
     return torch.load(path, weights_only=True)
 
 
-@pytest.mark.xfail(strict=False, reason="experimental loader-warp GEMM (HQQ_B200_GEMM_VARIANT=ld), first GPU execution pending")
 def test_loader_warp_gemm_is_bit_identical(tmp_path):
     ref = run_gemm(None, str(tmp_path / "default.pt"))
     got = run_gemm("ld", str(tmp_path / "ld.pt"))
