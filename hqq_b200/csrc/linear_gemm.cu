@@ -687,8 +687,10 @@ static int launch(const void* x, const Args& a, cudaStream_t st) {
 
 template <typename T, int NBITS, int GS>
 static int by_un(const void* x, const Args& a, cudaStream_t st) {
-  if (a.M <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
-  if (a.M <= 128) return launch<T, NBITS, GS, 128>(x, a, st);
+  static int un_cap = -1;  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
+  if (un_cap < 0) { const char* e = getenv("HQQ_B200_GEMM_UN"); un_cap = e ? atoi(e) : 256; }
+  if (a.M <= 64 || un_cap <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
+  if (a.M <= 128 || un_cap <= 128) return launch<T, NBITS, GS, 128>(x, a, st);
   return launch<T, NBITS, GS, 256>(x, a, st);
 }
 
