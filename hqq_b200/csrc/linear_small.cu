@@ -704,6 +704,32 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   //           1: every input from the preceding kernel is tagged -> no wait at all.
   //           2: our dependents skip THEIR wait, so they must not be released before everything older than us has completed,
   //              i.e. not before our own wait has returned.
+  if constexpr ((MR & 4) != 0) {
+    // MR bit 2: while this CTA waits for the previous kernel (its ring is full), pull the next units of its OWN weight stream
+    // into L2 -- the DRAM pipe is otherwise idle on this SM until the dependency resolves.  The cursor is advanced on a copy.
+    constexpr int kPfUnits = 6;
+    const int s_tile = i_tile, s_k = i_k, s_left = to_issue;
+    const uint8_t *s_a = iw_a, *s_b = iw_b;
+    const T* s_m = im;
+    for (int u = 0; u < kPfUnits && to_issue > 0; ++u) {
+      if (c == 0) {  // one lane per packed row: the unit's 256 bytes = two 128-byte lines
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_a));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_a + 128));
+        if (F == 1) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_b));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_b + 128));
+        }
+      }
+      --to_issue;
+      if (++i_k == upt) {
+        i_k = 0; ++i_tile;
+        if (to_issue > 0) issue_setup();
+      } else {
+        iw_a += 256; iw_b += 256;
+      }
+    }
+    i_tile = s_tile; i_k = s_k; to_issue = s_left; iw_a = s_a; iw_b = s_b; im = s_m;
+  }
   if (a.hint_rows) {
     // warm L2 with what the NEXT kernel will read and nobody in this step writes (KV-cache rows below the current position)
     const long long per_chunk = *a.hint_rows * a.hint_row_lines, total = per_chunk * a.hint_chunks;
@@ -1100,7 +1126,7 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
     if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
     // HQQ_B200_D1_VARIANT (tuning knob): 42 = 4 stages, 2 CTAs per SM (default; 43/33/23/62/41/61/81 were measured and are not
     // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 2042 = evict-first weight
-    // stream, 3042 = both, 1033 = both with 3 stages and 3 CTAs per SM
+    // stream, 3042 = both, 1033 = both with 3 stages and 3 CTAs per SM, 4042 = L2 prefetch under the dependency wait, 7042/7033 = all
     // (both experimental: written after round 1's GPU budget was spent, see D1Cfg)
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("HQQ_B200_D1_VARIANT"); variant = e ? atoi(e) : 0; }
@@ -1112,6 +1138,12 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
         if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(a, st);
       }
       if (variant == 2042) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 2>(a, st);  // evict-first weight stream only
+      if (variant == 4042) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 4>(a, st);  // L2 prefetch under the dependency wait only
+      if ((variant == 7042 || variant == 7033) && a.K % 512 == 0 && (variant == 7042 || a.K <= 8192)) {
+        bool ok = true;
+        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
+        if (ok) return variant == 7042 ? launch_d1<T, NBITS, GS, MAGIC, 4, 2, 7>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 3, 3, 7>(a, st);
+      }
       if (variant == 3042 && a.K % 512 == 0) {
         bool ok = true;
         for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);

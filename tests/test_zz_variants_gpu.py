@@ -52,7 +52,7 @@ def run_variant(variant, path):
     return torch.load(path, weights_only=True)
 
 
-@pytest.mark.parametrize("variant", [1042, 2042, 3042, 1033])
+@pytest.mark.parametrize("variant", [1042, 2042, 3042, 1033, 4042, 7042, 7033])
 def test_experimental_decode_variants_are_bit_identical(tmp_path, variant):
     if "ref" not in _CACHE:
         _CACHE["ref"] = run_variant(0, str(tmp_path / "default.pt"))
