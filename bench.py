@@ -9,7 +9,8 @@ stack whose 224 block linears are HQQLinear layers quantised on the GPU by this 
 configs[1]).  `value` is tokens/s with the token fed back on the device (inputs resident in HBM); `e2e` is the same loop
 driven from the host through the public API: every step copies the input token from pinned host memory, replays the
 decode graph and reads the produced token back.  For N > 1 the same model is tensor-parallel over N GPUs (column-sharded
-q/k/v/gate/up, row-sharded o/down + one NCCL all-reduce each), i.e. strong scaling.
+q/k/v/gate/up, row-sharded o/down whose partial sums are exchanged inside the kernels over NVLink peer memory -- NCCL
+all-reduce with HQQ_B200_TP_MODE=nccl), i.e. strong scaling.
 
 `--impl reference` times the reference algorithm's CPU implementation (the oracle port of HQQBackend.PYTORCH:
 dequantise -> matmul per linear) on this box's host cores on a bounded sample of the same workload.
