@@ -220,7 +220,11 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     lib = _lib.load()
-    shape = harness.LLAMA3_8B
+    big = args.model == "70b"  # BASELINE configs[4] (bs = 1 leg): needs --gpus 8 (4.8 GB of packed weights per rank); not the default line
+    shape = harness.LLAMA3_70B if big else harness.LLAMA3_8B
+    metric = "llama3_70b_4bit_gs64_decode_tokens_per_s" if big else METRIC
+    workload = ("Llama-3-70B-shaped decode bs=1 seq=1, 80 blocks x 7 HQQLinear 4-bit gs=64 axis=1, fp16 lm_head (BASELINE configs[4], bs=1)"
+                if big else WORKLOAD)
     n_layers = args.layers or shape.n_layers
     model = harness.DecodeModel(shape, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=args.cache_len, tp=world,
                                 rank=rank, process_group=pg, n_layers=n_layers)
@@ -284,10 +288,10 @@ def run_gpu(args, rank, world, local_rank):
         value = args.steps / (dev_ms / 1e3)
         e2e = args.steps / (e2e_ms / 1e3)
         bytes_tok = model.bytes_per_token() * world  # whole-job bytes (each rank streams 1/world of the blocks + full lm_head)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD,
+                "config": {"workload": workload,
                            "path": f"fused sm_100a kernels, kv cache {args.cache_len}, CUDA graph; {model.bytes_per_token() / 1e9:.2f} GB streamed per step "
                                    ">> 126 MB L2 (inputs larger than L2, no flush needed)",
                            "parallelism": f"tp{world}", "layers": n_layers},
@@ -299,7 +303,7 @@ def run_gpu(args, rank, world, local_rank):
             line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
         if roof is not None:
             line["roofline"] = roof
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not big:
             v, info = cpu_reference_tokens_per_s(budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
         print(json.dumps(line), flush=True)
@@ -321,6 +325,7 @@ def main():
     ap.add_argument("--cache-len", type=int, default=256)
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] at bs=1 (use with --gpus 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
