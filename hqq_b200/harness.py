@@ -358,3 +358,18 @@ class DecodeModel:
         self.graph.replay()
         if feed_back:
             self.tok.copy_(self.next_tok)
+
+
+# ---------------------------------------------------------------------------------------------- quantise-only sharding
+def assign_layers(sizes, world: int):
+    """Quantisation shards by layer with no collective (every linear depends only on its own weights, quantize.py:76-180):
+    size-balanced assignment of layer indices to ranks -- largest first, each to the least-loaded rank (ties -> lowest rank),
+    deterministic so every rank computes the same plan without talking.  Returns one index list per rank."""
+    order = sorted(range(len(sizes)), key=lambda i: (-sizes[i], i))
+    load = [0] * world
+    plan = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        plan[r].append(i)
+        load[r] += sizes[i]
+    return [sorted(p) for p in plan]

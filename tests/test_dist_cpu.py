@@ -68,3 +68,17 @@ def test_row_parallel_allreduce_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_layer_sharding_plan_is_complete_balanced_and_deterministic():
+    """Quantise-only sharding (BASELINE configs[3]): every rank derives the same size-balanced plan, no collective."""
+    from hqq_b200 import harness
+    dims = harness.shard_dims(harness.LLAMA3_70B, 1)
+    sizes = [dims[n][0] * dims[n][1] for _ in range(80) for n in ("q", "k", "v", "o", "gate", "up", "down")]
+    for world in (1, 2, 4, 8):
+        plan = harness.assign_layers(sizes, world)
+        assert plan == harness.assign_layers(list(sizes), world)
+        assert sorted(i for p in plan for i in p) == list(range(len(sizes)))
+        loads = [sum(sizes[i] for i in p) for p in plan]
+        assert max(loads) - min(loads) <= max(sizes)
+    assert harness.assign_layers([5, 1, 1], 2) == [[0], [1, 2]]
