@@ -9,3 +9,5 @@ timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
+# BASELINE configs[2]: the per-linear sweep (M x nbits x 3 shapes), kept under profiles/ afterwards
+timeout 900 python tools/prof_gemm.py 1,16,32,128,1024,4096 8,4,3,2,1 > gpurun_out/gemm_sweep.log 2>&1; grep -c fused gpurun_out/gemm_sweep.log
