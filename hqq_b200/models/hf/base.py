@@ -9,28 +9,37 @@ from __future__ import annotations
 from ..base import BaseHQQModel, BasePatch, init_empty_weights
 
 
+def _auto_class_for(architectures):
+    """The transformers auto class that rebuilds a saved architecture (hf/base.py:29-37: CausalLM and
+    SequenceClassification heads are recognised, everything else is a bare AutoModel)."""
+    import transformers
+
+    names = list(architectures or [])
+    if len(names) == 1:
+        for marker, auto in (("CausalLM", transformers.AutoModelForCausalLM),
+                             ("SequenceClassification", transformers.AutoModelForSequenceClassification)):
+            if marker in names[0]:
+                return auto
+    return transformers.AutoModel
+
+
 class BaseHQQHFModel(BaseHQQModel):
+    """`cache_model` / `create_model` for transformers models: the architecture is the model's own config.json."""
+
     @classmethod
     def cache_model(cls, model, save_dir):
-        model.config.architectures = [model.__class__.__name__]
-        model.config.save_pretrained(save_dir)
+        config = model.config
+        config.architectures = [type(model).__name__]
+        config.save_pretrained(save_dir)
 
     @classmethod
     def create_model(cls, save_dir, kwargs):
         import transformers
 
-        model_kwargs = {k: kwargs[k] for k in ("attn_implementation",) if k in kwargs}
         config = transformers.AutoConfig.from_pretrained(cls.get_config_file(save_dir))
-        auto_class = transformers.AutoModel
-        archs = config.architectures or []
-        if len(archs) == 1:
-            if "CausalLM" in archs[0]:
-                auto_class = transformers.AutoModelForCausalLM
-            elif "SequenceClassification" in archs[0]:
-                auto_class = transformers.AutoModelForSequenceClassification
+        passthrough = {key: kwargs[key] for key in ("attn_implementation",) if key in kwargs}
         with init_empty_weights():
-            model = auto_class.from_config(config, **model_kwargs)
-        return model
+            return _auto_class_for(config.architectures).from_config(config, **passthrough)
 
 
 class AutoHQQHFModel(BaseHQQHFModel, BasePatch):
