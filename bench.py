@@ -226,6 +226,8 @@ def run_gpu(args, rank, world, local_rank):
     workload = ("Llama-3-70B-shaped decode bs=1 seq=1, 80 blocks x 7 HQQLinear 4-bit gs=64 axis=1, fp16 lm_head (BASELINE configs[4], bs=1)"
                 if big else WORKLOAD)
     n_layers = args.layers or shape.n_layers
+    if args.cache_len <= 0:  # every timed loop starts at position 0 and must not wrap inside the cache
+        args.cache_len = min(8192, max(256, args.steps + max(args.warmup, 3) + 8))
     model = harness.DecodeModel(shape, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=args.cache_len, tp=world,
                                 rank=rank, process_group=pg, n_layers=n_layers)
     lib.hqq_b200_launch_count_reset()
@@ -322,7 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="hqq_b200", choices=["hqq_b200", "reference"])
-    ap.add_argument("--cache-len", type=int, default=256)
+    ap.add_argument("--cache-len", type=int, default=0, help="KV-cache length; 0 = large enough that the timed loops never wrap (>= 256)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] at bs=1 (use with --gpus 8)")
