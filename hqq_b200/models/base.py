@@ -390,6 +390,9 @@ class BaseHQQModel:
                 del config._attn_implementation_autoset
             config.to_json_file(os.path.join(save_dir, "config.json"))
 
+        for module in model.modules():  # safetensors holds tensors only (save_quantized switches the encoding off)
+            if isinstance(module, HQQLinear):
+                module.encoded_state_dict = True
         tensors = model.state_dict()
         host = lambda keys: {k: tensors[k].cpu().contiguous() for k in keys}
         num_chunks = num_layers // num_blocks_per_file
