@@ -13,6 +13,9 @@
 // Arithmetic notes (see DESIGN.md "parity"): everything is fp32 with explicit non-fused mul/add where the
 // final W_q depends on it; inside the solver W_r = (W_q - z) * (1/s) replaces the division and
 // |x|^(p-1) is ex2(p-1 * lg2|x|) on the SFU -- both perturb the zero-point at the 1e-7 relative level.
+#include <math.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hqq {
@@ -26,6 +29,7 @@ struct SolverArgs {
   int gs;
   int maxv, round_zero, iters, lp_is_one;
   float inv_beta, pm1;
+  float thr;  // |W - W_r| below this shrinks to exactly 0 (see solver_axis1_fast_kernel); 0 disables the shortcut
   const float* s_init;  // optional [G]: caller-supplied inverse scale / zero (optimize_weights_proximal seam)
   const float* z_init;
   float* s_inv;     // [G]   inverse scale (the solver's `scale`)
@@ -188,6 +192,100 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis1_kernel(SolverArgs
       if (valid && l == 0) a.hist[(long long)(it + 1) * a.G + g] = st.z;
       acc.add(it, valid ? errsum : 0.0f);
     }
+  }
+  block_flush_errors(err_w, a.iters, a.partial);
+}
+
+// ---- K1, axis = 1, fast variant (HQQ_B200_SOLVER_VARIANT=1): same results bit for bit, ~5x fewer instructions ----
+// Two exact shortcuts on top of solver_axis1_kernel:
+//  (1) shrink_lp_op(x) is exactly 0 wherever |x| - (1/beta)|x|^(p-1) <= 0, i.e. |x| <= beta^(-1/(2-p)) (0.170 for the
+//      default beta = 10, p = 0.7; optimize.py:96-108).  Quantisation errors of real weight matrices are far below that,
+//      so W_e = 0, `W_f - W_e` = W_f and the update collapses to z = mean(W_q - W_f*scale): no SFU work, and W_f*scale is
+//      loop-invariant.  The warp falls back to the full formula whenever any of its elements is at or above `thr`
+//      (= 0.9 x the root, a 10 % margin against the 2^-22 error of ex2/lg2) -- a warp-uniform branch.
+//  (2) one iteration is a deterministic function of the group's zero-point alone.  Once z_{i+1} == z_i (bitwise) every later
+//      iteration repeats the same W_q, error and zero, so the warp stops as soon as all of its groups sit on a fixed point and
+//      writes the remaining trajectory slots / error sums without recomputing them (measured on Gaussian weights: a group is
+//      fixed after 3.4 iterations on average, a warp of four groups after 7.4, instead of 20).
+template <typename TIn, int L>
+__global__ void __launch_bounds__(kSolverThreads) solver_axis1_fast_kernel(SolverArgs a) {
+  __shared__ double err_w[kSolverThreads / 32][kMaxIters];
+  for (int i = threadIdx.x; i < (kSolverThreads / 32) * kMaxIters; i += blockDim.x) (&err_w[0][0])[i] = 0.0;
+  __syncthreads();
+  double* row = err_w[threadIdx.x >> 5];
+  constexpr int GPW = 32 / L;
+  const int lane = threadIdx.x & 31, l = lane % L;
+  const long long warp_global = (long long)blockIdx.x * (kSolverThreads / 32) + (threadIdx.x >> 5);
+  const long long warp_stride = (long long)gridDim.x * (kSolverThreads / 32);
+  const float fmaxv = (float)a.maxv;
+  const float thr = a.thr;
+  const TIn* W = reinterpret_cast<const TIn*>(a.W);
+
+  for (long long gb = warp_global * GPW; gb < a.G; gb += warp_stride * GPW) {  // warp-uniform
+    const long long g = gb + lane / L;
+    const bool valid = g < a.G;
+    float w[8];
+    if (valid) {
+      load8_group<TIn>(W + g * (long long)a.gs, l, L, w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = 0.0f;
+    }
+    float mn = w[0], mx = w[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { mn = fminf(mn, w[j]); mx = fmaxf(mx, w[j]); }
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    GroupState st;
+    if (a.s_init) init_group_ext(a, g, valid, st);
+    else init_group(mn, mx, a.maxv, a.round_zero, st);
+    if (valid && l == 0) { a.s_inv[g] = st.s; a.hist[g] = st.z; }
+    float ws[8];  // W_f * scale, the same rounding solver_elem applies every iteration
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[j] = __fmul_rn(w[j], st.s);
+    float ew = 0.0f;  // warp-wide error sum of the last iteration executed
+    int it = 0;
+    while (it < a.iters) {
+      float errsum = 0.0f, zs = 0.0f, amax = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float q = rint_magic(__fadd_rn(ws[j], st.z));
+        q = fminf(fmaxf(q, 0.0f), fmaxv);
+        const float wr = __fmul_rn(__fsub_rn(q, st.z), st.rs);
+        const float ad = fabsf(__fsub_rn(w[j], wr));
+        errsum += ad;
+        amax = fmaxf(amax, ad);
+        zs += __fsub_rn(q, ws[j]);
+      }
+      if (__any_sync(0xffffffffu, !(amax < thr))) {  // some |W - W_r| may survive the shrinkage: full formula for the warp
+        zs = 0.0f;
+        float unused = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
+      }
+#pragma unroll
+      for (int o = 1; o < L; o <<= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+      // torch.mean = sum / n; n = 8L is a power of two, so the correctly rounded product with 1/n IS the correctly rounded quotient
+      const float znew = __fmul_rn(zs, 1.0f / (float)(8 * L));
+      if (valid && l == 0) a.hist[(long long)(it + 1) * a.G + g] = znew;
+      ew = valid ? errsum : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ew += __shfl_xor_sync(0xffffffffu, ew, o);  // same order as ErrAcc::add
+      if (lane == 0) row[it] += (double)ew;
+      const bool fixed = !valid || __float_as_uint(znew) == __float_as_uint(st.z);
+      st.z = znew;
+      ++it;
+      if (__all_sync(0xffffffffu, fixed)) break;
+    }
+    // iterations it .. iters-1 would reproduce (st.z, ew) exactly: fill their slots without recomputing them
+    __syncwarp();
+    if (valid)
+      for (int t = it + l; t < a.iters; t += L) a.hist[(long long)(t + 1) * a.G + g] = st.z;
+    for (int t = it + lane; t < a.iters; t += 32) row[t] += (double)ew;
+    __syncwarp();
   }
   block_flush_errors(err_w, a.iters, a.partial);
 }
@@ -402,9 +500,25 @@ static Layout make_layout(long long N, long long K, int gs, int nbits, int axis,
   return L;
 }
 
+// HQQ_B200_SOLVER_VARIANT=1 selects solver_axis1_fast_kernel (bit-identical outputs; written after round 1's GPU budget was
+// spent, so it stays opt-in until tests/test_zz_variants_gpu.py has seen it green).  Read per call: quantisation is not launch-bound.
+static int solver_variant() {
+  const char* e = getenv("HQQ_B200_SOLVER_VARIANT");
+  return e ? atoi(e) : 0;
+}
+
 template <typename TIn>
 static int launch_solver(const SolverArgs& a, int axis, int nblocks, cudaStream_t st) {
-  if (axis == 1 && fast_axis1(a.gs)) {
+  if (axis == 1 && fast_axis1(a.gs) && solver_variant() == 1) {
+    switch (a.gs / 8) {
+      case 1: solver_axis1_fast_kernel<TIn, 1><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 2: solver_axis1_fast_kernel<TIn, 2><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 4: solver_axis1_fast_kernel<TIn, 4><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 8: solver_axis1_fast_kernel<TIn, 8><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 16: solver_axis1_fast_kernel<TIn, 16><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 32: solver_axis1_fast_kernel<TIn, 32><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+    }
+  } else if (axis == 1 && fast_axis1(a.gs)) {
     switch (a.gs / 8) {
       case 1: solver_axis1_kernel<TIn, 1><<<nblocks, kSolverThreads, 0, st>>>(a); break;
       case 2: solver_axis1_kernel<TIn, 2><<<nblocks, kSolverThreads, 0, st>>>(a); break;
@@ -458,6 +572,8 @@ static int quantize_typed(const void* W, long long N, long long K, int gs, int n
   a.s_init = s_init; a.z_init = z_init;
   a.maxv = maxv; a.round_zero = round_zero; a.iters = optimize ? iters : 0;
   a.lp_is_one = (lp_norm == 1.0f); a.inv_beta = 1.0f / beta; a.pm1 = lp_norm - 1.0f;
+  // below thr the shrinkage is exactly zero: lp = 1 -> |x| <= 1/beta; lp < 1 -> |x| <= beta^(-1/(2-lp)) (10 % margin for the SFU)
+  a.thr = a.lp_is_one ? a.inv_beta : (lp_norm < 1.0f ? 0.9f * (float)pow((double)a.inv_beta, 1.0 / (2.0 - (double)lp_norm)) : 0.0f);
   a.s_inv = reinterpret_cast<float*>(ws + L.off_s);
   a.hist = reinterpret_cast<float*>(ws + L.off_hist);
   a.partial = reinterpret_cast<double*>(ws + L.off_partial);

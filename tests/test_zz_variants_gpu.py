@@ -103,3 +103,32 @@ def test_loader_warp_gemm_is_bit_identical(tmp_path):
     assert ref.keys() == got.keys()
     for k in ref:
         assert torch.equal(ref[k], got[k]), k
+
+
+@pytest.mark.parametrize("src", [torch.float16, torch.bfloat16, torch.float32])
+def test_fast_solver_variant_is_bit_identical(src):
+    """HQQ_B200_SOLVER_VARIANT=1 (threshold shortcut + per-warp fixed-point exit, csrc/quantize.cu) must reproduce the default
+    solver bit for bit: packed levels, scale, zero, the iteration count and every per-iteration error.  The knob is read on each
+    call, so both run in this process.  tests/test_solver_shortcuts_cpu.py proves the shortcuts on the oracle's arithmetic."""
+    from hqq_b200 import ops
+    dev = torch.device("cuda", 0)
+    cases = [(4, 64, 1024, 1024, 0.02), (4, 64, 1000, 512, 1.0),    # std 1.0: errors above the threshold -> the fallback runs
+             (2, 64, 512, 2048, 0.02), (2, 32, 256, 512, 2.0), (8, 128, 512, 1024, 0.05), (1, 16, 128, 512, 0.02),
+             (3, 64, 330, 640, 0.02), (4, 8, 96, 256, 0.5), (4, 256, 64, 1024, 0.02), (4, 64, 38, 64, 0.02)]
+    for nbits, gs, N, K, std in cases:
+        for lp in (0.7, 1.0):
+            torch.manual_seed(nbits * 100 + gs + N)
+            W = (torch.randn(N, K, device=dev) * std).to(src)
+            outs = []
+            for variant in ("0", "1"):
+                os.environ["HQQ_B200_SOLVER_VARIANT"] = variant
+                try:
+                    Wq, s, z, tr = ops.quantize(W, nbits, gs, 1, nbits == 4, True, lp_norm=lp, want_trace=True)
+                    torch.cuda.synchronize()
+                finally:
+                    os.environ.pop("HQQ_B200_SOLVER_VARIANT", None)
+                outs.append((Wq.cpu(), s.cpu(), z.cpu(), tr["info"].cpu(), tr["errors"].cpu()))
+            for a, b, what in zip(outs[0], outs[1], ("W_q", "scale", "zero", "info", "errors")):
+                a = a.view(torch.int32) if a.dtype == torch.float32 else a
+                b = b.view(torch.int32) if b.dtype == torch.float32 else b
+                assert torch.equal(a, b), (what, nbits, gs, N, K, std, lp)
