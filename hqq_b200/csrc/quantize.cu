@@ -550,7 +550,13 @@ static int launch_quant_pack(const void* W, const float* s_inv, const float* his
   bool vec = (n % 4 == 0) && (L.total % 4 == 0) && aligned(W, a_in) && aligned(out, 4 * sizeof(PT)) &&
              (axis == 1 ? (gs % 4 == 0) : (L.C % 4 == 0));
   const long long gdiv = (axis == 1) ? gs : L.C;
-  if (vec) {
+  // 16-bit sources: 8 packed elements per thread -> 16-byte loads of W instead of 8-byte ones (part of the opt-in fast variant)
+  const bool vec8 = vec && sizeof(TIn) == 2 && axis == 1 && solver_variant() == 1 && (n % 8 == 0) && (L.total % 8 == 0) &&
+                    (gs % 8 == 0) && aligned(W, 16) && aligned(out, 8 * sizeof(PT) >= 16 ? 16 : 8 * sizeof(PT));
+  if (vec8) {
+    unsigned grid = (unsigned)cdiv(cdiv(n, 8), 256);
+    quant_pack_kernel<NBITS, TIn, 8, 1><<<grid, 256, 0, st>>>((const TIn*)W, s_inv, hist, info, (PT*)out, n, L.total, gdiv, L.G, maxv, scale_out, zero_out);
+  } else if (vec) {
     unsigned grid = (unsigned)cdiv(cdiv(n, 4), 256);
     if (axis == 1) quant_pack_kernel<NBITS, TIn, 4, 1><<<grid, 256, 0, st>>>((const TIn*)W, s_inv, hist, info, (PT*)out, n, L.total, gdiv, L.G, maxv, scale_out, zero_out);
     else quant_pack_kernel<NBITS, TIn, 4, 0><<<grid, 256, 0, st>>>((const TIn*)W, s_inv, hist, info, (PT*)out, n, L.total, gdiv, L.G, maxv, scale_out, zero_out);
