@@ -383,6 +383,228 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 }
 
 // =====================================================================================================================
+// Variant "un512" (HQQ_B200_GEMM_VARIANT=un512, experimental -- written after round 1's GPU budget was spent, not yet run):
+// ncu on linear_gemm_kernel shows the dequant warps, not the tensor pipe, on the critical path (tensor pipe 61 % active).  Their
+// work per weight is already near its floor for the reference's two-rounding dequant (2.5 ALU ops per weight), so the lever is
+// amortisation: here every dequantised A stage feeds TWO 128 x 256 accumulators (all 512 TMEM columns), i.e. 512 tokens per
+// weight tile instead of 256 -- half the dequant work, packed-byte traffic and A-stage stores per flop.  The A ring keeps four
+// 16 KB stages, the B ring has two 64 KB stages (two TMA boxes of 256 tokens each) with their own empty barriers.
+struct Smem512 {
+  static constexpr int UN = 512, UNH = 256, kStagesB = 2;
+  static constexpr int A_STAGE = kTileRows * 128;
+  static constexpr int B_HALF = UNH * 128;
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int BYTES = kStages * A_STAGE + kStagesB * B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <typename T, int NBITS, int GS>
+__global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  constexpr int F = 8 / NBITS;             // slabs per byte
+  constexpr int PR = kTileRows / F;        // packed rows per tile
+  constexpr int BPT = 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
+  constexpr int TPR = 64 / BPT;            // dequant threads per packed row
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = Smem512;
+  constexpr int UN = S::UN, UNH = S::UNH;
+  using P2 = Pair<T>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * S::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::A_STAGE + S::kStagesB * S::B_STAGE);
+  uint64_t* full_a = bars;                      // [kStages]  dequant warps -> MMA (one arrival per warp)
+  uint64_t* empty = full_a + kStages;           // [kStages]  MMA (tcgen05.commit) -> dequant warps
+  uint64_t* full_b = empty + kStages;           // [kStagesB] TMA -> MMA (1 arrival + tx bytes of both halves)
+  uint64_t* empty_b = full_b + S::kStagesB;     // [kStagesB] MMA (tcgen05.commit) -> TMA
+  uint64_t* accum_full = empty_b + S::kStagesB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int prow0 = tile_n * PR;           // first packed row of the tile
+  const int m0 = tile_m * UN;
+  const int num_kb = a.K / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < S::kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    __syncwarp();
+    tmem_alloc<UN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: activation tiles =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S::kStagesB;
+        mbar_wait(&empty_b[s], ((kb / S::kStagesB) & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], S::B_STAGE);  // both boxes; a box past the last token is zero-filled and still counts in full
+        tma_load_2d(sB + s * S::B_STAGE, &xmap, &full_b[s], kb * kBlockK, m0);
+        tma_load_2d(sB + s * S::B_STAGE + S::B_HALF, &xmap, &full_b[s], kb * kBlockK, m0 + UNH);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    const uint32_t idesc = make_idesc<T>(UNH);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages, sb = kb % S::kStagesB;
+      mbar_wait(&full_a[s], (kb / kStages) & 1);
+      mbar_wait(&full_b[sb], (kb / S::kStagesB) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_desc_sw128(smem_u32(sA + s * S::A_STAGE));
+        const uint64_t bdesc0 = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE));
+        const uint64_t bdesc1 = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE + S::B_HALF));
+        // the same dequantised A stage feeds two accumulators (TMEM columns 0..255 and 256..511): 512 tokens per weight tile
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          tc_mma_f16(tmem_base + (uint32_t)UNH, adesc + (uint64_t)(k * 2), bdesc1 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(&empty[s]);                          // frees the A stage when these MMAs have read it
+        tc_commit(&empty_b[sb]);                       // and the B stage
+        if (kb == num_kb - 1) tc_commit(accum_full);   // accumulators complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
+    static_assert(kStages == 4, "the dequant loop is unrolled over the 4 ring stages");
+    const int td = threadIdx.x - 64;
+    const int pr = td / TPR, c = td % TPR;
+    const bool row_ok = (prow0 + pr) < a.step;
+    const uint8_t* wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
+    // per-slab meta rows and shared-memory offsets are loop invariant
+    constexpr int GPQ = 256 / GS;  // quantisation groups per 4 k-blocks (4 or 2): one vector load per slab and array
+    const T* sptr[F];
+    const T* zptr[F];
+    uint32_t soff[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+      sptr[f] = reinterpret_cast<const T*>(a.scale) + mrow;
+      zptr[f] = reinterpret_cast<const T*>(a.zero) + mrow;
+      const int row = f * PR + pr;
+      // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
+      if constexpr (BPT >= 8) soff[f] = (uint32_t)(row * 128) | ((uint32_t)(row & 7) << 16);  // chunk applied below
+      else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
+
+    // Packed bytes and scale/zero for the NEXT four k-blocks sit in registers while the current four are expanded: their
+    // HBM/L2 latency stays off the critical path of the 64-k stages.
+    uint32_t wbuf[4][BPT / 4];
+    Vec<T, GPQ> sv[F], zv[F];
+    auto load_w = [&](const uint8_t* p, uint32_t (&w)[BPT / 4]) {
+      if constexpr (BPT == 32) { const uint4 v0 = ldg_stream_v4(p), v1 = ldg_stream_v4(p + 16); w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; }
+      else if constexpr (BPT == 16) { const uint4 v = ldg_stream_v4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      else if constexpr (BPT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+      else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    auto load_quad = [&]() {  // the four k-blocks starting at wptr, and their groups
+#pragma unroll
+      for (int d = 0; d < 4; ++d) load_w(wptr + d * kBlockK, wbuf[d]);
+#pragma unroll
+      for (int f = 0; f < F; ++f) { sv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(sptr[f]); zv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(zptr[f]); }
+    };
+    load_quad();
+    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router)
+    for (int q = 0; q < num_quads; ++q) {
+      uint32_t wq[4][BPT / 4];
+      typename P2::T2 s2[4][F], z2[4][F];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+#pragma unroll
+        for (int i = 0; i < BPT / 4; ++i) wq[d][i] = wbuf[d][i];
+#pragma unroll
+        for (int f = 0; f < F; ++f) { s2[d][f] = P2::bcast(sv[f].v[(d * kBlockK) / GS]); z2[d][f] = P2::bcast(zv[f].v[(d * kBlockK) / GS]); }
+      }
+      if (q + 1 < num_quads) {
+        wptr += 4 * kBlockK;
+#pragma unroll
+        for (int f = 0; f < F; ++f) { sptr[f] += GPQ; zptr[f] += GPQ; }
+        load_quad();
+      }
+      const uint32_t parity = (uint32_t)(q & 1) ^ 1u;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {  // stage index == d because the ring has exactly four stages
+        mbar_wait(&empty[d], parity);
+        const uint32_t stage = sA_u32 + d * S::A_STAGE;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int sh = 8 - NBITS * (f + 1);
+          uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
+#pragma unroll
+          for (int i = 0; i < BPT / 4; ++i) {
+            const uint32_t t = (wq[d][i] >> sh) & (MASK * 0x01010101u);
+            P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
+          }
+          if constexpr (BPT >= 8) {
+            const uint32_t rowbase = stage + (soff[f] & 0xFFFFu), rx = soff[f] >> 16;
+#pragma unroll
+            for (int ch = 0; ch < BPT / 8; ++ch) {
+              const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+            }
+          } else {  // BPT == 4: half a chunk
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+          }
+        }
+        fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[d]);  // one arrival per warp: every lane has fenced its stores before the syncwarp
+      }
+    }
+
+    // ================= epilogue: TMEM -> registers -> y =================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 2) >> 2;             // two warps share a quarter: split the token columns
+    const int t = quarter * 32 + lane;            // tile row = weight row inside the tile
+    const int tf = t / PR, tp = t % PR;
+    const bool n_ok = (prow0 + tp) < a.step;
+    const int n = tf * a.step + prow0 + tp;
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const bool has_bias = bias != nullptr;
+    T bn = cvt_out<T>(0.0f);
+    if (has_bias && n_ok) bn = bias[n];
+#pragma unroll 1
+    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + col + j;
+        if (n_ok && m < a.M) {
+          T o = cvt_out<T>(__uint_as_float(v[j]));
+          if (has_bias) o = __hadd(o, bn);  // out += bias: second rounding, as in the reference
+          y[(long long)m * a.N + n] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<UN>(tmem_base);
+  }
+}
+
+// =====================================================================================================================
 // Variant "ld" (HQQ_B200_GEMM_VARIANT=ld, experimental -- written after round 1's GPU budget was spent, not yet run):
 // ncu on the kernel above shows the dequant warps, not the tensor pipe, on the critical path (tensor pipe 61 % active), and
 // a third of their stall samples sit on `fence.proxy.async` and on the first use of the register-prefetched bytes: the
@@ -643,6 +865,50 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// HQQ_B200_GEMM_VARIANT: "ld" = loader-warp kernel (linear_gemm_ld_kernel), "un512" = two accumulators per weight tile
+// (linear_gemm_un512_kernel, M > 256 only); both experimental
+static int gemm_variant() {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("HQQ_B200_GEMM_VARIANT");
+    variant = (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : 0;
+  }
+  return variant;
+}
+
+static int encode_xmap(CUtensorMap* xmap, const void* x, const Args& a, CUtensorMapDataType dt, size_t esize, int box_tokens) {
+  EncodeTiledFn enc = get_encode();
+  HQQ_REQUIRE(enc != nullptr, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+  const cuuint64_t strides[1] = {(cuuint64_t)a.K * esize};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_tokens};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(xmap, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HQQ_REQUIRE(r == CUDA_SUCCESS, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return HQQ_OK;
+}
+
+template <typename T, int NBITS, int GS>
+static int launch_un512(const void* x, const Args& a, cudaStream_t st) {
+  CUtensorMap xmap;
+  const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc = encode_xmap(&xmap, x, a, dt, sizeof(T), Smem512::UNH);
+  if (rc) return rc;
+  constexpr int PR = kTileRows / (8 / NBITS);
+  const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, Smem512::UN));
+  auto k = linear_gemm_un512_kernel<T, NBITS, GS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem512::BYTES);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem512::BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  k<<<grid, kThreads, Smem512::BYTES, st>>>(xmap, a);
+  HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05-un512");
+  return HQQ_OK;
+}
+
 template <typename T, int NBITS, int GS, int UN>
 static int launch(const void* x, const Args& a, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
@@ -658,8 +924,7 @@ static int launch(const void* x, const Args& a, cudaStream_t st) {
   HQQ_REQUIRE(r == CUDA_SUCCESS, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
   constexpr int PR = kTileRows / (8 / NBITS);
   const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, UN));
-  static int variant = -1;  // HQQ_B200_GEMM_VARIANT=ld: loader-warp kernel (experimental, see linear_gemm_ld_kernel)
-  if (variant < 0) { const char* e = getenv("HQQ_B200_GEMM_VARIANT"); variant = (e && !strcmp(e, "ld")) ? 1 : 0; }
+  const int variant = gemm_variant();
   if (variant == 1) {
     auto kl = linear_gemm_ld_kernel<T, NBITS, GS, UN>;
     using SL = SmemLd<UN, NBITS>;
@@ -689,6 +954,7 @@ template <typename T, int NBITS, int GS>
 static int by_un(const void* x, const Args& a, cudaStream_t st) {
   static int un_cap = -1;  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
   if (un_cap < 0) { const char* e = getenv("HQQ_B200_GEMM_UN"); un_cap = e ? atoi(e) : 256; }
+  if (a.M > 256 && gemm_variant() == 2) return launch_un512<T, NBITS, GS>(x, a, st);
   if (a.M <= 64 || un_cap <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
   if (a.M <= 128 || un_cap <= 128) return launch<T, NBITS, GS, 128>(x, a, st);
   return launch<T, NBITS, GS, 256>(x, a, st);

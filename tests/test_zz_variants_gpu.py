@@ -75,7 +75,7 @@ for dt in (torch.float16, torch.bfloat16):
         if nbits == 8 and dt == torch.bfloat16:
             continue
         for gs in (64, 128):
-            for N, K, M in ((512, 512, 64), (1000, 1024, 200), (256, 2048, 600)):
+            for N, K, M in ((512, 512, 64), (1000, 1024, 200), (256, 2048, 600), (384, 512, 1024), (520, 768, 513), (128, 256, 257)):
                 torch.manual_seed(nbits * 1000 + N + K + M + gs)
                 lin = HQQLinear.from_weights((torch.randn(N, K, device=dev) * 0.05).to(dt), (torch.randn(N, device=dev) * 0.1).to(dt),
                                              BaseQuantizeConfig(nbits=nbits, group_size=gs, axis=1), compute_dtype=dt, device=dev)
@@ -97,9 +97,14 @@ def run_gemm(variant, path):
     return torch.load(path, weights_only=True)
 
 
-def test_loader_warp_gemm_is_bit_identical(tmp_path):
-    ref = run_gemm(None, str(tmp_path / "default.pt"))
-    got = run_gemm("ld", str(tmp_path / "ld.pt"))
+@pytest.mark.parametrize("variant", ["ld", "un512"])
+def test_gemm_variants_are_bit_identical(tmp_path, variant):
+    """ld: loader warp + cp.async rings; un512: two accumulators (512 tokens) per dequantised weight tile, taken for M > 256.
+    Both issue the same MMAs in the same k order as the default kernel, so the outputs must match bit for bit."""
+    if "gemm_ref" not in _CACHE:
+        _CACHE["gemm_ref"] = run_gemm(None, str(tmp_path / "default.pt"))
+    ref = _CACHE["gemm_ref"]
+    got = run_gemm(variant, str(tmp_path / f"{variant}.pt"))
     assert ref.keys() == got.keys()
     for k in ref:
         assert torch.equal(ref[k], got[k]), k
