@@ -605,6 +605,242 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
 }
 
 // =====================================================================================================================
+// Variant "split-K" (HQQ_B200_GEMM_SPLITK=1, experimental -- written after round 1's GPU budget was spent, not yet run):
+// for 32 < M <= ~256 the grid of linear_gemm_kernel is (N/128) x 1 tiles -- 32 CTAs for a 4096-row matrix on 148 SMs, each
+// walking all of K.  Here gridDim.z CTAs share an output tile, each accumulating a contiguous k-slice in TMEM; the slices meet
+// as fp32 partials in a caller-provided workspace and the last CTA to arrive sums them in slice order (deterministic) and
+// applies bias/rounding.  Same tiles, descriptors and dequant as the kernel above.
+struct ArgsSK : Args {
+  float* ws;           // [gridDim.z][M][N] fp32 partials
+  unsigned* counters;  // [tiles_m][tiles_n], zero on entry, zero again on exit
+};
+
+template <typename T, int NBITS, int GS, int UN>
+__global__ void __launch_bounds__(kThreads, 1) linear_gemm_splitk_kernel(const __grid_constant__ CUtensorMap xmap, const ArgsSK a) {
+  constexpr int F = 8 / NBITS;             // slabs per byte
+  constexpr int PR = kTileRows / F;        // packed rows per tile
+  constexpr int BPT = 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
+  constexpr int TPR = 64 / BPT;            // dequant threads per packed row
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = Smem<UN>;
+  using P2 = Pair<T>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * S::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (S::A_STAGE + S::B_STAGE));
+  uint64_t* full_a = bars;                 // [kStages] dequant warps -> MMA (one arrival per warp)
+  uint64_t* full_b = bars + kStages;       // [kStages] TMA -> MMA (1 arrival + tx bytes)
+  uint64_t* empty = bars + 2 * kStages;    // [kStages] MMA (tcgen05.commit) -> producers
+  uint64_t* accum_full = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  volatile uint32_t* last_flag = tmem_slot + 1;  // 1 when this CTA is the last of its output tile to finish its k-slice
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int prow0 = tile_n * PR;           // first packed row of the tile
+  const int m0 = tile_m * UN;
+  // k-slice of this CTA, in quads of four 64-k blocks (the dequant loop's granularity): balanced to within one quad
+  const int nq_total = a.K / (4 * kBlockK), KS = (int)gridDim.z, z = (int)blockIdx.z;
+  const int q_first = (int)((long long)nq_total * z / KS), q_last = (int)((long long)nq_total * (z + 1) / KS);
+  const int kb0 = 4 * q_first;
+  const int num_kb = 4 * (q_last - q_first);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    __syncwarp();
+    tmem_alloc<UN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: activation tiles =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], S::B_STAGE);
+        tma_load_2d(sB + s * S::B_STAGE, &xmap, &full_b[s], (kb0 + kb) * kBlockK, m0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    const uint32_t idesc = make_idesc<T>(UN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full_a[s], ph);
+      mbar_wait(&full_b[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_desc_sw128(smem_u32(sA + s * S::A_STAGE));
+        const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * S::B_STAGE));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(&empty[s]);                          // frees the stage when these MMAs have read it
+        if (kb == num_kb - 1) tc_commit(accum_full);   // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
+    static_assert(kStages == 4, "the dequant loop is unrolled over the 4 ring stages");
+    const int td = threadIdx.x - 64;
+    const int pr = td / TPR, c = td % TPR;
+    const bool row_ok = (prow0 + pr) < a.step;
+    const uint8_t* wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + (long long)kb0 * kBlockK + c * BPT;
+    // per-slab meta rows and shared-memory offsets are loop invariant
+    constexpr int GPQ = 256 / GS;  // quantisation groups per 4 k-blocks (4 or 2): one vector load per slab and array
+    const T* sptr[F];
+    const T* zptr[F];
+    uint32_t soff[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+      sptr[f] = reinterpret_cast<const T*>(a.scale) + mrow + q_first * GPQ;
+      zptr[f] = reinterpret_cast<const T*>(a.zero) + mrow + q_first * GPQ;
+      const int row = f * PR + pr;
+      // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 8-row x 128-byte atom
+      if constexpr (BPT >= 8) soff[f] = (uint32_t)(row * 128) | ((uint32_t)(row & 7) << 16);  // chunk applied below
+      else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
+
+    // Packed bytes and scale/zero for the NEXT four k-blocks sit in registers while the current four are expanded: their
+    // HBM/L2 latency stays off the critical path of the 64-k stages.
+    uint32_t wbuf[4][BPT / 4];
+    Vec<T, GPQ> sv[F], zv[F];
+    auto load_w = [&](const uint8_t* p, uint32_t (&w)[BPT / 4]) {
+      if constexpr (BPT == 32) { const uint4 v0 = ldg_stream_v4(p), v1 = ldg_stream_v4(p + 16); w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; }
+      else if constexpr (BPT == 16) { const uint4 v = ldg_stream_v4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      else if constexpr (BPT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+      else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    auto load_quad = [&]() {  // the four k-blocks starting at wptr, and their groups
+#pragma unroll
+      for (int d = 0; d < 4; ++d) load_w(wptr + d * kBlockK, wbuf[d]);
+#pragma unroll
+      for (int f = 0; f < F; ++f) { sv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(sptr[f]); zv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(zptr[f]); }
+    };
+    load_quad();
+    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router)
+    for (int q = 0; q < num_quads; ++q) {
+      uint32_t wq[4][BPT / 4];
+      typename P2::T2 s2[4][F], z2[4][F];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+#pragma unroll
+        for (int i = 0; i < BPT / 4; ++i) wq[d][i] = wbuf[d][i];
+#pragma unroll
+        for (int f = 0; f < F; ++f) { s2[d][f] = P2::bcast(sv[f].v[(d * kBlockK) / GS]); z2[d][f] = P2::bcast(zv[f].v[(d * kBlockK) / GS]); }
+      }
+      if (q + 1 < num_quads) {
+        wptr += 4 * kBlockK;
+#pragma unroll
+        for (int f = 0; f < F; ++f) { sptr[f] += GPQ; zptr[f] += GPQ; }
+        load_quad();
+      }
+      const uint32_t parity = (uint32_t)(q & 1) ^ 1u;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {  // stage index == d because the ring has exactly four stages
+        mbar_wait(&empty[d], parity);
+        const uint32_t stage = sA_u32 + d * S::A_STAGE;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int sh = 8 - NBITS * (f + 1);
+          uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
+#pragma unroll
+          for (int i = 0; i < BPT / 4; ++i) {
+            const uint32_t t = (wq[d][i] >> sh) & (MASK * 0x01010101u);
+            P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
+          }
+          if constexpr (BPT >= 8) {
+            const uint32_t rowbase = stage + (soff[f] & 0xFFFFu), rx = soff[f] >> 16;
+#pragma unroll
+            for (int ch = 0; ch < BPT / 8; ++ch) {
+              const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+            }
+          } else {  // BPT == 4: half a chunk
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+          }
+        }
+        fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[d]);  // one arrival per warp: every lane has fenced its stores before the syncwarp
+      }
+    }
+
+    // ================= epilogue: TMEM -> registers -> y =================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 2) >> 2;             // two warps share a quarter: split the token columns
+    const int t = quarter * 32 + lane;            // tile row = weight row inside the tile
+    const int tf = t / PR, tp = t % PR;
+    const bool n_ok = (prow0 + tp) < a.step;
+    const int n = tf * a.step + prow0 + tp;
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const bool has_bias = bias != nullptr;
+    T bn = cvt_out<T>(0.0f);
+    if (has_bias && n_ok) bn = bias[n];
+    float* wsz = a.ws + (size_t)z * (size_t)a.M * (size_t)a.N;  // this k-slice's fp32 partial of y
+#pragma unroll 1
+    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + col + j;
+        if (n_ok && m < a.M) __stcg(&wsz[(size_t)m * a.N + n], __uint_as_float(v[j]));
+      }
+    }
+    // last-arriver reduction (the threadFenceReduction pattern): every slice publishes its partial, bumps the tile's counter, and
+    // the CTA that observes KS-1 sums the KS partials in slice order -- a fixed order, so the result does not depend on timing
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(kDequantThreads) : "memory");
+    unsigned* ctr = a.counters + ((size_t)tile_m * gridDim.x + tile_n);
+    if (td == 0) *last_flag = (atomicAdd(ctr, 1u) == (unsigned)(KS - 1)) ? 1u : 0u;
+    asm volatile("bar.sync 1, %0;" ::"n"(kDequantThreads) : "memory");
+    if (*last_flag) {
+      __threadfence();
+#pragma unroll 1
+      for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const int m = m0 + col + j;
+          if (n_ok && m < a.M) {
+            float acc = 0.0f;
+            for (int zz = 0; zz < KS; ++zz) acc += __ldcg(&a.ws[((size_t)zz * a.M + m) * (size_t)a.N + n]);
+            T o = cvt_out<T>(acc);
+            if (has_bias) o = __hadd(o, bn);  // out += bias: second rounding, as in the reference
+            y[(long long)m * a.N + n] = o;
+          }
+        }
+      }
+      if (td == 0) *ctr = 0u;  // leave the counter clean for a replay of the same launch (CUDA graphs)
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<UN>(tmem_base);
+  }
+}
+
+// =====================================================================================================================
 // Variant "ld" (HQQ_B200_GEMM_VARIANT=ld, experimental -- written after round 1's GPU budget was spent, not yet run):
 // ncu on the kernel above shows the dequant warps, not the tensor pipe, on the critical path (tensor pipe 61 % active), and
 // a third of their stall samples sit on `fence.proxy.async` and on the first use of the register-prefetched bytes: the
@@ -909,6 +1145,55 @@ static int launch_un512(const void* x, const Args& a, cudaStream_t st) {
   return HQQ_OK;
 }
 
+// ---- split-K selection (opt-in) ---------------------------------------------------------------------------------------
+static bool splitk_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HQQ_B200_GEMM_SPLITK"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+static int un_for(int64_t M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
+// k-slices per output tile: fill the 148 SMs when the tile grid alone cannot (at most 8 slices, at least one 256-k quad each)
+static int splitk_factor(int64_t M, int64_t N, int64_t K, int nbits) {
+  if (!splitk_enabled() || M > 1024) return 1;
+  const int64_t tiles = cdiv(N, kTileRows) * cdiv(M, un_for(M));  // N % F == 0, so cdiv(step, PR) == cdiv(N, 128)
+  (void)nbits;
+  if (tiles * 2 > kNumSMs) return 1;
+  int64_t S = kNumSMs / tiles;
+  if (S > 8) S = 8;
+  if (S > K / 256) S = K / 256;
+  return S < 1 ? 1 : (int)S;
+}
+static size_t splitk_counter_bytes(int64_t M, int64_t N) { return (size_t)((cdiv(N, kTileRows) * cdiv(M, 64) * 4 + 255) & ~(int64_t)255); }
+
+template <typename T, int NBITS, int GS, int UN>
+static int launch_splitk(const void* x, const Args& a0, int S, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t cbytes = splitk_counter_bytes(a0.M, a0.N), need = cbytes + (size_t)S * a0.M * a0.N * sizeof(float);
+  HQQ_REQUIRE(ws != nullptr && ws_bytes >= need && aligned(ws, 256), HQQ_E_WORKSPACE,
+              "hqq_b200_linear_fwd: split-K needs a 256-byte aligned workspace of %zu bytes (got %zu)", need, ws_bytes);
+  CUtensorMap xmap;
+  const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc = encode_xmap(&xmap, x, a0, dt, sizeof(T), UN);
+  if (rc) return rc;
+  ArgsSK a;
+  static_cast<Args&>(a) = a0;
+  a.counters = reinterpret_cast<unsigned*>(ws);
+  a.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + cbytes);
+  cudaError_t e = cudaMemsetAsync(a.counters, 0, cbytes, st);  // the workspace is the caller's scratch: never assume it is clean
+  HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: counter memset failed: %s", cudaGetErrorString(e));
+  constexpr int PR = kTileRows / (8 / NBITS);
+  const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, UN), (unsigned)S);
+  auto k = linear_gemm_splitk_kernel<T, NBITS, GS, UN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<UN>::BYTES);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem<UN>::BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  k<<<grid, kThreads, Smem<UN>::BYTES, st>>>(xmap, a);
+  HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05-splitk");
+  return HQQ_OK;
+}
+
 template <typename T, int NBITS, int GS, int UN>
 static int launch(const void* x, const Args& a, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
@@ -951,7 +1236,13 @@ static int launch(const void* x, const Args& a, cudaStream_t st) {
 }
 
 template <typename T, int NBITS, int GS>
-static int by_un(const void* x, const Args& a, cudaStream_t st) {
+static int by_un(const void* x, const Args& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int S = splitk_factor(a.M, a.N, a.K, NBITS);
+  if (S > 1) {
+    if (a.M <= 64) return launch_splitk<T, NBITS, GS, 64>(x, a, S, ws, ws_bytes, st);
+    if (a.M <= 128) return launch_splitk<T, NBITS, GS, 128>(x, a, S, ws, ws_bytes, st);
+    return launch_splitk<T, NBITS, GS, 256>(x, a, S, ws, ws_bytes, st);
+  }
   static int un_cap = -1;  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
   if (un_cap < 0) { const char* e = getenv("HQQ_B200_GEMM_UN"); un_cap = e ? atoi(e) : 256; }
   if (a.M > 256 && gemm_variant() == 2) return launch_un512<T, NBITS, GS>(x, a, st);
@@ -961,18 +1252,18 @@ static int by_un(const void* x, const Args& a, cudaStream_t st) {
 }
 
 template <typename T, int NBITS>
-static int by_gs(const void* x, const Args& a, int gs, cudaStream_t st) {
-  if (gs == 64) return by_un<T, NBITS, 64>(x, a, st);
-  return by_un<T, NBITS, 128>(x, a, st);
+static int by_gs(const void* x, const Args& a, int gs, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (gs == 64) return by_un<T, NBITS, 64>(x, a, ws, ws_bytes, st);
+  return by_un<T, NBITS, 128>(x, a, ws, ws_bytes, st);
 }
 
 template <typename T>
-static int by_bits(const void* x, const Args& a, int gs, int nbits, cudaStream_t st) {
+static int by_bits(const void* x, const Args& a, int gs, int nbits, void* ws, size_t ws_bytes, cudaStream_t st) {
   switch (nbits) {
-    case 8: return by_gs<T, 8>(x, a, gs, st);
-    case 4: return by_gs<T, 4>(x, a, gs, st);
-    case 2: return by_gs<T, 2>(x, a, gs, st);
-    case 1: return by_gs<T, 1>(x, a, gs, st);
+    case 8: return by_gs<T, 8>(x, a, gs, ws, ws_bytes, st);
+    case 4: return by_gs<T, 4>(x, a, gs, ws, ws_bytes, st);
+    case 2: return by_gs<T, 2>(x, a, gs, ws, ws_bytes, st);
+    case 1: return by_gs<T, 1>(x, a, gs, ws, ws_bytes, st);
   }
   return HQQ_E_UNSUPPORTED;
 }
@@ -990,18 +1281,21 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
   return true;
 }
 
-size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int, int nbits, int) {
+  const int S = gemm::splitk_factor(M, N, K, nbits);
+  return S > 1 ? gemm::splitk_counter_bytes(M, N) + (size_t)S * M * N * sizeof(float) : 0;
+}
 
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M, int64_t N,
-                int64_t K, int gs, int nbits, int dtype, void*, size_t, cudaStream_t st) {
+                int64_t K, int gs, int nbits, int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   HQQ_REQUIRE(aligned(x, 16) && aligned(Wq, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x and W_q must be 16-byte aligned");
   gemm::Args a;
   a.Wq = (const uint8_t*)Wq; a.scale = scale; a.zero = zero; a.bias = bias; a.y = y;
   a.M = (int)M; a.N = (int)N; a.K = (int)K;
   a.step = (int)(N / (8 / nbits));
   a.Gk = (int)(K / gs);
-  if (dtype == HQQ_F16) return gemm::by_bits<__half>(x, a, gs, nbits, st);
-  return gemm::by_bits<__nv_bfloat16>(x, a, gs, nbits, st);
+  if (dtype == HQQ_F16) return gemm::by_bits<__half>(x, a, gs, nbits, ws, ws_bytes, st);
+  return gemm::by_bits<__nv_bfloat16>(x, a, gs, nbits, ws, ws_bytes, st);
 }
 
 }  // namespace hqq

@@ -137,3 +137,24 @@ def test_fast_solver_variant_is_bit_identical(src):
                 a = a.view(torch.int32) if a.dtype == torch.float32 else a
                 b = b.view(torch.int32) if b.dtype == torch.float32 else b
                 assert torch.equal(a, b), (what, nbits, gs, N, K, std, lp)
+
+
+def test_splitk_gemm_matches_default(tmp_path):
+    """HQQ_B200_GEMM_SPLITK=1: k-slices of one output tile meet as fp32 partials and are summed in slice order by the last CTA.
+    Same products, different fp32 summation order than one accumulator walking all of K: equal to rounding, and deterministic."""
+    if "gemm_ref" not in _CACHE:
+        _CACHE["gemm_ref"] = run_gemm(None, str(tmp_path / "default.pt"))
+    ref = _CACHE["gemm_ref"]
+    env = dict(os.environ)
+    env.pop("HQQ_B200_GEMM_VARIANT", None)
+    env["HQQ_B200_GEMM_SPLITK"] = "1"
+    outs = []
+    for i in range(2):
+        path = str(tmp_path / f"splitk{i}.pt")
+        subprocess.run([sys.executable, "-c", GEMM_SCRIPT % {"root": ROOT}, path], check=True, env=env, timeout=240)
+        outs.append(torch.load(path, weights_only=True))
+    assert ref.keys() == outs[0].keys()
+    for k in ref:
+        a, b = ref[k].float(), outs[0][k].float()
+        assert (a - b).norm() <= 1e-3 * a.norm(), k
+        assert torch.equal(outs[0][k], outs[1][k]), k  # run-to-run bit-identical
