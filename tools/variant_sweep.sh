@@ -1,13 +1,27 @@
-# Round-2 first call: decode step time under each experimental M = 1 kernel variant (same box, same process layout), then the
-# GEMM variants.  Usage: gpurun --timeout 900 -- 'bash tools/variant_sweep.sh'
+# Round-2 first call: validate every experimental variant (bit-identity tests), then time each against the default on the same
+# box.  Usage: gpurun --timeout 1500 -- 'bash tools/variant_sweep.sh'
+mkdir -p gpurun_out
 export HQQ_B200_RUN_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_zz_variants_gpu.py -m gpu -q 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_zz_variants_gpu.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/variants_tests.log
+unset HQQ_B200_RUN_EXPERIMENTAL
+{
+echo "== decode step under each M = 1 kernel variant"
 for v in 0 1042 2042 3042 4042 7042 1033 7033; do
-  HQQ_B200_D1_VARIANT=$v timeout 120 python tools/step_time.py 2>&1 | tail -1
+  echo -n "D1_VARIANT=$v: "; HQQ_B200_D1_VARIANT=$v timeout 120 python tools/step_time.py 2>&1 | tail -1
 done
+echo "== quantizer: default vs fast solver (HQQ_B200_SOLVER_VARIANT=1), Llama-3-8B and 70B layer shapes"
+timeout 200 python tools/prof_quantize.py 8b 4
+HQQ_B200_SOLVER_VARIANT=1 timeout 200 python tools/prof_quantize.py 8b 4,2
+HQQ_B200_SOLVER_VARIANT=1 timeout 200 python tools/prof_quantize.py 70b 4
+echo "== GEMM M=4096: default / ld / un512 / UN caps"
 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
+HQQ_B200_GEMM_VARIANT=un512 timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
+echo "== GEMM mid M: default vs split-K"
+timeout 200 python tools/prof_gemm.py 64,128,256,512 4 2>&1 | grep fused
+HQQ_B200_GEMM_SPLITK=1 timeout 200 python tools/prof_gemm.py 64,128,256,512 4 2>&1 | grep fused
+} 2>&1 | tee gpurun_out/variant_sweep.log
 # BASELINE configs[2]: the per-linear sweep (M x nbits x 3 shapes), kept under profiles/ afterwards
 timeout 900 python tools/prof_gemm.py 1,16,32,128,1024,4096 8,4,3,2,1 > gpurun_out/gemm_sweep.log 2>&1; grep -c fused gpurun_out/gemm_sweep.log
