@@ -208,6 +208,40 @@ def kernel_roofline(model, torch, peaks, reps=4):
             "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: profiles/r1_decode1_traffic.json (ncu dram bytes)"}
 
 
+def quantizer_roofline(torch, peaks, dev, reps=3):
+    """North-star path (a): Quantizer.quantize (min/max init + proximal solver + round + pack) of ONE Llama-3-8B block's seven
+    matrices (218 M weights, fp16 source, 4-bit gs=64 axis=1, 20 iterations max), timed with CUDA events on the launching stream.
+    Algorithmic bytes: N*K*(2 + 0.5) + 2*(N*K/64)*4 per matrix.  Reported next to the decode roofline; the solver is
+    instruction-bound by construction, so the HBM fraction is a ceiling statement, not a tuning target."""
+    from hqq_b200 import ops
+    shapes = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    Ws = [(torch.randn(n, k, device=dev, generator=g, dtype=torch.float32) * 0.02).half() for n, k in shapes]
+    stream = torch.cuda.current_stream(dev)
+
+    def run():
+        for W in Ws:
+            ops.quantize(W, 4, 64, 1, True, True)
+
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    weights = sum(n * k for n, k in shapes)
+    nbytes = sum(n * k * 2.5 + 2 * (n * k // 64) * 4 for n, k in shapes)
+    achieved = nbytes / ms / 1e6
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "ms_per_block": ms, "gweights_per_s": weights / ms / 1e6, "algorithmic_bytes_per_block": nbytes,
+            "solver_variant": os.environ.get("HQQ_B200_SOLVER_VARIANT", "0"),
+            "workload": "one Llama-3-8B block (7 matrices, 218 M weights) fp16 -> 4-bit gs=64 axis=1, solver + pack, 3 launches per matrix"}
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -305,6 +339,13 @@ def run_gpu(args, rank, world, local_rank):
             line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
         if roof is not None:
             line["roofline"] = roof
+        if world == 1 and not big:
+            try:  # extra object, never allowed to cost the bench line
+                del model
+                torch.cuda.empty_cache()
+                line["quantizer"] = quantizer_roofline(torch, peaks, dev)
+            except Exception as e:  # noqa: BLE001
+                line["quantizer"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline and not big:
             v, info = cpu_reference_tokens_per_s(budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
