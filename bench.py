@@ -262,8 +262,12 @@ def run_gpu(args, rank, world, local_rank):
     n_layers = args.layers or shape.n_layers
     if args.cache_len <= 0:  # every timed loop starts at position 0 and must not wrap inside the cache
         args.cache_len = min(8192, max(256, args.steps + max(args.warmup, 3) + 8))
+    B = max(1, args.batch)
+    if B > 1:  # BASELINE configs[4] bs = 32 leg: not the default line
+        metric += f"_bs{B}"
+        workload = workload.replace("bs=1", f"bs={B}")
     model = harness.DecodeModel(shape, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=args.cache_len, tp=world,
-                                rank=rank, process_group=pg, n_layers=n_layers)
+                                rank=rank, process_group=pg, n_layers=n_layers, batch=B)
     lib.hqq_b200_launch_count_reset()
     model.capture(warmup=3)
     # launches of OUR kernels in one step = those issued while capturing one step (3 warm-up steps + 1 captured)
@@ -293,8 +297,8 @@ def run_gpu(args, rank, world, local_rank):
     dev_ms = e0.elapsed_time(e1)
 
     # ---- end-to-end loop through the public API with host buffers ------------------------------
-    h_in = torch.ones(1, dtype=torch.long).pin_memory()
-    h_out = torch.zeros(1, dtype=torch.long).pin_memory()
+    h_in = torch.ones(B, dtype=torch.long).pin_memory()
+    h_out = torch.zeros(B, dtype=torch.long).pin_memory()
     model.pos.zero_()
     for _ in range(3):
         model.tok.copy_(h_in, non_blocking=True); model.graph.replay(); h_out.copy_(model.next_tok, non_blocking=True); torch.cuda.synchronize(dev)
@@ -306,7 +310,7 @@ def run_gpu(args, rank, world, local_rank):
         model.graph.replay()
         h_out.copy_(model.next_tok, non_blocking=True)    # D2H: the produced token
         stream.synchronize()
-        h_in[0] = h_out[0]                                # host-side feedback, as a generation loop would
+        h_in.copy_(h_out)                                 # host-side feedback, as a generation loop would
     t1.record(stream)
     barrier()
     e2e_ms = t0.elapsed_time(t1)
@@ -318,11 +322,11 @@ def run_gpu(args, rank, world, local_rank):
         dev_ms, e2e_ms = t.tolist()
 
     peaks = load_peaks()
-    roof = kernel_roofline(model, torch, peaks) if (rank == 0 and world == 1) else None
+    roof = kernel_roofline(model, torch, peaks) if (rank == 0 and world == 1 and B == 1) else None
     if rank == 0:
         scale_layers = shape.n_layers / n_layers
-        value = args.steps / (dev_ms / 1e3)
-        e2e = args.steps / (e2e_ms / 1e3)
+        value = args.steps * B / (dev_ms / 1e3)
+        e2e = args.steps * B / (e2e_ms / 1e3)
         bytes_tok = model.bytes_per_token() * world  # whole-job bytes (each rank streams 1/world of the blocks + full lm_head)
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
@@ -330,23 +334,23 @@ def run_gpu(args, rank, world, local_rank):
                 "config": {"workload": workload,
                            "path": f"fused sm_100a kernels, kv cache {args.cache_len}, CUDA graph; {model.bytes_per_token() / 1e9:.2f} GB streamed per step "
                                    ">> 126 MB L2 (inputs larger than L2, no flush needed)",
-                           "parallelism": f"tp{world}", "layers": n_layers},
+                           "parallelism": f"tp{world}", "layers": n_layers, "global_batch": B},
                 "clocks": clocks,
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B},
                 "gpu_launches": launches_per_step * args.steps,
                 "step_hbm_GBps": bytes_tok / world / (dev_ms / args.steps) / 1e6}
         if scale_layers != 1.0:
             line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
         if roof is not None:
             line["roofline"] = roof
-        if world == 1 and not big:
+        if world == 1 and not big and B == 1:
             try:  # extra object, never allowed to cost the bench line
                 del model
                 torch.cuda.empty_cache()
                 line["quantizer"] = quantizer_roofline(torch, peaks, dev)
             except Exception as e:  # noqa: BLE001
                 line["quantizer"] = {"error": repr(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and not big:
+        if world == 1 and not args.no_cpu_baseline and not big and B == 1:
             v, info = cpu_reference_tokens_per_s(budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
         print(json.dumps(line), flush=True)
@@ -368,6 +372,8 @@ def main():
     ap.add_argument("--cache-len", type=int, default=0, help="KV-cache length; 0 = large enough that the timed loops never wrap (>= 256)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1, help="sequences decoded in lock-step (BASELINE configs[4]: 32); > 1 uses the fused small-M "
+                    "kernel between framework glue ops and NCCL all-reduce")
     ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] at bs=1 (use with --gpus 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -1,21 +1,7 @@
 // hqq_b200_linear_fwd / hqq_b200_linear_fwd_multi: routing between the fused forward kernels.
-#include "common.cuh"
+#include "linear_internal.cuh"
 
 namespace hqq {
-struct TpExchange {
-  int tp, rank;
-  void* const* peer_data;
-  const void* red_data;
-  void* const* y_tagged;
-  const void* x_tagged;
-  const void* x2_tagged;
-  const int* step_ctr;
-  int x_index, x_per_step, skip_wait;
-  const void* l2_hint[2];
-  const int64_t* l2_hint_rows;
-  int l2_hint_chunks, l2_hint_row_bytes;
-  int64_t l2_hint_chunk_stride;
-};
 bool small_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t small_workspace_bytes(int64_t M);
 int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,

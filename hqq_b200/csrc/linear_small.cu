@@ -23,24 +23,10 @@
 #include <string.h>
 #include <type_traits>
 
-#include "common.cuh"
+#include "linear_internal.cuh"
 
 namespace hqq {
 
-struct TpExchange {  // host-side view of the optional tagged-word exchange (see SKArgs)
-  int tp, rank;
-  void* const* peer_data;
-  const void* red_data;
-  void* const* y_tagged;
-  const void* x_tagged;
-  const void* x2_tagged;
-  const int* step_ctr;
-  int x_index, x_per_step, skip_wait;
-  const void* l2_hint[2];
-  const int64_t* l2_hint_rows;
-  int l2_hint_chunks, l2_hint_row_bytes;
-  int64_t l2_hint_chunk_stride;
-};
 
 constexpr int kMaxProb = 4;   // weight matrices sharing one activation in a single launch (q/k/v, gate/up)
 

@@ -59,8 +59,16 @@ def shard_dims(shape: LlamaShape, tp: int):
 class DecodeModel:
     def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
                  device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
-                 n_layers: int | None = None, fused=5, tp_mode: str | None = None):
+                 n_layers: int | None = None, fused=5, tp_mode: str | None = None, batch: int = 1):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
+        # batch > 1 (BASELINE configs[4], bs = 32): `batch` sequences decode in lock-step at the same position; the linears then
+        # run the fused small-M kernel (M = batch <= 32) between framework glue ops -- the one-token glue kernels and the fused
+        # NVLink exchange are M = 1 only, so tensor-parallel partials are summed by NCCL
+        self.batch = int(batch)
+        if self.batch < 1:
+            raise ValueError("batch must be >= 1")
+        if self.batch > 1:
+            fused = False
         self.fused = fused
         import os
         self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")  # "p2p": tagged-word chaining / fused exchange; "nccl": plain
@@ -96,8 +104,8 @@ class DecodeModel:
             blk["norm1"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)
             blk["norm2"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)
             hkv = shape.n_kv_heads // tp
-            blk["k_cache"] = torch.zeros(1, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
-            blk["v_cache"] = torch.zeros(1, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
+            blk["k_cache"] = torch.zeros(self.batch, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
+            blk["v_cache"] = torch.zeros(self.batch, hkv, cache_len, shape.head_dim, device=self.device, dtype=dtype)
             self.blocks.append(blk)
         hd = shape.head_dim
         inv = 1.0 / (shape.rope_theta ** (torch.arange(0, hd, 2, device=self.device, dtype=torch.float32) / hd))
@@ -107,9 +115,9 @@ class DecodeModel:
         self.sin = torch.cat([fr.sin(), fr.sin()], dim=-1).to(dtype)
         self.arange = torch.arange(cache_len, device=self.device)
         # static I/O for graph capture
-        self.tok = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.tok = torch.zeros(self.batch, dtype=torch.long, device=self.device)
         self.pos = torch.zeros(1, dtype=torch.long, device=self.device)
-        self.next_tok = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.next_tok = torch.zeros(self.batch, dtype=torch.long, device=self.device)
         self.graph = None
 
     # bytes one decode step must read from HBM: packed weights + meta + fp16 lm_head row-major
@@ -130,23 +138,24 @@ class DecodeModel:
         return x * cos + torch.cat((-x2, x1), dim=-1) * sin
 
     def step(self):
-        """One token: reads self.tok / self.pos, writes self.next_tok and advances self.pos (all on device)."""
+        """One token per sequence: reads self.tok [batch] / self.pos, writes self.next_tok and advances self.pos (all on device)."""
         s = self.shape
+        B = self.batch
         hd, hq, hkv = s.head_dim, s.n_heads // self.tp, s.n_kv_heads // self.tp
-        h = self.embed.index_select(0, self.tok)  # [1, hidden]
+        h = self.embed.index_select(0, self.tok)  # [B, hidden]
         cos = self.cos.index_select(0, self.pos).view(1, 1, hd)
         sin = self.sin.index_select(0, self.pos).view(1, 1, hd)
         mask = (self.arange <= self.pos).view(1, 1, 1, self.cache_len)
         for blk in self.blocks:
             x = F.rms_norm(h, (s.hidden,), blk["norm1"], s.rms_eps)
             q, k, v = self._multi(x, (blk["q"], blk["k"], blk["v"]))  # one launch: the three matrices share x
-            q, k, v = q.view(1, hq, hd), k.view(1, hkv, hd), v.view(1, hkv, hd)
+            q, k, v = q.view(B, hq, hd), k.view(B, hkv, hd), v.view(B, hkv, hd)
             q = self._rope(q, cos, sin)
             k = self._rope(k, cos, sin)
-            blk["k_cache"].index_copy_(2, self.pos, k.view(1, hkv, 1, hd))
-            blk["v_cache"].index_copy_(2, self.pos, v.view(1, hkv, 1, hd))
-            a = F.scaled_dot_product_attention(q.view(1, hq, 1, hd), blk["k_cache"], blk["v_cache"], attn_mask=mask, enable_gqa=True)
-            o = blk["o"](a.reshape(1, hq * hd))
+            blk["k_cache"].index_copy_(2, self.pos, k.view(B, hkv, 1, hd))
+            blk["v_cache"].index_copy_(2, self.pos, v.view(B, hkv, 1, hd))
+            a = F.scaled_dot_product_attention(q.view(B, hq, 1, hd), blk["k_cache"], blk["v_cache"], attn_mask=mask, enable_gqa=True)
+            o = blk["o"](a.reshape(B, hq * hd))
             if self.tp > 1:
                 torch.distributed.all_reduce(o, group=self.pg)
             h = h + o

@@ -82,3 +82,39 @@ def test_layer_sharding_plan_is_complete_balanced_and_deterministic():
         loads = [sum(sizes[i] for i in p) for p in plan]
         assert max(loads) - min(loads) <= max(sizes)
     assert harness.assign_layers([5, 1, 1], 2) == [[0], [1, 2]]
+
+
+def test_batched_decode_step_equals_independent_sequences(monkeypatch):
+    """BASELINE configs[4] bs = 32 leg: DecodeModel(batch=B).step() decodes B sequences in lock-step.  Host glue only (KV cache
+    per sequence, RoPE at the shared position, GQA attention, per-sequence argmax), checked on CPU with dense stand-ins for the
+    HQQLinear layers: every sequence must produce the tokens it produces alone."""
+    class Dense:
+        def __init__(self, W):
+            self.W = W
+
+        def __call__(self, x):
+            return x @ self.W.t()
+
+    monkeypatch.setattr(harness.HQQLinear, "from_weights", staticmethod(lambda W, bias, cfg, compute_dtype=None, device=None: Dense(W)))
+    monkeypatch.setattr(harness.ops, "linear_fwd_multi", lambda x, layers, outs=None: None)
+    shape = harness.LlamaShape(hidden=64, inter=128, n_layers=2, n_heads=4, n_kv_heads=2, vocab=97)
+    toks = [5, 9, 11]
+
+    def run(batch, first):
+        m = harness.DecodeModel(shape, dtype=torch.float64, device="cpu", cache_len=16, fused=False, seed=1, batch=batch)
+        assert m.fused is False and m.blocks[0]["k_cache"].shape[0] == batch
+        m.tok.copy_(torch.tensor(first))
+        out = []
+        for _ in range(5):
+            m.step()
+            out.append(m.next_tok.clone())
+            m.tok.copy_(m.next_tok)
+        return torch.stack(out, 1)  # [batch, steps]
+
+    together = run(3, toks)
+    for i, t in enumerate(toks):
+        alone = run(1, [t])
+        assert torch.equal(together[i], alone[0]), (i, together[i], alone[0])
+    assert len({tuple(r.tolist()) for r in together}) > 1  # the sequences really differ
+    with pytest.raises(ValueError):
+        harness.DecodeModel(shape, dtype=torch.float64, device="cpu", cache_len=16, fused=False, batch=0)
