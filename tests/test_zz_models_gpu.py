@@ -55,3 +55,31 @@ def test_quantize_model_matches_the_reference_checkpoint(tmp_path):
     again = AutoHQQHFModel.from_quantized(out, compute_dtype=torch.float32, device=dev, cache_dir=None)
     with torch.no_grad():
         assert torch.equal(again(ids).logits.float(), la)
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; not yet seen on a GPU")
+def test_batched_decode_matches_single_sequences():
+    """DecodeModel(batch=3): the fused small-M kernel (M = 3) between framework glue ops, captured in a CUDA graph; every sequence
+    decodes the tokens it decodes alone (batch = 1, same unfused path).  Near-ties may flip late tokens: the first ones must agree."""
+    from hqq_b200 import harness
+    dev = torch.device("cuda", 0)
+    shape = harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)
+    first = [5, 9, 11]
+
+    def run(batch, toks):
+        m = harness.DecodeModel(shape, dtype=torch.float16, device=dev, cache_len=32, fused=False, seed=3, batch=batch)
+        m.capture()
+        m.tok.copy_(torch.tensor(toks, device=dev)); m.pos.zero_()
+        for blk in m.blocks:
+            blk["k_cache"].zero_(); blk["v_cache"].zero_()
+        out = []
+        for _ in range(8):
+            m.decode()
+            out.append(m.next_tok.clone())
+        return torch.stack(out, 1).cpu()
+
+    together = run(3, first)
+    for i, t in enumerate(first):
+        alone = run(1, [t])[0]
+        assert torch.equal(together[i][:3], alone[:3]), (i, together[i], alone)
+        assert int((together[i] == alone).sum()) >= 6, (i, together[i], alone)
