@@ -13,6 +13,10 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int gs, int nbits, int dtype);
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int gs, int nbits, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+bool fused3_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
+size_t fused3_workspace_bytes(int64_t N);
+int linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N, int64_t K,
+                  int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace hqq
 
 using namespace hqq;
@@ -20,12 +24,14 @@ using namespace hqq;
 extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {
   if (small_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 1;
   if (gemm_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 2;
+  if (fused3_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 3;  // opt-in (HQQ_B200_FUSED_3BIT=1), one token, 3-bit
   return 0;
 }
 
 extern "C" size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int dtype) {
   if (small_route_ok(M, N, K, group_size, nbits, 1, dtype)) return small_workspace_bytes(M);
   if (gemm_route_ok(M, N, K, group_size, nbits, 1, dtype)) return gemm_workspace_bytes(M, N, K, group_size, nbits, dtype);
+  if (fused3_route_ok(M, N, K, group_size, nbits, 1, dtype)) return fused3_workspace_bytes(N);
   return 0;
 }
 
@@ -47,6 +53,7 @@ extern "C" int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* s
   const int route = hqq_b200_linear_fwd_route(M, N, K, group_size, nbits, axis, dtype);
   if (route == 1) return linear_small_multi(x, 1, &W_q, &scale, &zero, &bias, &y, &N, M, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
   if (route == 2) return linear_gemm(x, W_q, scale, zero, bias, y, M, N, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
+  if (route == 3) return linear_fused3(x, W_q, scale, zero, bias, y, N, K, dtype, workspace, workspace_bytes, st);
   set_error("hqq_b200_linear_fwd: no fused kernel for M=%lld N=%lld K=%lld gs=%d nbits=%d axis=%d dtype=%d", (long long)M, (long long)N,
             (long long)K, group_size, nbits, axis, dtype);
   return HQQ_E_UNSUPPORTED;

@@ -158,3 +158,34 @@ def test_splitk_gemm_matches_default(tmp_path):
         a, b = ref[k].float(), outs[0][k].float()
         assert (a - b).norm() <= 1e-3 * a.norm(), k
         assert torch.equal(outs[0][k], outs[1][k]), k  # run-to-run bit-identical
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_fused_3bit_one_token_kernel(dt):
+    """HQQ_B200_FUSED_3BIT=1: 3-bit layers at M = 1 take csrc/linear3.cu (route 3) instead of dequantize + GEMM.  Checked against the
+    default path on the same quantised layer (tolerance of the other fused kernels) and for run-to-run bit-identity (no atomics)."""
+    from hqq_b200 import ops
+    from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
+    dev = torch.device("cuda", 0)
+    tol = 2e-3 if dt == torch.float16 else 1e-2
+    for N, K, with_bias in ((16, 64, False), (10, 128, True), (33, 256, False), (7, 640, True), (1000, 1024, False), (4096, 4096, True),
+                            (11008, 4096, False), (4096, 11008, False), (4096, 14336, True), (3, 64, False), (1, 128, False)):
+        torch.manual_seed(N + K)
+        bias = (torch.randn(N, device=dev) * 0.1).to(dt) if with_bias else None
+        lin = HQQLinear.from_weights((torch.randn(N, K, device=dev) * 0.05).to(dt), bias, BaseQuantizeConfig(nbits=3, group_size=64, axis=1),
+                                     compute_dtype=dt, device=dev)
+        x = torch.randn(1, K, device=dev).to(dt)
+        assert ops.linear_route(1, N, K, 64, 3, 1, dt) == 0
+        with torch.no_grad():
+            ref = lin(x).float()
+        os.environ["HQQ_B200_FUSED_3BIT"] = "1"
+        try:
+            assert ops.linear_route(1, N, K, 64, 3, 1, dt) == 3
+            with torch.no_grad():
+                a = lin(x).clone()
+                b = lin(x).clone()
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("HQQ_B200_FUSED_3BIT", None)
+        assert torch.equal(a, b), (N, K)
+        assert (a.float() - ref).norm() <= tol * ref.norm(), (N, K, float((a.float() - ref).norm() / ref.norm()))

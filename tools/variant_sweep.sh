@@ -19,6 +19,9 @@ HQQ_B200_GEMM_VARIANT=un512 timeout 200 python tools/prof_gemm.py 1024,4096,8192
 HQQ_B200_GEMM_VARIANT=ld timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
+echo "== 3-bit, one token: dequantise + GEMM (default) vs fused (HQQ_B200_FUSED_3BIT=1)"
+timeout 200 python tools/prof_gemm.py 1 3 2>&1 | grep fused
+HQQ_B200_FUSED_3BIT=1 timeout 200 python tools/prof_gemm.py 1 3 2>&1 | grep fused
 echo "== GEMM mid M: default vs split-K"
 timeout 200 python tools/prof_gemm.py 64,128,256,512 4 2>&1 | grep fused
 HQQ_B200_GEMM_SPLITK=1 timeout 200 python tools/prof_gemm.py 64,128,256,512 4 2>&1 | grep fused
