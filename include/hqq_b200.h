@@ -118,8 +118,10 @@ int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int64_t K,
  *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
  *   axis must be 1.  Returns HQQ_E_UNSUPPORTED for configurations the fused kernels do
  *   not cover (the Python layer then runs hqq_b200_dequantize + a library GEMM).
- *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes (currently 0 for every route: split-K partials meet in
- *   shared memory; the parameter is kept so the ABI does not change when a kernel needs scratch).              */
+ *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, 256-byte aligned scratch owned by the caller.  0 for every
+ *   default route (split-K partials of the small-M kernel meet in shared memory); non-zero only for the opt-in
+ *   kernels that need global scratch (HQQ_B200_GEMM_SPLITK=1: fp32 k-slice partials + tile counters;
+ *   HQQ_B200_FUSED_3BIT=1: three fp32 slots per output row).  Contents on entry are irrelevant.                    */
 size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size,
                                            int nbits, int dtype);
 int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero,
@@ -138,7 +140,8 @@ int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, 
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Which fused kernel hqq_b200_linear_fwd would use: 0 none (unsupported), 1 small-M
- * mma.sync weight-streaming kernel, 2 tcgen05/TMA GEMM.                                 */
+ * mma.sync weight-streaming kernel, 2 tcgen05/TMA GEMM, 3 the 3-bit one-token kernel
+ * (only with HQQ_B200_FUSED_3BIT=1; 3-bit is route 0 otherwise).                         */
 int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits,
                               int axis, int dtype);
 
