@@ -242,6 +242,78 @@ def quantizer_roofline(torch, peaks, dev, reps=3):
             "workload": "one Llama-3-8B block (7 matrices, 218 M weights) fp16 -> 4-bit gs=64 axis=1, solver + pack, 3 launches per matrix"}
 
 
+def _finite(o):
+    """json.dumps would print NaN / Infinity, which is not JSON: map non-finite floats to None."""
+    if isinstance(o, float):
+        return o if o == o and abs(o) != float("inf") else None
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    return o
+
+
+def run_probes(budget_s=150.0, timeout_s=50.0):
+    """First GPU execution of the kernels written after round 1's GPU budget was spent: each knob runs
+    tools/variant_probe.py in its OWN process under a timeout -- a crash or a hang there cannot reach this process -- on a fixed
+    seeded workload, and is compared with the default kernels (sha256 of the outputs, relative error where the summation order
+    differs by design).  Reported under "experimental"; nothing here touches the timed regions or the default kernels."""
+    import tempfile
+    import torch
+    probe = os.path.join(ROOT, "tools", "variant_probe.py")
+    tmp = tempfile.mkdtemp(prefix="hqq_probe_")
+    t_start = time.perf_counter()
+    base_env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
+
+    def run(what, knob=None, both=None, save=None):
+        if time.perf_counter() - t_start > budget_s:
+            return {"skipped": "probe time budget spent"}
+        env = dict(base_env)
+        if knob:
+            env[knob[0]] = knob[1]
+        cmd = [sys.executable, probe, what]
+        if both:
+            cmd += ["--both", both]
+        if save:
+            cmd += ["--save", save]
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            return {"error": f"timeout after {timeout_s:.0f} s"}
+        for ln in r.stdout.splitlines():
+            if ln.startswith("PROBE "):
+                return json.loads(ln[6:])
+        return {"error": (r.stderr or r.stdout)[-300:].replace("\n", " | ")}
+
+    def against_default(what, knobs):
+        ref_path = os.path.join(tmp, what + "_default.pt")
+        ref = run(what, save=ref_path)
+        out = {"default": ref}
+        for key, val in knobs:
+            path = os.path.join(tmp, f"{what}_{key}_{val}.pt")
+            got = run(what, knob=(key, val), save=path)
+            if "digest" in ref and "digest" in got:
+                got["bit_identical"] = got["digest"] == ref["digest"]
+                got["speedup"] = ref["us"] / got["us"]
+                if not got["bit_identical"]:
+                    try:
+                        a, b = torch.load(ref_path, weights_only=True), torch.load(path, weights_only=True)
+                        got["rel_err"] = max(float((x.double() - y.double()).norm() / x.double().norm().clamp_min(1e-30)) if x.shape == y.shape
+                                             else float("inf") for x, y in zip(a, b))
+                    except Exception as e:  # noqa: BLE001
+                        got["rel_err"] = repr(e)[:100]
+            out[f"{key}={val}"] = got
+        return out
+
+    res = {"solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
+           "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
+           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
+           "gemm_mid": against_default("gemm_mid", [("HQQ_B200_GEMM_SPLITK", "1")]),
+           "decode_8_blocks": against_default("decode", [("HQQ_B200_D1_VARIANT", "7042"), ("HQQ_B200_D1_VARIANT", "1042")])}
+    res["seconds"] = round(time.perf_counter() - t_start, 1)
+    return res
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -350,10 +422,15 @@ def run_gpu(args, rank, world, local_rank):
                 line["quantizer"] = quantizer_roofline(torch, peaks, dev)
             except Exception as e:  # noqa: BLE001
                 line["quantizer"] = {"error": repr(e)[:200]}
+        if world == 1 and not big and B == 1 and not args.no_probes:
+            try:
+                line["experimental"] = run_probes()
+            except Exception as e:  # noqa: BLE001
+                line["experimental"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline and not big and B == 1:
             v, info = cpu_reference_tokens_per_s(budget_s=15.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_finite(line)), flush=True)
     if world > 1:
         # Tear down without touching NCCL again: destroying a process group while captured graphs still hold its kernels
         # can hang.  Everything is measured and printed; leave through the fast exit on every rank.
@@ -372,6 +449,7 @@ def main():
     ap.add_argument("--cache-len", type=int, default=0, help="KV-cache length; 0 = large enough that the timed loops never wrap (>= 256)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probes", action="store_true", help="skip the experimental-kernel probes (sub-processes, N=1 only)")
     ap.add_argument("--batch", type=int, default=1, help="sequences decoded in lock-step (BASELINE configs[4]: 32); > 1 uses the fused small-M "
                     "kernel between framework glue ops and NCCL all-reduce")
     ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] at bs=1 (use with --gpus 8)")
