@@ -1,0 +1,137 @@
+// TEST INFRASTRUCTURE ONLY -- a stand-in for <cuda_runtime.h> that lets the *simple* kernels of hqq_b200/csrc (no tcgen05, TMA,
+// cp.async, mma.sync or inline PTX on their path) be compiled by g++ and EXECUTED ON THE CPU by a cooperative-fiber emulator:
+// every CUDA thread of a block is a ucontext fiber, warp collectives (__shfl_xor_sync, __any_sync, __all_sync, __syncwarp) and
+// __syncthreads are rendezvous points between fibers.  It exists so that kernels written without access to a GPU can be executed
+// and compared with the oracle before their first GPU run (tests/test_emu_cpu.py).  Nothing in the hqq_b200 package includes,
+// links or loads this; the product path has no CPU arithmetic.
+#pragma once
+#define __shared__ static
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#include "vector_types.h"  // real CUDA header: float4, uint2, dim3, ... and crt/host_defines.h (empty __device__/__global__ for g++)
+
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+// ---- runtime API surface: the REAL declarations (types, enums, C prototypes); the handful of functions the host side of the
+// .cu files calls are DEFINED by emu_runtime.cpp (memcpy/memset/no-ops), nothing links libcudart
+#include <cuda_runtime_api.h>
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
+
+// ---- the emulator ------------------------------------------------------------------------------------------------------------
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+
+namespace emu {
+
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  uint3 tid;
+};
+struct Barrier { int count = 0; unsigned gen = 0; };
+
+extern ucontext_t g_sched;
+extern Fiber* g_cur;
+extern std::vector<Fiber>* g_fibers;
+extern Barrier g_warp_bar[64], g_block_bar;
+extern unsigned long long g_slot[64][32];
+extern int g_block_threads;
+extern char* dyn_smem;
+extern std::function<void()> g_body;
+extern long long g_progress;
+
+inline int linear_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
+inline void yield() { Fiber* f = g_cur; swapcontext(&f->ctx, &g_sched); }
+inline void arrive(Barrier& b, int need) {
+  const unsigned gen = b.gen;
+  ++g_progress;
+  if (++b.count == need) { b.count = 0; ++b.gen; }
+  else while (b.gen == gen) yield();
+}
+inline int warp_lanes(int warp) { const int left = g_block_threads - 32 * warp; return left < 32 ? left : 32; }
+inline void warp_barrier() { const int w = linear_tid() >> 5; arrive(g_warp_bar[w], warp_lanes(w)); }
+
+template <typename T> inline T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  const int t = linear_tid(), w = t >> 5, l = t & 31;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  g_slot[w][l] = bits;
+  warp_barrier();
+  const unsigned long long got = g_slot[w][src_lane & 31];
+  warp_barrier();
+  T r;
+  memcpy(&r, &got, sizeof(T));
+  return r;
+}
+inline int vote(bool p, bool all) {
+  const int t = linear_tid(), w = t >> 5, l = t & 31, n = warp_lanes(w);
+  g_slot[w][l] = p ? 1ull : 0ull;
+  warp_barrier();
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) cnt += (int)g_slot[w][i];
+  warp_barrier();
+  return all ? (cnt == n) : (cnt > 0);
+}
+
+void run_block(std::function<void()> body, dim3 block);
+
+template <typename K, typename... A>
+void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
+  gridDim = grid; blockDim = block;
+  std::vector<char> dyn(smem + 64);
+  dyn_smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 63) & ~(uintptr_t)63);
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        blockIdx = uint3{bx, by, bz};
+        run_block([&]() { kernel(args...); }, block);
+      }
+}
+template <typename K>
+struct Bound {
+  K k; dim3 grid, block; size_t smem;
+  template <typename... A> void operator()(A... a) { launch(k, grid, block, smem, a...); }
+};
+template <typename K> inline Bound<K> bind(K k, dim3 g, dim3 b, size_t s = 0, cudaStream_t = nullptr) { return Bound<K>{k, g, b, s}; }
+
+}  // namespace emu
+
+// generated sources replace  kernel<<<g, b, s, st>>>(args)  by  EMU_LAUNCH((kernel), g, b, s, st)(args)
+#define EMU_LAUNCH(k, ...) ::emu::bind(k, __VA_ARGS__)
+
+// ---- device intrinsics ---------------------------------------------------------------------------------------------------------
+inline void __syncthreads() { emu::arrive(emu::g_block_bar, emu::g_block_threads); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) { return emu::shfl(v, (emu::linear_tid() & 31) ^ o); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
+inline int __any_sync(unsigned, int p) { return emu::vote(p != 0, false); }
+inline int __all_sync(unsigned, int p) { return emu::vote(p != 0, true); }
+
+template <typename T> inline T __ldg(const T* p) { return *p; }
+// one IEEE operation each: build with -ffp-contract=off so that nothing is fused
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __frcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+inline float __log2f(float a) { return log2f(a); }
+inline float __expf(float a) { return expf(a); }
+inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
