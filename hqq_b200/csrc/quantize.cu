@@ -328,6 +328,75 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis0_kernel(SolverArgs
   block_flush_errors(err_w, a.iters, a.partial);
 }
 
+// ---- K1, axis = 0, fast variant (HQQ_B200_SOLVER_VARIANT=1): the two exact shortcuts of solver_axis1_fast_kernel with one
+// thread per group (32 groups per warp: the warp leaves once all 32 zero-points repeat) ---------------------------------------
+template <typename TIn, int GS>
+__global__ void __launch_bounds__(kSolverThreads) solver_axis0_fast_kernel(SolverArgs a) {
+  __shared__ double err_w[kSolverThreads / 32][kMaxIters];
+  for (int i = threadIdx.x; i < (kSolverThreads / 32) * kMaxIters; i += blockDim.x) (&err_w[0][0])[i] = 0.0;
+  __syncthreads();
+  double* row = err_w[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const long long C = a.G;
+  const float fmaxv = (float)a.maxv;
+  const float thr = a.thr;
+  const TIn* W = reinterpret_cast<const TIn*>(a.W);
+  const long long stride = (long long)gridDim.x * kSolverThreads;
+  const long long first = (long long)blockIdx.x * kSolverThreads + (threadIdx.x & ~31);
+  for (long long gb = first; gb < C; gb += stride) {  // warp-uniform trip count
+    const long long g = gb + lane;
+    const bool valid = g < C;
+    float w[GS];
+#pragma unroll
+    for (int j = 0; j < GS; ++j) w[j] = valid ? to_f32<TIn>(W[(long long)j * C + g]) : 0.0f;
+    float mn = w[0], mx = w[0];
+#pragma unroll
+    for (int j = 1; j < GS; ++j) { mn = fminf(mn, w[j]); mx = fmaxf(mx, w[j]); }
+    GroupState st;
+    if (a.s_init) init_group_ext(a, g, valid, st);
+    else init_group(mn, mx, a.maxv, a.round_zero, st);
+    if (valid) { a.s_inv[g] = st.s; a.hist[g] = st.z; }
+    float ew = 0.0f;
+    int it = 0;
+    while (it < a.iters) {
+      float errsum = 0.0f, zs = 0.0f, amax = 0.0f;
+#pragma unroll
+      for (int j = 0; j < GS; ++j) {
+        const float ws = __fmul_rn(w[j], st.s);
+        float q = rint_magic(__fadd_rn(ws, st.z));
+        q = fminf(fmaxf(q, 0.0f), fmaxv);
+        const float wr = __fmul_rn(__fsub_rn(q, st.z), st.rs);
+        const float ad = fabsf(__fsub_rn(w[j], wr));
+        errsum += ad;
+        amax = fmaxf(amax, ad);
+        zs += __fsub_rn(q, ws);
+      }
+      if (__any_sync(0xffffffffu, !(amax < thr))) {
+        zs = 0.0f;
+        float unused = 0.0f;
+#pragma unroll
+        for (int j = 0; j < GS; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
+      }
+      const float znew = __fmul_rn(zs, 1.0f / (float)GS);  // GS is a power of two: identical to the division
+      if (valid) a.hist[(long long)(it + 1) * a.G + g] = znew;
+      ew = valid ? errsum : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ew += __shfl_xor_sync(0xffffffffu, ew, o);
+      if (lane == 0) row[it] += (double)ew;
+      const bool fixed = !valid || __float_as_uint(znew) == __float_as_uint(st.z);
+      st.z = znew;
+      ++it;
+      if (__all_sync(0xffffffffu, fixed)) break;
+    }
+    __syncwarp();
+    if (valid)
+      for (int t = it; t < a.iters; ++t) a.hist[(long long)(t + 1) * a.G + g] = st.z;
+    for (int t = it + lane; t < a.iters; t += 32) row[t] += (double)ew;
+    __syncwarp();
+  }
+  block_flush_errors(err_w, a.iters, a.partial);
+}
+
 // ---- K1, generic path: one warp per group, any gs / axis; elements are re-read (L1/L2) every iteration --
 template <typename TIn>
 __global__ void __launch_bounds__(kSolverThreads) solver_generic_kernel(SolverArgs a, int axis) {
@@ -517,6 +586,13 @@ static int launch_solver(const SolverArgs& a, int axis, int nblocks, cudaStream_
       case 8: solver_axis1_fast_kernel<TIn, 8><<<nblocks, kSolverThreads, 0, st>>>(a); break;
       case 16: solver_axis1_fast_kernel<TIn, 16><<<nblocks, kSolverThreads, 0, st>>>(a); break;
       case 32: solver_axis1_fast_kernel<TIn, 32><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+    }
+  } else if (axis == 0 && fast_axis0(a.gs) && solver_variant() == 1) {
+    switch (a.gs) {
+      case 8: solver_axis0_fast_kernel<TIn, 8><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 16: solver_axis0_fast_kernel<TIn, 16><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 32: solver_axis0_fast_kernel<TIn, 32><<<nblocks, kSolverThreads, 0, st>>>(a); break;
+      case 64: solver_axis0_fast_kernel<TIn, 64><<<nblocks, kSolverThreads, 0, st>>>(a); break;
     }
   } else if (axis == 1 && fast_axis1(a.gs)) {
     switch (a.gs / 8) {

@@ -49,7 +49,7 @@ def to_bf16_bits(x):
     return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
 
 
-def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20):
+def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20, axis=1):
     N, K = W.shape
     if src == F16:
         Wd = aligned(W.shape, np.float16); Wd[...] = W.astype(np.float16)
@@ -59,16 +59,17 @@ def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20):
         Wd = aligned(W.shape, np.float32); Wd[...] = W
     G = N * K // gs
     fields = 10 if nbits == 3 else 8 // nbits
-    prow = -(-G // 10) if nbits == 3 else G // fields
-    Wq = aligned((prow, gs), np.int32 if nbits == 3 else np.uint8)
+    R, C = (G, gs) if axis == 1 else (gs, G)  # the grouped view [R, C]; packing runs along R
+    prow = -(-R // 10) if nbits == 3 else R // fields
+    Wq = aligned((prow, C), np.int32 if nbits == 3 else np.uint8)
     s, z = aligned((G,), np.float32), aligned((G,), np.float32)
     info, err = aligned((4,), np.int32), aligned((iters,), np.float32)
-    nb = lib.hqq_b200_quantize_workspace_bytes(N, K, gs, nbits, 1, iters)
+    nb = lib.hqq_b200_quantize_workspace_bytes(N, K, gs, nbits, axis, iters)
     assert nb > 0
     ws = aligned((nb,), np.uint8)
     os.environ["HQQ_B200_SOLVER_VARIANT"] = str(variant)
     try:
-        rc = lib.hqq_b200_quantize(P(Wd), src, ctypes.c_int64(N), ctypes.c_int64(K), gs, nbits, 1, int(nbits == 4), 1, ctypes.c_float(lp),
+        rc = lib.hqq_b200_quantize(P(Wd), src, ctypes.c_int64(N), ctypes.c_int64(K), gs, nbits, axis, int(nbits == 4), 1, ctypes.c_float(lp),
                                    ctypes.c_float(10.0), iters, P(Wq), P(s), P(z), P(info), P(err), P(ws), ctypes.c_size_t(nb), None)
     finally:
         os.environ.pop("HQQ_B200_SOLVER_VARIANT", None)
@@ -122,6 +123,18 @@ def test_emulated_fast_solver_is_bit_identical_to_the_default(emu, nbits, gs, sh
     for x, y, what in zip(a[:5], b[:5], ("W_q", "scale", "zero", "info", "errors")):
         assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
     assert 1 <= a[3][0] <= 20
+
+
+@pytest.mark.parametrize("nbits,gs,shape,std,src", [(4, 64, (64, 48), 0.02, F16), (4, 64, (64, 33), 1.0, F32), (2, 32, (32, 100), 0.02, BF16),
+                                                    (8, 16, (16, 70), 0.05, F16), (3, 8, (8, 90), 0.5, F32), (1, 64, (128, 40), 0.02, F16)])
+@pytest.mark.parametrize("lp", [0.7, 1.0])
+def test_emulated_fast_solver_axis0_is_bit_identical_to_the_default(emu, nbits, gs, shape, std, src, lp):
+    rng = np.random.default_rng(nbits * 10 + gs)
+    W = (rng.standard_normal(shape) * std).astype(np.float32)
+    a = quantize(emu, W, src, nbits, gs, 0, lp, axis=0)
+    b = quantize(emu, W, src, nbits, gs, 1, lp, axis=0)
+    for x, y, what in zip(a[:5], b[:5], ("W_q", "scale", "zero", "info", "errors")):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
 
 
 @pytest.mark.parametrize("N,K", [(16, 64), (10, 128), (33, 256), (7, 640), (50, 1024), (3, 64), (1, 128)])

@@ -120,7 +120,9 @@ def test_fast_solver_variant_is_bit_identical(src):
     cases = [(4, 64, 1024, 1024, 0.02), (4, 64, 1000, 512, 1.0),    # std 1.0: errors above the threshold -> the fallback runs
              (2, 64, 512, 2048, 0.02), (2, 32, 256, 512, 2.0), (8, 128, 512, 1024, 0.05), (1, 16, 128, 512, 0.02),
              (3, 64, 330, 640, 0.02), (4, 8, 96, 256, 0.5), (4, 256, 64, 1024, 0.02), (4, 64, 38, 64, 0.02)]
-    for nbits, gs, N, K, std in cases:
+    cases = [c + (1,) for c in cases] + [(4, 64, 1024, 512, 0.02, 0), (4, 64, 64, 33, 1.0, 0), (2, 32, 256, 100, 0.02, 0), (8, 16, 128, 70, 0.05, 0),
+                                        (3, 8, 64, 90, 0.5, 0), (1, 64, 128, 40, 0.02, 0)]
+    for nbits, gs, N, K, std, axis in cases:
         for lp in (0.7, 1.0):
             torch.manual_seed(nbits * 100 + gs + N)
             W = (torch.randn(N, K, device=dev) * std).to(src)
@@ -128,7 +130,7 @@ def test_fast_solver_variant_is_bit_identical(src):
             for variant in ("0", "1"):
                 os.environ["HQQ_B200_SOLVER_VARIANT"] = variant
                 try:
-                    Wq, s, z, tr = ops.quantize(W, nbits, gs, 1, nbits == 4, True, lp_norm=lp, want_trace=True)
+                    Wq, s, z, tr = ops.quantize(W, nbits, gs, axis, nbits == 4, True, lp_norm=lp, want_trace=True)
                     torch.cuda.synchronize()
                 finally:
                     os.environ.pop("HQQ_B200_SOLVER_VARIANT", None)
@@ -136,7 +138,7 @@ def test_fast_solver_variant_is_bit_identical(src):
             for a, b, what in zip(outs[0], outs[1], ("W_q", "scale", "zero", "info", "errors")):
                 a = a.view(torch.int32) if a.dtype == torch.float32 else a
                 b = b.view(torch.int32) if b.dtype == torch.float32 else b
-                assert torch.equal(a, b), (what, nbits, gs, N, K, std, lp)
+                assert torch.equal(a, b), (what, nbits, gs, N, K, std, lp, axis)
 
 
 def test_splitk_gemm_matches_default(tmp_path):
