@@ -7,3 +7,4 @@ timeout 150 $R --master-port 29521 bench.py --gpus 8 --steps 100 --warmup 5 > gp
 timeout 200 $R --master-port 29522 bench.py --gpus 8 --steps 50 --warmup 5 --model 70b > gpurun_out/bench_70b_tp8.json 2> gpurun_out/bench_70b_tp8.err; grep '"metric"' gpurun_out/bench_70b_tp8.json | head -c 400; echo
 timeout 200 $R --master-port 29524 bench.py --gpus 8 --steps 30 --warmup 5 --model 70b --batch 32 > gpurun_out/bench_70b_tp8_bs32.json 2> gpurun_out/bench_70b_tp8_bs32.err; grep '"metric"' gpurun_out/bench_70b_tp8_bs32.json | head -c 400; echo
 timeout 150 $R --master-port 29523 tools/quantize_sharded.py --model 70b --blocks 16 > gpurun_out/quant_70b_8gpu.json 2> gpurun_out/quant_70b_8gpu.err; tail -1 gpurun_out/quant_70b_8gpu.json | head -c 500; echo
+HQQ_B200_SOLVER_VARIANT=1 timeout 150 $R --master-port 29525 tools/quantize_sharded.py --model 70b --blocks 16 > gpurun_out/quant_70b_8gpu_fast.json 2> gpurun_out/quant_70b_8gpu_fast.err; tail -1 gpurun_out/quant_70b_8gpu_fast.json | head -c 500; echo
