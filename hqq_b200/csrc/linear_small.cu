@@ -89,19 +89,40 @@ struct SKArgs {
   long long hint_stride;
 };
 
+// L2 prefetch (a pure hint): nothing to do on the emulator
+#ifdef HQQ_EMU
+#define HQQ_PREFETCH_L2(p) ((void)(p))
+#else
+#define HQQ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#endif
+
+#ifdef HQQ_EMU
+#define HQQ_ST_RELAXED_SYS(p, v) (*reinterpret_cast<volatile uint32_t*>(p) = (v))
+#else
+#define HQQ_ST_RELAXED_SYS(p, v) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory")
+#endif
+
 template <typename T> struct MT16;
 template <> struct MT16<__half> {
   static constexpr uint32_t ONE2 = 0x3C003C00u;
   __device__ __forceinline__ static void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifndef HQQ_EMU
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#else
+    ::emu::mma_m16n8k16<__half>(d, a0, a1, a2, a3, b0, b1, false);
+#endif
   }
   // same with C = 0 (first MMA of a group): no accumulator clearing instructions needed
   __device__ __forceinline__ static void mma0(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifndef HQQ_EMU
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.0f));
+#else
+    ::emu::mma_m16n8k16<__half>(d, a0, a1, a2, a3, b0, b1, true);
+#endif
   }
   __device__ __forceinline__ static float ld(const void* p, long long i) { return __half2float(reinterpret_cast<const __half*>(p)[i]); }
   __device__ __forceinline__ static __half cvt(float v, const void* bias, int n) {
@@ -114,14 +135,22 @@ template <> struct MT16<__half> {
 template <> struct MT16<__nv_bfloat16> {
   static constexpr uint32_t ONE2 = 0x3F803F80u;
   __device__ __forceinline__ static void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifndef HQQ_EMU
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#else
+    ::emu::mma_m16n8k16<__nv_bfloat16>(d, a0, a1, a2, a3, b0, b1, false);
+#endif
   }
   __device__ __forceinline__ static void mma0(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifndef HQQ_EMU
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.0f));
+#else
+    ::emu::mma_m16n8k16<__nv_bfloat16>(d, a0, a1, a2, a3, b0, b1, true);
+#endif
   }
   __device__ __forceinline__ static float ld(const void* p, long long i) { return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]); }
   __device__ __forceinline__ static __nv_bfloat16 cvt(float v, const void* bias, int n) {
@@ -133,15 +162,23 @@ template <> struct MT16<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+#ifdef HQQ_EMU
+  return ::emu::prmt(a, b, s);
+#else
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
   return r;
+#endif
 }
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef HQQ_EMU
+  return ::emu::lop3(a, b, c, (uint32_t)LUT);
+#else
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
   return r;
+#endif
 }
 // (a & b) | c
 __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xEA>(a, b, c); }
@@ -241,44 +278,78 @@ struct Lanes<__half, 8, MAGIC> {
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+#ifdef HQQ_EMU
+  memcpy(smem, g, 16);  // the emulator copies at issue time; commit/wait are no-ops
+#else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+#endif
 }
 // the same copy, marked evict-first in L2: a stream that is read once should not push the step's reusable lines (KV cache,
 // activations, norm weights) out of the 126 MB L2
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
+#ifdef HQQ_EMU
+  return 0;
+#else
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
+#endif
 }
 __device__ __forceinline__ void cp_async16_hint(void* smem, const void* g, uint64_t pol) {
+#ifdef HQQ_EMU
+  (void)pol;
+  memcpy(smem, g, 16);
+#else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "l"(pol) : "memory");
+#endif
 }
 template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* smem, const void* g) {
+#ifdef HQQ_EMU
+  memcpy(smem, g, BYTES);
+#else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(g), "n"(BYTES) : "memory");
+#endif
 }
+#ifdef HQQ_EMU
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 template <typename T> __device__ __forceinline__ T from_f32_t(float v);
 template <> __device__ __forceinline__ __half from_f32_t<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
+#ifdef HQQ_EMU
+  return *reinterpret_cast<const volatile int*>(p);
+#else
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+#endif
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
+#ifdef HQQ_EMU
+  *reinterpret_cast<volatile int*>(p) = v;
+#else
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
+#ifndef HQQ_EMU
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
 struct SKCfg {
@@ -699,11 +770,11 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const T* s_m = im;
     for (int u = 0; u < kPfUnits && to_issue > 0; ++u) {
       if (c == 0) {  // one lane per packed row: the unit's 256 bytes = two 128-byte lines
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_a));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_a + 128));
+        HQQ_PREFETCH_L2(iw_a);
+        HQQ_PREFETCH_L2(iw_a + 128);
         if (F == 1) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_b));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(iw_b + 128));
+          HQQ_PREFETCH_L2(iw_b);
+          HQQ_PREFETCH_L2(iw_b + 128);
         }
       }
       --to_issue;
@@ -721,8 +792,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     const long long per_chunk = *a.hint_rows * a.hint_row_lines, total = per_chunk * a.hint_chunks;
     for (long long i = (long long)blockIdx.x * 256 + tid; i < total; i += (long long)gridDim.x * 256) {
       const long long ch = i / per_chunk, off = ch * a.hint_stride + ((i - ch * per_chunk) << 7);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.hint[0] + off));
-      if (a.hint[1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.hint[1] + off));
+      HQQ_PREFETCH_L2(a.hint[0] + off);
+      if (a.hint[1]) HQQ_PREFETCH_L2(a.hint[1] + off);
     }
   }
   if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
@@ -748,8 +819,12 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       uint4 w0, w1;
       bool ok;
       do {
+#ifdef HQQ_EMU
+        memcpy(&w0, src, 16); memcpy(&w1, src + 4, 16);
+#else
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src) : "memory");
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 4) : "memory");
+#endif
         ok = ((w0.x >> 16) == rtag) & ((w0.y >> 16) == rtag) & ((w0.z >> 16) == rtag) & ((w0.w >> 16) == rtag) &
              ((w1.x >> 16) == rtag) & ((w1.y >> 16) == rtag) & ((w1.z >> 16) == rtag) & ((w1.w >> 16) == rtag);
       } while (!ok);
@@ -968,9 +1043,9 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
             const size_t off = ((size_t)send_par * a.tp + a.rank) * t.N + n;
 #pragma unroll
             for (int dst = 0; dst < 8; ++dst)
-              if (dst < a.tp) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer_data[dst] + off), "r"(word) : "memory");
+              if (dst < a.tp) HQQ_ST_RELAXED_SYS(a.peer_data[dst] + off, word);
           }
-          if (t.ytag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(t.ytag + (size_t)send_par * t.N + n), "r"(word) : "memory");
+          if (t.ytag) HQQ_ST_RELAXED_SYS(t.ytag + (size_t)send_par * t.N + n, word);
         }
       }
     }

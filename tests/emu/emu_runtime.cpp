@@ -22,6 +22,7 @@ int g_block_threads = 0;
 char* dyn_smem = nullptr;
 std::function<void()> g_body;
 long long g_progress = 0;
+unsigned g_mma_a[64][32][4], g_mma_b[64][32][2];
 
 static void trampoline() {
   g_body();

@@ -25,7 +25,10 @@
 // ---- runtime API surface: the REAL declarations (types, enums, C prototypes); the handful of functions the host side of the
 // .cu files calls are DEFINED by emu_runtime.cpp (memcpy/memset/no-ops), nothing links libcudart
 #include <cuda_runtime_api.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F*, int, size_t) { *n = 2; return cudaSuccess; }
 
 // ---- the emulator ------------------------------------------------------------------------------------------------------------
 extern uint3 threadIdx, blockIdx;
@@ -108,8 +111,67 @@ template <typename K> inline Bound<K> bind(K k, dim3 g, dim3 b, size_t s = 0, cu
 
 }  // namespace emu
 
+namespace emu {
+// ---- warp-level tensor-core op used by the small-M forward: mma.sync.aligned.m16n8k16.row.col.f32.{f16,bf16} ----------------
+// A collective: every lane deposits its fragments, then computes its four outputs from the assembled 16x16 / 16x8 tiles
+// (PTX ISA fragment layouts; products of two 16-bit floats are exact in fp32, the k-sum runs in index order).
+extern unsigned g_mma_a[64][32][4], g_mma_b[64][32][2];
+template <typename T> float half_bits_to_float(unsigned short h);
+template <typename T>
+inline void mma_m16n8k16(float (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, bool zero_c) {
+  const int t = linear_tid(), w = t >> 5, l = t & 31, g = l >> 2, q = l & 3;
+  g_mma_a[w][l][0] = a0; g_mma_a[w][l][1] = a1; g_mma_a[w][l][2] = a2; g_mma_a[w][l][3] = a3;
+  g_mma_b[w][l][0] = b0; g_mma_b[w][l][1] = b1;
+  warp_barrier();
+  auto A = [&](int r, int k) {
+    const unsigned reg = g_mma_a[w][(r & 7) * 4 + ((k & 7) >> 1)][(r >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0)];
+    return half_bits_to_float<T>((unsigned short)((reg >> (16 * (k & 1))) & 0xFFFFu));
+  };
+  auto B = [&](int k, int n) {
+    const unsigned reg = g_mma_b[w][n * 4 + ((k & 7) >> 1)][k >= 8 ? 1 : 0];
+    return half_bits_to_float<T>((unsigned short)((reg >> (16 * (k & 1))) & 0xFFFFu));
+  };
+  float out[4];
+  for (int i = 0; i < 4; ++i) {
+    const int r = g + ((i & 2) ? 8 : 0), n = 2 * q + (i & 1);
+    float acc = zero_c ? 0.0f : d[i];
+    for (int k = 0; k < 16; ++k) { volatile float p = A(r, k) * B(k, n); volatile float s2 = acc + p; acc = s2; }
+    out[i] = acc;
+  }
+  warp_barrier();
+  for (int i = 0; i < 4; ++i) d[i] = out[i];
+}
+template <> inline float half_bits_to_float<__half>(unsigned short h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+template <> inline float half_bits_to_float<__nv_bfloat16>(unsigned short h) { unsigned u = (unsigned)h << 16; float f; memcpy(&f, &u, 4); return f; }
+inline unsigned prmt(unsigned a, unsigned b, unsigned s) {  // prmt.b32, default mode
+  const unsigned long long src = ((unsigned long long)b << 32) | a;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const unsigned sel = (s >> (4 * i)) & 0xFu;
+    unsigned byte = (unsigned)((src >> (8 * (sel & 7))) & 0xFFu);
+    if (sel & 8) byte = (byte & 0x80u) ? 0xFFu : 0x00u;
+    r |= byte << (8 * i);
+  }
+  return r;
+}
+inline unsigned lop3(unsigned a, unsigned b, unsigned c, unsigned lut) {
+  unsigned r = 0;
+  for (int m = 0; m < 8; ++m)
+    if ((lut >> m) & 1u) r |= ((m & 4) ? a : ~a) & ((m & 2) ? b : ~b) & ((m & 1) ? c : ~c);
+  return r;
+}
+
+}  // namespace emu
+
 // generated sources replace  kernel<<<g, b, s, st>>>(args)  by  EMU_LAUNCH((kernel), g, b, s, st)(args)
 #define EMU_LAUNCH(k, ...) ::emu::bind(k, __VA_ARGS__)
+
+// cudaLaunchKernelEx (programmatic dependent launch attributes are meaningless here: blocks and kernels run one after another)
+template <typename... E, typename... A>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(E...), A&&... args) {
+  ::emu::launch(kernel, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, args...);
+  return cudaSuccess;
+}
 
 // ---- device intrinsics ---------------------------------------------------------------------------------------------------------
 inline void __syncthreads() { emu::arrive(emu::g_block_bar, emu::g_block_threads); }

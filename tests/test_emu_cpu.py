@@ -166,3 +166,85 @@ def test_emulated_fused_3bit_forward_matches_the_oracle(emu, oracle, N, K, with_
     assert rc == 0, emu.hqq_b200_last_error()
     err = np.linalg.norm(y.astype(np.float64) - ref) / max(np.linalg.norm(ref), 1e-30)
     assert err <= (2e-3 if N >= 8 else 5e-3), err  # a norm over one or two fp16 values is dominated by their last bit
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The headline kernels: csrc/linear_small.cu (generic small-M kernel and the one-token kernel) on the emulator.  mma.sync,
+# prmt, lop3 and cp.async are emulated (tests/emu/include/cuda_runtime.h); the kernel source is the product's, with its inline
+# PTX switched to those stand-ins by -DHQQ_EMU (the GPU build's SASS is byte-identical with and without the #ifdefs).
+# ---------------------------------------------------------------------------------------------------------------------------
+import subprocess  # noqa: E402
+
+RUNNER = os.path.join(HERE, "emu", "run_small.py")
+_RUNS = {}
+
+
+def run_small(tmp_path_factory, variant=None):
+    key = variant or "default"
+    if key not in _RUNS:
+        out = str(tmp_path_factory.mktemp("emu_small") / f"{key}.npz")
+        env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
+        if variant:
+            env["HQQ_B200_D1_VARIANT"] = str(variant)
+        r = subprocess.run([sys.executable, RUNNER, out], env=env, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            if "emulator build unavailable" in r.stderr or "g++" in r.stderr and "not found" in r.stderr:
+                pytest.skip("emulator build unavailable")
+            raise AssertionError(r.stderr[-3000:])
+        _RUNS[key] = dict(np.load(out))
+    return _RUNS[key]
+
+
+def rel(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_emulated_small_m_and_one_token_forward_match_the_oracle(emu, tmp_path_factory):
+    d = run_small(tmp_path_factory)
+    refs = [k for k in d if k.endswith("_ref")]
+    assert len(refs) >= 20
+    for k in refs:
+        assert rel(d[k[:-4]], d[k]) <= 2e-3, k  # fp16 tolerance of tests/test_linear_gpu.py (measured there and here: ~3e-4)
+
+
+def test_emulated_one_token_prologues_and_paired_epilogue(emu, oracle, tmp_path_factory):
+    """x_op 1 (residual add + RMSNorm), x_op 2 (SiLU * mul) and the paired SiLU*mul epilogue against numpy restatements of the
+    documented roundings (include/hqq_b200.h: every intermediate is rounded to the compute dtype)."""
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import run_small as R
+    d = run_small(tmp_path_factory)
+    f16 = lambda v: np.asarray(v, dtype=np.float32).astype(np.float16)  # noqa: E731
+    silu = lambda v: f16(v.astype(np.float32) / (1.0 + np.exp(-v.astype(np.float32))))  # noqa: E731
+    for ci, (nbits, N, K) in enumerate(R.DECODE):
+        rng = np.random.default_rng(200 + ci)
+        A, B = R.make_layer(rng, N, K, nbits, 64), R.make_layer(rng, N, K, nbits, 64)
+        x = rng.standard_normal((1, K)).astype(np.float16)
+        x2 = (rng.standard_normal((1, K)) * 0.5).astype(np.float16)
+        w = rng.random(K).astype(np.float16)
+        fwd = lambda act, L: oracle.linear_forward(act.astype(np.float32), L["Wq_host"], L["meta"], None, "float16")  # noqa: E731
+        # x_op 1
+        t = f16(x.astype(np.float32) + x2.astype(np.float32))
+        inv = 1.0 / np.sqrt(np.mean(t.astype(np.float32) ** 2) + 1e-5)
+        xn = f16(f16(t.astype(np.float32) * np.float32(inv)).astype(np.float32) * w.astype(np.float32))
+        assert np.array_equal(d[f"dec{ci}_x1_h"], t)
+        assert rel(d[f"dec{ci}_x1_a"], fwd(xn, A)) <= 3e-3 and rel(d[f"dec{ci}_x1_b"], fwd(xn, B)) <= 3e-3
+        # x_op 2
+        xm = f16(silu(x).astype(np.float32) * x2.astype(np.float32))
+        assert rel(d[f"dec{ci}_x2_a"], fwd(xm, A)) <= 3e-3
+        # paired epilogue on the plain activation: silu(W0 x) * (W1 x), both products rounded first
+        g, u = d[f"dec{ci}_x0_a"], d[f"dec{ci}_x0_b"]
+        assert np.array_equal(d[f"dec{ci}_x0pair_a"], f16(silu(g).astype(np.float32) * u.astype(np.float32)))
+        g1, u1 = d[f"dec{ci}_x1_a"], d[f"dec{ci}_x1_b"]
+        assert np.array_equal(d[f"dec{ci}_x1pair_a"], f16(silu(g1).astype(np.float32) * u1.astype(np.float32)))
+        assert np.array_equal(d[f"dec{ci}_x1pair_h"], t)
+
+
+@pytest.mark.parametrize("variant", [32, 1042, 2042, 3042, 1033, 4042, 7042, 7033])
+def test_emulated_one_token_kernel_variants_are_bit_identical(emu, tmp_path_factory, variant):
+    """The experimental M = 1 kernel variants (scale/zero through the cp.async ring, evict-first hint, 3 CTAs per SM, L2 prefetch
+    under the dependency wait) executed on the emulator: every output equals the default kernel's bit for bit."""
+    ref, got = run_small(tmp_path_factory), run_small(tmp_path_factory, variant)
+    assert ref.keys() == got.keys()
+    for k in ref:
+        assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
