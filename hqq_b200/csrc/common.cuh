@@ -87,6 +87,9 @@ struct alignas(sizeof(T) * N >= 16 ? 16 : sizeof(T) * N) Vec {
 
 // streaming 16-byte global load that does not pollute L1 (weights are read exactly once)
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+#ifdef HQQ_EMU
+  return *reinterpret_cast<const uint4*>(p);
+#endif
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)

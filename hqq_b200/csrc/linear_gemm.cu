@@ -40,6 +40,30 @@ struct Args {
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
+#ifdef HQQ_EMU
+// CPU emulation (tests/emu): the same entry points, backed by a functional model of mbarrier / TMA / tcgen05 / TMEM
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return ::emu::smem_offset(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { ::emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { ::emu::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { ::emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) { ::emu::tma_load_2d(smem_dst, map, bar, c0, c1); }
+__device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void tc_fence_before() {}
+__device__ __forceinline__ void tc_fence_after() {}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) { ::emu::mbar_arrive(bar); }  // the emulated MMAs complete at issue
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  ::emu::umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) { ::emu::tmem_alloc(dst_in_smem, NCOLS); }
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t) {}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) { ::emu::tmem_ld32(taddr, v); }
+#define HQQ_STS_V4(addr, a, b, c, d) ::emu::sts(addr, a, b, c, d)
+#define HQQ_STS_V2(addr, a, b) ::emu::sts(addr, a, b)
+#define HQQ_PREFETCH_TENSORMAP(p) ((void)(p))
+#define HQQ_NAMED_BAR_SYNC(id, n) ::emu::named_barrier(id, n)
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -108,6 +132,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+#define HQQ_STS_V4(addr, a, b, c, d) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
+#define HQQ_STS_V2(addr, a, b) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory")
+#define HQQ_PREFETCH_TENSORMAP(p) asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory")
+#define HQQ_NAMED_BAR_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(n) : "memory")
+#endif  // HQQ_EMU
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
 // leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte offset = 1024 B between 8-row groups in
 // [32,46), descriptor version 1 (Blackwell) in [46,48), layout type 2 = SWIZZLE_128B in [61,64).
@@ -137,9 +167,13 @@ __device__ __forceinline__ uint32_t make_idesc(int UN) {
 // ---- level -> T with the reference's roundings -------------------------------------------------------------------
 // Two k-adjacent levels (bytes b0, b1 already masked to the field) -> T2 {fl(fl(q0 - z) * s), fl(fl(q1 - z) * s)}.
 __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef HQQ_EMU
+  return ::emu::prmt(a, b, sel);
+#else
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
+#endif
 }
 
 // Four k-adjacent levels (one per byte of `t`, already masked to the field) -> two packed T2
@@ -216,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+      HQQ_PREFETCH_TENSORMAP(&xmap);
     }
     __syncwarp();
     tmem_alloc<UN>(tmem_slot);
@@ -333,10 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 #pragma unroll
             for (int ch = 0; ch < BPT / 8; ++ch) {
               const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+              HQQ_STS_V4(addr, out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
             }
           } else {  // BPT == 4: half a chunk
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+            HQQ_STS_V2(stage + soff[f], out[0], out[1]);
           }
         }
         fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
@@ -432,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
       for (int s = 0; s < S::kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+      HQQ_PREFETCH_TENSORMAP(&xmap);
     }
     __syncwarp();
     tmem_alloc<UN>(tmem_slot);
@@ -555,10 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
 #pragma unroll
             for (int ch = 0; ch < BPT / 8; ++ch) {
               const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+              HQQ_STS_V4(addr, out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
             }
           } else {  // BPT == 4: half a chunk
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+            HQQ_STS_V2(stage + soff[f], out[0], out[1]);
           }
         }
         fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
@@ -652,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_splitk_kernel(const _
       for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+      HQQ_PREFETCH_TENSORMAP(&xmap);
     }
     __syncwarp();
     tmem_alloc<UN>(tmem_slot);
@@ -769,10 +803,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_splitk_kernel(const _
 #pragma unroll
             for (int ch = 0; ch < BPT / 8; ++ch) {
               const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+              HQQ_STS_V4(addr, out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
             }
           } else {  // BPT == 4: half a chunk
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+            HQQ_STS_V2(stage + soff[f], out[0], out[1]);
           }
         }
         fence_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
@@ -809,10 +843,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_splitk_kernel(const _
     // last-arriver reduction (the threadFenceReduction pattern): every slice publishes its partial, bumps the tile's counter, and
     // the CTA that observes KS-1 sums the KS partials in slice order -- a fixed order, so the result does not depend on timing
     __threadfence();
-    asm volatile("bar.sync 1, %0;" ::"n"(kDequantThreads) : "memory");
+    HQQ_NAMED_BAR_SYNC(1, kDequantThreads);
     unsigned* ctr = a.counters + ((size_t)tile_m * gridDim.x + tile_n);
     if (td == 0) *last_flag = (atomicAdd(ctr, 1u) == (unsigned)(KS - 1)) ? 1u : 0u;
-    asm volatile("bar.sync 1, %0;" ::"n"(kDequantThreads) : "memory");
+    HQQ_NAMED_BAR_SYNC(1, kDequantThreads);
     if (*last_flag) {
       __threadfence();
 #pragma unroll 1
@@ -867,12 +901,20 @@ struct SmemLd {
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_b(uint32_t smem_addr, const void* g) {
+#ifdef HQQ_EMU
+  memcpy(::emu::smem_ptr(smem_addr), g, BYTES);  // copies at issue time
+#else
   if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(g), "n"(BYTES) : "memory");
+#endif
 }
 // the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed (the count is part of init)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+#ifdef HQQ_EMU
+  ::emu::mbar_arrive(bar);
+#else
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+#endif
 }
 
 template <typename T, int NBITS, int GS, int UN>
@@ -916,7 +958,7 @@ __global__ void __launch_bounds__(kLdThreads, 1) linear_gemm_ld_kernel(const __g
       for (int s = 0; s < NW; ++s) { mbar_init(&full_w[s], 32); mbar_init(&empty_w[s], kDequantThreads / 32); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+      HQQ_PREFETCH_TENSORMAP(&xmap);
     }
     __syncwarp();
     tmem_alloc<UN>(tmem_slot);
@@ -1037,10 +1079,10 @@ __global__ void __launch_bounds__(kLdThreads, 1) linear_gemm_ld_kernel(const __g
 #pragma unroll
             for (int ch = 0; ch < BPT / 8; ++ch) {
               const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(out[4 * ch]), "r"(out[4 * ch + 1]), "r"(out[4 * ch + 2]), "r"(out[4 * ch + 3]) : "memory");
+              HQQ_STS_V4(addr, out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
             }
           } else {
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(stage + soff[f]), "r"(out[0]), "r"(out[1]) : "memory");
+            HQQ_STS_V2(stage + soff[f], out[0], out[1]);
           }
         }
         fence_async_smem();
@@ -1091,6 +1133,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode() {
+#ifdef HQQ_EMU
+  return &::emu::encode_tiled;
+#endif
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "hqq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libhqq_b200_emu.so")
-SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear3.cu", "linear_small.cu", "linear.cu"]
+SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear3.cu", "linear_small.cu", "linear_gemm.cu", "linear.cu"]
 CUDA_INC = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
 EXTRA = r'''
@@ -25,12 +25,6 @@ namespace hqq {
 size_t fused3_workspace_bytes(int64_t N);
 int linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N, int64_t K,
                   int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
-}
-namespace hqq {  // the tcgen05 GEMM cannot be emulated: its router entries answer "not covered"
-bool gemm_route_ok(int64_t, int64_t, int64_t, int, int, int, int) { return false; }
-size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
-int linear_gemm(const void*, const void*, const void*, const void*, const void*, void*, int64_t, int64_t, int64_t, int, int, int, void*, size_t,
-                cudaStream_t) { return HQQ_E_UNSUPPORTED; }
 }
 extern "C" size_t emu_fused3_workspace_bytes(int64_t N) { return hqq::fused3_workspace_bytes(N); }
 extern "C" int emu_linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N,

@@ -23,6 +23,8 @@ char* dyn_smem = nullptr;
 std::function<void()> g_body;
 long long g_progress = 0;
 unsigned g_mma_a[64][32][4], g_mma_b[64][32][2];
+float g_tmem[128][512];
+Barrier g_named_bar[16];
 
 static void trampoline() {
   g_body();
@@ -38,6 +40,7 @@ void run_block(std::function<void()> body, dim3 block) {
   g_body = body;
   for (auto& b : g_warp_bar) b = Barrier();
   g_block_bar = Barrier();
+  for (auto& b : g_named_bar) b = Barrier();
   std::vector<Fiber> fibers(n);
   g_fibers = &fibers;
   for (int t = 0; t < n; ++t) {
@@ -50,7 +53,7 @@ void run_block(std::function<void()> body, dim3 block) {
     f.ctx.uc_link = &g_sched;
     makecontext(&f.ctx, trampoline, 0);
   }
-  int left = n;
+  int left = n, stalled = 0;
   while (left > 0) {
     const long long before = g_progress;
     for (int t = 0; t < n; ++t) {
@@ -61,8 +64,11 @@ void run_block(std::function<void()> body, dim3 block) {
       swapcontext(&g_sched, &f.ctx);
       if (f.done) --left;
     }
-    if (left > 0 && g_progress == before) {
-      fprintf(stderr, "emu: deadlock -- %d threads of block (%u,%u,%u) wait at a barrier the others never reach\n", left, blockIdx.x, blockIdx.y, blockIdx.z);
+    // A pass without a single arrival / completion is not yet a deadlock (a thread may have moved silently from one wait to the
+    // next), but thousands in a row are: everybody spins on something nobody will ever signal.
+    stalled = (g_progress == before) ? stalled + 1 : 0;
+    if (left > 0 && stalled > 4000) {
+      fprintf(stderr, "emu: deadlock -- %d threads of block (%u,%u,%u) wait for something the others never signal\n", left, blockIdx.x, blockIdx.y, blockIdx.z);
       abort();
     }
   }

@@ -24,6 +24,7 @@
 
 // ---- runtime API surface: the REAL declarations (types, enums, C prototypes); the handful of functions the host side of the
 // .cu files calls are DEFINED by emu_runtime.cpp (memcpy/memset/no-ops), nothing links libcudart
+#include <cuda.h>  // driver TYPES only (CUtensorMap, CUresult): nothing is linked
 #include <cuda_runtime_api.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -93,8 +94,8 @@ void run_block(std::function<void()> body, dim3 block);
 template <typename K, typename... A>
 void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
   gridDim = grid; blockDim = block;
-  std::vector<char> dyn(smem + 64);
-  dyn_smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 63) & ~(uintptr_t)63);
+  std::vector<char> dyn(smem + 2048);
+  dyn_smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 1023) & ~(uintptr_t)1023);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -162,6 +163,104 @@ inline unsigned lop3(unsigned a, unsigned b, unsigned c, unsigned lut) {
 }
 
 }  // namespace emu
+
+// ---- functional model of the Blackwell tensor-core path used by csrc/linear_gemm.cu ------------------------------------------
+// mbarrier (arrival count + transaction bytes + phase), TMA 2-D tile loads with SWIZZLE_128B, UMMA descriptors (K-major,
+// SWIZZLE_128B), tcgen05.mma kind::f16 (M = 128, N from the instruction descriptor) accumulating into a [128 lanes x 512 columns]
+// fp32 TMEM array, tcgen05.ld 32x32b.x32.  MMAs and copies complete at issue; what is modelled is the LOGIC (addresses,
+// swizzles, phases, who waits for whom) -- a protocol that deadlocks here is reported by the scheduler -- not timing, proxies
+// or memory ordering.
+namespace emu {
+struct Mbar { uint16_t init, pending; int32_t tx; };  // the 8 bytes of the kernel's uint64_t; phase in the sign of `init`'s top bit
+static_assert(sizeof(Mbar) == 8, "mbarrier model must fit the 64-bit object");
+extern float g_tmem[128][512];
+extern Barrier g_named_bar[16];
+inline uint32_t smem_offset(const void* p) { return (uint32_t)(reinterpret_cast<const char*>(p) - dyn_smem); }
+inline char* smem_ptr(uint32_t off) { return dyn_smem + off; }
+inline Mbar* mb(uint64_t* bar) { return reinterpret_cast<Mbar*>(bar); }
+inline unsigned mbar_phase(uint64_t* bar) { return mb(bar)->init >> 15; }
+inline void mbar_check(uint64_t* bar) {
+  Mbar* m = mb(bar);
+  if (m->pending == 0 && m->tx == 0) { m->init ^= 0x8000u; m->pending = m->init & 0x7FFFu; }
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) { Mbar* m = mb(bar); m->init = (uint16_t)count; m->pending = (uint16_t)count; m->tx = 0; ++g_progress; }
+inline void mbar_arrive(uint64_t* bar) {
+  Mbar* m = mb(bar);
+  if (m->pending == 0) { fprintf(stderr, "emu: mbarrier over-arrival\n"); abort(); }
+  --m->pending; ++g_progress; mbar_check(bar);
+}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { mb(bar)->tx += (int32_t)bytes; mbar_arrive(bar); }
+inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) { mb(bar)->tx -= (int32_t)bytes; ++g_progress; mbar_check(bar); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (mbar_phase(bar) == (parity & 1u)) yield(); }  // spinning is not progress
+struct TMap { const char* base; uint64_t dims[2]; uint64_t stride_bytes; uint32_t box[2]; uint32_t esize; };
+static_assert(sizeof(TMap) <= sizeof(CUtensorMap), "fake tensor map must fit the opaque CUtensorMap");
+inline CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32_t rank, void* gaddr, const cuuint64_t* dims, const cuuint64_t* strides,
+                             const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
+                             CUtensorMapFloatOOBfill) {
+  if (rank != 2 || sw != CU_TENSOR_MAP_SWIZZLE_128B || box[0] * 2 != 128) return CUDA_ERROR_INVALID_VALUE;  // what the model covers
+  TMap t{reinterpret_cast<const char*>(gaddr), {dims[0], dims[1]}, strides[0], {box[0], box[1]}, 2};
+  memset(out, 0, sizeof(*out));
+  memcpy(out, &t, sizeof(t));
+  return CUDA_SUCCESS;
+}
+inline void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  TMap t;
+  memcpy(&t, map, sizeof(t));
+  char* dst = reinterpret_cast<char*>(smem_dst);
+  if (smem_offset(dst) % 1024) { fprintf(stderr, "emu: TMA destination not 1024-byte aligned\n"); abort(); }
+  for (uint32_t j = 0; j < t.box[1]; ++j) {
+    const long long row = (long long)c1 + j;
+    for (uint32_t ch = 0; ch < 8; ++ch) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+      char* d = dst + j * 128 + ((ch ^ (j & 7)) << 4);
+      const long long k = (long long)c0 + ch * 8;
+      if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k + 8 <= (long long)t.dims[0]) memcpy(d, t.base + row * t.stride_bytes + k * 2, 16);
+      else memset(d, 0, 16);  // out-of-range elements are zero-filled and still count as transferred bytes
+    }
+  }
+  mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esize);
+}
+inline float smem_half(uint32_t start, int row, int k, bool bf16) {  // K-major SWIZZLE_128B operand element
+  uint32_t logical = start + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
+  const uint32_t phys = logical ^ (((logical >> 7) & 7u) << 4);
+  unsigned short h;
+  memcpy(&h, dyn_smem + phys, 2);
+  return bf16 ? half_bits_to_float<__nv_bfloat16>(h) : half_bits_to_float<__half>(h);
+}
+inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+  const bool bf16 = ((idesc >> 7) & 7u) == 1u;
+  if (M != 128 || N < 8 || N > 256 || (adesc >> 61) != 2 || (bdesc >> 61) != 2) { fprintf(stderr, "emu: unsupported UMMA descriptor\n"); abort(); }
+  const uint32_t sa = (uint32_t)(adesc & 0x3FFFu) << 4, sb = (uint32_t)(bdesc & 0x3FFFu) << 4;
+  const int col0 = (int)(tmem_d & 0xFFFFu), lane0 = (int)(tmem_d >> 16);
+  if (col0 + N > 512 || lane0 != 0) { fprintf(stderr, "emu: accumulator outside TMEM\n"); abort(); }
+  static float Bt[256][16];
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) Bt[n][k] = smem_half(sb, n, k, bf16);
+  for (int r = 0; r < 128; ++r) {
+    float a[16];
+    for (int k = 0; k < 16; ++k) a[k] = smem_half(sa, r, k, bf16);
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? g_tmem[r][col0 + n] : 0.0f;
+      for (int k = 0; k < 16; ++k) acc += a[k] * Bt[n][k];
+      g_tmem[r][col0 + n] = acc;
+    }
+  }
+  ++g_progress;
+}
+inline void tmem_alloc(uint32_t* dst, int) { *dst = 0u; }
+inline void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  const int lane = (int)(taddr >> 16) + (linear_tid() & 31), col = (int)(taddr & 0xFFFFu);
+  if (lane >= 128 || col + 32 > 512) { fprintf(stderr, "emu: tcgen05.ld outside TMEM\n"); abort(); }
+  for (int j = 0; j < 32; ++j) memcpy(&v[j], &g_tmem[lane][col + j], 4);
+}
+inline void sts(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { const uint32_t v[4] = {a, b, c, d}; memcpy(dyn_smem + addr, v, 16); }
+inline void sts(uint32_t addr, uint32_t a, uint32_t b) { const uint32_t v[2] = {a, b}; memcpy(dyn_smem + addr, v, 8); }
+inline void named_barrier(int id, int n) { arrive(g_named_bar[id & 15], n); }
+}  // namespace emu
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
+inline void __threadfence() {}
+template <typename T> inline void __stcg(T* p, T v) { *p = v; }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
 
 // generated sources replace  kernel<<<g, b, s, st>>>(args)  by  EMU_LAUNCH((kernel), g, b, s, st)(args)
 #define EMU_LAUNCH(k, ...) ::emu::bind(k, __VA_ARGS__)

@@ -248,3 +248,64 @@ def test_emulated_one_token_kernel_variants_are_bit_identical(emu, tmp_path_fact
     assert ref.keys() == got.keys()
     for k in ref:
         assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# csrc/linear_gemm.cu on the emulator's functional model of mbarrier / TMA (SWIZZLE_128B) / UMMA descriptors / tcgen05.mma /
+# TMEM / tcgen05.ld: addresses, swizzles, barrier phases and who-waits-for-whom are executed; timing, async proxies and memory
+# ordering are not.  A barrier protocol that cannot make progress is reported as a deadlock by the scheduler.
+# ---------------------------------------------------------------------------------------------------------------------------
+GEMM_RUNNER = os.path.join(HERE, "emu", "run_gemm.py")
+_GEMM = {}
+
+
+def run_gemm_emu(tmp_path_factory, knob=None):
+    key = "default" if knob is None else "=".join(knob)
+    if key not in _GEMM:
+        out = str(tmp_path_factory.mktemp("emu_gemm") / "out.npz")
+        env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
+        if knob:
+            env[knob[0]] = knob[1]
+        r = subprocess.run([sys.executable, GEMM_RUNNER, out], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-3000:]
+        _GEMM[key] = dict(np.load(out))
+    return _GEMM[key]
+
+
+def test_emulated_tcgen05_gemm_matches_the_oracle(emu, tmp_path_factory):
+    d = run_gemm_emu(tmp_path_factory)
+    refs = [k for k in d if k.endswith("_ref")]
+    assert len(refs) == 12
+    for k in refs:
+        # the A operand is dequantised with the reference's two roundings and accumulated in fp32: far inside the fp16 tolerance
+        assert rel(d[k[:-4]], d[k]) <= 1e-4, k
+        assert np.array_equal(d[k[:-4]], d[k[:-4] + "_again"]), k
+        assert int(d[k[:-4] + "_ws"][0]) == 0  # no default route needs scratch
+
+
+@pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_UN", "128")])
+def test_emulated_gemm_variants_are_bit_identical(emu, tmp_path_factory, knob):
+    """un512 (two accumulators per dequantised weight tile), ld (loader warp + cp.async rings) and the UN cap issue the same MMAs in
+    the same k order as the default kernel: identical outputs, and no barrier protocol that stalls."""
+    ref, got = run_gemm_emu(tmp_path_factory), run_gemm_emu(tmp_path_factory, knob)
+    for k in ref:
+        if not k.endswith("_ws"):
+            assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
+
+
+def test_emulated_splitk_gemm(emu, tmp_path_factory):
+    """Split-K: k-slices in TMEM, fp32 partials in a (dirty) workspace, last-arriver reduction in slice order -- equal to the
+    one-accumulator kernel up to fp32 summation order, identical run to run, and the tile counters are left clean."""
+    ref, got = run_gemm_emu(tmp_path_factory), run_gemm_emu(tmp_path_factory, ("HQQ_B200_GEMM_SPLITK", "1"))
+    split = [k[:-3] for k in got if k.endswith("_ws") and int(got[k][0]) > 0]
+    assert len(split) >= 5  # the case list holds few-tile / long-K shapes on purpose
+    for k in ref:
+        if k.endswith("_ws"):
+            continue
+        base = k[:-6] if k.endswith("_again") else (k[:-4] if k.endswith("_ref") else k)
+        if base in split and not k.endswith("_ref"):
+            assert rel(got[k], ref[k]) <= 1e-4, k
+        else:
+            assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
+    for b in split:
+        assert np.array_equal(got[b], got[b + "_again"]), b  # second launch on the same workspace: counters were reset
