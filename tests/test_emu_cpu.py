@@ -309,3 +309,16 @@ def test_emulated_splitk_gemm(emu, tmp_path_factory):
             assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
     for b in split:
         assert np.array_equal(got[b], got[b + "_again"]), b  # second launch on the same workspace: counters were reset
+
+
+@pytest.mark.parametrize("tp", [2, 8])
+def test_emulated_tensor_parallel_exchange(emu, tmp_path, tp):
+    """The fused all-reduce (tagged words over peer memory, csrc/linear_small.cu) with `tp` ranks as `tp` buffer sets in one process:
+    every rank's buffer receives every rank's partial in slot [parity][rank][n] with the exchange's tag, the consumer's fp32
+    reduction in rank order + residual add reproduce numpy bit for bit, and the next linear sees the right activation -- over
+    three steps x two blocks, so tags and parities roll.  tp = 8 has not run on GPUs yet; this is its data path."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_tp.py"), str(tp), str(tmp_path / "tp.npz")], capture_output=True, text=True,
+                       timeout=900, env={k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")})
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = np.load(str(tmp_path / "tp.npz"))
+    assert len(d.files) == 3 * 2 * tp
