@@ -50,10 +50,10 @@ def make_layer(rng, N, K, nbits, gs, with_bias=False):
 
 # (nbits, gs, N, K, M, bias)
 PLAIN = [(4, 64, 32, 256, 1, False), (4, 64, 48, 512, 1, True), (4, 128, 32, 512, 1, False), (2, 64, 64, 256, 1, False), (1, 64, 64, 512, 1, True),
-         (8, 64, 32, 256, 1, False), (4, 64, 40, 768, 1, False), (4, 64, 32, 2304, 1, False),
+         (8, 64, 32, 256, 1, False), (4, 64, 40, 768, 1, False), (4, 64, 32, 2304, 1, False), (4, 64, 32, 1792, 1, False),
          (4, 64, 32, 256, 5, False), (2, 128, 64, 512, 3, True), (8, 64, 16, 256, 20, False), (4, 64, 48, 512, 32, False)]
 # one-token kernel with prologues / paired epilogue: (nbits, N, K)
-DECODE = [(4, 64, 512), (2, 64, 1024), (1, 128, 512), (4, 48, 1536)]
+DECODE = [(4, 64, 512), (2, 64, 1024), (1, 128, 512), (4, 48, 1536), (4, 224, 512)]
 
 
 def main(out_path):
