@@ -52,7 +52,7 @@ __device__ __forceinline__ void fence_async_smem() {}
 __device__ __forceinline__ void fence_barrier_init() {}
 __device__ __forceinline__ void tc_fence_before() {}
 __device__ __forceinline__ void tc_fence_after() {}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) { ::emu::mbar_arrive(bar); }  // the emulated MMAs complete at issue
+__device__ __forceinline__ void tc_commit(uint64_t* bar) { ::emu::tc_commit(bar); }  // arrives once the MMAs issued before it have executed
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   ::emu::umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
 }
@@ -902,7 +902,7 @@ struct SmemLd {
 template <int BYTES>
 __device__ __forceinline__ void cp_async_b(uint32_t smem_addr, const void* g) {
 #ifdef HQQ_EMU
-  memcpy(::emu::smem_ptr(smem_addr), g, BYTES);  // copies at issue time
+  ::emu::cp_async(::emu::smem_ptr(smem_addr), g, BYTES);  // lands when the mbarrier it is tied to says so
 #else
   if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr), "l"(g), "n"(BYTES) : "memory");
@@ -911,7 +911,7 @@ __device__ __forceinline__ void cp_async_b(uint32_t smem_addr, const void* g) {
 // the mbarrier receives one arrival from this thread once all of its earlier cp.async have landed (the count is part of init)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 #ifdef HQQ_EMU
-  ::emu::mbar_arrive(bar);
+  ::emu::cp_async_mbar_arrive(bar);
 #else
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 #endif

@@ -279,7 +279,7 @@ struct Lanes<__half, 8, MAGIC> {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
 #ifdef HQQ_EMU
-  memcpy(smem, g, 16);  // the emulator copies at issue time; commit/wait are no-ops
+  ::emu::cp_async(smem, g, 16);  // lands at the wait_group that covers it (tests/emu)
 #else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
@@ -299,7 +299,7 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 __device__ __forceinline__ void cp_async16_hint(void* smem, const void* g, uint64_t pol) {
 #ifdef HQQ_EMU
   (void)pol;
-  memcpy(smem, g, 16);
+  ::emu::cp_async(smem, g, 16);
 #else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "l"(pol) : "memory");
@@ -308,15 +308,15 @@ __device__ __forceinline__ void cp_async16_hint(void* smem, const void* g, uint6
 template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* smem, const void* g) {
 #ifdef HQQ_EMU
-  memcpy(smem, g, BYTES);
+  ::emu::cp_async(smem, g, BYTES);
 #else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(g), "n"(BYTES) : "memory");
 #endif
 }
 #ifdef HQQ_EMU
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N> __device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ void cp_async_commit() { ::emu::cp_async_commit(); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { ::emu::cp_async_wait(N); }
 __device__ __forceinline__ void pdl_wait() {}
 __device__ __forceinline__ void pdl_launch_dependents() {}
 #else

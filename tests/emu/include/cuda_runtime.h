@@ -55,6 +55,17 @@ extern char* dyn_smem;
 extern std::function<void()> g_body;
 extern long long g_progress;
 
+// Asynchronous engines (TMA, tensor core, cp.async-with-mbarrier) are modelled as deferred events: with EMU_ASYNC=<n> an operation
+// takes effect a random number (0..n) of scheduler passes after it was issued -- tensor-core operations in issue order, copies in
+// any order -- so a kernel that reads a stage without waiting for its barrier, or refills one the tensor core has not read yet,
+// computes garbage here too.  EMU_ASYNC unset: everything completes at issue.  EMU_SEED seeds the delays and shuffles the order
+// in which threads are resumed.
+extern long long g_tick;
+extern int g_async_max;
+void defer_ordered(std::function<void()> fn);    // tensor-core queue (FIFO)
+void defer_unordered(std::function<void()> fn);  // copy engines
+unsigned rnd();
+
 inline int linear_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
 inline void yield() { Fiber* f = g_cur; swapcontext(&f->ctx, &g_sched); }
 inline void arrive(Barrier& b, int need) {
@@ -208,16 +219,18 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, i
   memcpy(&t, map, sizeof(t));
   char* dst = reinterpret_cast<char*>(smem_dst);
   if (smem_offset(dst) % 1024) { fprintf(stderr, "emu: TMA destination not 1024-byte aligned\n"); abort(); }
-  for (uint32_t j = 0; j < t.box[1]; ++j) {
-    const long long row = (long long)c1 + j;
-    for (uint32_t ch = 0; ch < 8; ++ch) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
-      char* d = dst + j * 128 + ((ch ^ (j & 7)) << 4);
-      const long long k = (long long)c0 + ch * 8;
-      if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k + 8 <= (long long)t.dims[0]) memcpy(d, t.base + row * t.stride_bytes + k * 2, 16);
-      else memset(d, 0, 16);  // out-of-range elements are zero-filled and still count as transferred bytes
+  defer_unordered([=]() {
+    for (uint32_t j = 0; j < t.box[1]; ++j) {
+      const long long row = (long long)c1 + j;
+      for (uint32_t ch = 0; ch < 8; ++ch) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+        char* d = dst + j * 128 + ((ch ^ (j & 7)) << 4);
+        const long long k = (long long)c0 + ch * 8;
+        if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k + 8 <= (long long)t.dims[0]) memcpy(d, t.base + row * t.stride_bytes + k * 2, 16);
+        else memset(d, 0, 16);  // out-of-range elements are zero-filled and still count as transferred bytes
+      }
     }
-  }
-  mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esize);
+    mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esize);
+  });
 }
 inline float smem_half(uint32_t start, int row, int k, bool bf16) {  // K-major SWIZZLE_128B operand element
   uint32_t logical = start + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
@@ -226,7 +239,7 @@ inline float smem_half(uint32_t start, int row, int k, bool bf16) {  // K-major 
   memcpy(&h, dyn_smem + phys, 2);
   return bf16 ? half_bits_to_float<__nv_bfloat16>(h) : half_bits_to_float<__half>(h);
 }
-inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+inline void umma_now(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
   const bool bf16 = ((idesc >> 7) & 7u) == 1u;
   if (M != 128 || N < 8 || N > 256 || (adesc >> 61) != 2 || (bdesc >> 61) != 2) { fprintf(stderr, "emu: unsupported UMMA descriptor\n"); abort(); }
@@ -247,6 +260,12 @@ inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t i
   }
   ++g_progress;
 }
+// operands are read when the operation EXECUTES, which is when the deferred event fires
+inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  defer_ordered([=]() { umma_now(tmem_d, adesc, bdesc, idesc, accumulate); });
+}
+// tcgen05.commit: the barrier is signalled once every tensor-core operation issued before it has executed
+inline void tc_commit(uint64_t* bar) { defer_ordered([=]() { mbar_arrive(bar); }); }
 inline void tmem_alloc(uint32_t* dst, int) { *dst = 0u; }
 inline void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   const int lane = (int)(taddr >> 16) + (linear_tid() & 31), col = (int)(taddr & 0xFFFFu);
@@ -256,6 +275,30 @@ inline void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 inline void sts(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { const uint32_t v[4] = {a, b, c, d}; memcpy(dyn_smem + addr, v, 16); }
 inline void sts(uint32_t addr, uint32_t a, uint32_t b) { const uint32_t v[2] = {a, b}; memcpy(dyn_smem + addr, v, 8); }
 inline void named_barrier(int id, int n) { arrive(g_named_bar[id & 15], n); }
+// cp.async: a copy is only guaranteed to have landed after the thread's wait_group (or the mbarrier it signals) says so.  The
+// model performs it at the LATEST moment the program may rely on -- a kernel that consumes a ring slot too early reads old bytes.
+struct Copy { void* dst; const void* src; int bytes; };
+extern std::vector<Copy> g_cp_open[2048];               // per thread: copies of the group that is still open
+extern std::vector<std::vector<Copy>> g_cp_groups[2048];  // per thread: committed groups, oldest first
+inline void cp_async(void* dst, const void* src, int bytes) { g_cp_open[linear_tid()].push_back(Copy{dst, src, bytes}); }
+inline void cp_async_commit() { const int t = linear_tid(); g_cp_groups[t].push_back(std::move(g_cp_open[t])); g_cp_open[t].clear(); }
+inline void cp_async_wait(int allow_pending) {
+  auto& q = g_cp_groups[linear_tid()];
+  while ((int)q.size() > allow_pending) {
+    for (const Copy& c : q.front()) memcpy(c.dst, c.src, (size_t)c.bytes);
+    q.erase(q.begin());
+  }
+}
+// cp.async.mbarrier.arrive.noinc: the barrier is signalled when all of this thread's earlier copies have landed -- a deferred event
+inline void cp_async_mbar_arrive(uint64_t* bar) {
+  const int t = linear_tid();
+  std::vector<Copy> mine = std::move(g_cp_open[t]);
+  g_cp_open[t].clear();
+  defer_unordered([mine, bar]() {
+    for (const Copy& c : mine) memcpy(c.dst, c.src, (size_t)c.bytes);
+    mbar_arrive(bar);
+  });
+}
 }  // namespace emu
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
 inline void __threadfence() {}

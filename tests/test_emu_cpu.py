@@ -259,13 +259,15 @@ GEMM_RUNNER = os.path.join(HERE, "emu", "run_gemm.py")
 _GEMM = {}
 
 
-def run_gemm_emu(tmp_path_factory, knob=None):
-    key = "default" if knob is None else "=".join(knob)
+def run_gemm_emu(tmp_path_factory, knob=None, async_seed=None):
+    key = ("default" if knob is None else "=".join(knob)) + (f"@{async_seed}" if async_seed is not None else "")
     if key not in _GEMM:
         out = str(tmp_path_factory.mktemp("emu_gemm") / "out.npz")
-        env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
+        env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_") and not k.startswith("EMU_")}
         if knob:
             env[knob[0]] = knob[1]
+        if async_seed is not None:  # adversarial timing: asynchronous operations land 0..8 scheduler passes late, threads in random order
+            env["EMU_ASYNC"], env["EMU_SEED"] = "8", str(async_seed)
         r = subprocess.run([sys.executable, GEMM_RUNNER, out], env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-3000:]
         _GEMM[key] = dict(np.load(out))
@@ -351,3 +353,16 @@ def test_emulated_forward_random_shapes(emu, oracle):
         ref = oracle.linear_forward(x.astype(np.float32), L["Wq_host"], L["meta"], None if not wb else L["bias_host"].astype(np.float32), "float16")
         assert rel(y, ref) <= 2e-3, (nbits, gs, N, K, M, wb, route)
     assert routes == {1, 2}
+
+
+@pytest.mark.parametrize("knob", [None, ("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_SPLITK", "1")])
+def test_emulated_gemm_pipelines_under_adversarial_timing(emu, tmp_path_factory, knob):
+    """The emulator as a protocol checker: TMA copies, tensor-core operations (operands read when they EXECUTE, commits after them)
+    and mbarrier-tied cp.async land a random number of scheduler passes after issue, and threads are resumed in random order.  A
+    pipeline that reads a stage before its full barrier, or refills one before its empty barrier, computes garbage or deadlocks
+    here (checked by removing a wait while developing this); a correct one reproduces the in-order result bit for bit."""
+    ref = run_gemm_emu(tmp_path_factory, knob)
+    for seed in (1, 2):
+        got = run_gemm_emu(tmp_path_factory, knob, async_seed=seed)
+        for k in ref:
+            assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), (k, seed)
