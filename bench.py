@@ -307,7 +307,7 @@ def run_probes(budget_s=150.0, timeout_s=50.0):
 
     res = {"solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
            "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
-           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
+           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
            "gemm_mid": against_default("gemm_mid", [("HQQ_B200_GEMM_SPLITK", "1")]),
            "decode_8_blocks": against_default("decode", [("HQQ_B200_D1_VARIANT", "7042"), ("HQQ_B200_D1_VARIANT", "1042")])}
     res["seconds"] = round(time.perf_counter() - t_start, 1)

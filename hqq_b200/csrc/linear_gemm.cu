@@ -1128,6 +1128,242 @@ __global__ void __launch_bounds__(kLdThreads, 1) linear_gemm_ld_kernel(const __g
   }
 }
 
+// =====================================================================================================================
+// Variant "ld512" (HQQ_B200_GEMM_VARIANT=ld512, experimental): the loader-warp kernel above with the two accumulators of
+// "un512" -- dequant warps that never touch global memory AND half the dequant work per flop.  Shared memory: 4 x 16 KB A
+// stages, 2 x 64 KB B stages, a 16 KB packed-byte ring (8-bit: 2 k-blocks, 4-bit: 4, 2/1-bit: 8), 4 meta slots.
+template <int NBITS>
+struct SmemLd512 {
+  static constexpr int UN = 512, UNH = 256, kStagesB = 2;
+  static constexpr int PR = kTileRows / (8 / NBITS);
+  static constexpr int A_STAGE = kTileRows * 128;
+  static constexpr int B_HALF = UNH * 128;
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int W_STAGE = PR * kBlockK;
+  static constexpr int NW = (16 * 1024 / W_STAGE) < 8 ? (16 * 1024 / W_STAGE) : 8;
+  static constexpr int M_SLOT = kTileRows * 2 * 8;
+  static constexpr int BYTES = kStages * A_STAGE + kStagesB * B_STAGE + NW * W_STAGE + kMetaSlots * M_SLOT + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(4 * kMetaSlots >= NW + 4, "a meta slot must outlive the W stages of its four k-blocks");
+  static_assert(BYTES <= 227 * 1024, "shared-memory budget");
+};
+
+template <typename T, int NBITS, int GS>
+__global__ void __launch_bounds__(kLdThreads, 1) linear_gemm_ld512_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  constexpr int F = 8 / NBITS;
+  constexpr int PR = kTileRows / F;
+  constexpr int BPT = 64 * PR / kDequantThreads;
+  constexpr int TPR = 64 / BPT;
+  constexpr int GPQ = 256 / GS;  // groups per four k-blocks
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = SmemLd512<NBITS>;
+  constexpr int UN = S::UN, UNH = S::UNH, kStagesB = S::kStagesB;
+  using P2 = Pair<T>;
+  constexpr int NW = S::NW;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kStages * S::A_STAGE;
+  uint8_t* sW = sB + kStagesB * S::B_STAGE;
+  uint8_t* sM = sW + NW * S::W_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sM + kMetaSlots * S::M_SLOT);
+  uint64_t* full_a = bars;                       // [kStages]  dequant warps -> MMA (one arrival per warp)
+  uint64_t* empty_a = full_a + kStages;          // [kStages]  MMA (tcgen05.commit) -> dequant warps
+  uint64_t* full_b = empty_a + kStages;          // [kStagesB] TMA -> MMA
+  uint64_t* empty_b = full_b + kStagesB;         // [kStagesB] MMA -> TMA
+  uint64_t* full_w = empty_b + kStagesB;         // [NW] loader lanes (32 async arrivals) -> dequant warps
+  uint64_t* empty_w = full_w + NW;               // [NW] dequant warps (one arrival per warp) -> loader
+  uint64_t* accum_full = empty_w + NW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int prow0 = tile_n * PR;
+  const int m0 = tile_m * UN;
+  const int num_kb = a.K / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty_a[s], 1); }
+      for (int s = 0; s < kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+      for (int s = 0; s < NW; ++s) { mbar_init(&full_w[s], 32); mbar_init(&empty_w[s], kDequantThreads / 32); }
+      mbar_init(accum_full, 1);
+      fence_barrier_init();
+      HQQ_PREFETCH_TENSORMAP(&xmap);
+    }
+    __syncwarp();
+    tmem_alloc<UN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: activation tiles =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStagesB;
+        mbar_wait(&empty_b[s], ((kb / kStagesB) & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], S::B_STAGE);  // both 256-token boxes
+        tma_load_2d(sB + s * S::B_STAGE, &xmap, &full_b[s], kb * kBlockK, m0);
+        tma_load_2d(sB + s * S::B_STAGE + S::B_HALF, &xmap, &full_b[s], kb * kBlockK, m0 + UNH);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one elected thread) =================
+    const uint32_t idesc = make_idesc<T>(UNH);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sa = kb % kStages, sb = kb % kStagesB;
+      mbar_wait(&full_a[sa], (kb / kStages) & 1);
+      mbar_wait(&full_b[sb], (kb / kStagesB) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_desc_sw128(smem_u32(sA + sa * S::A_STAGE));
+        const uint64_t bdesc0 = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE));
+        const uint64_t bdesc1 = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE + S::B_HALF));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)  // second accumulator: TMEM columns 256..511
+          tc_mma_f16(tmem_base + (uint32_t)UNH, adesc + (uint64_t)(k * 2), bdesc1 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(&empty_a[sa]);
+        tc_commit(&empty_b[sb]);
+        if (kb == num_kb - 1) tc_commit(accum_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ================= loader: packed tile + scale/zero -> shared-memory rings (cp.async, no registers) =================
+    const uint32_t sW_u32 = smem_u32(sW), sM_u32 = smem_u32(sM);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sw = kb % NW;
+      mbar_wait(&empty_w[sw], ((kb / NW) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < PR * 4 / 32; ++i) {  // PR rows x four 16-byte chunks, lanes along the row: coalesced 64-byte rows
+        const int id = i * 32 + lane, row = id >> 2, ch = id & 3;
+        const int prow = prow0 + row;
+        const uint8_t* src = a.Wq + (long long)(prow < a.step ? prow : 0) * a.K + kb * kBlockK + ch * 16;
+        cp_async_b<16>(sW_u32 + sw * S::W_STAGE + row * kBlockK + ch * 16, src);
+      }
+      if ((kb & 3) == 0) {  // the groups of k-blocks kb .. kb+3: GPQ values per row and array
+        const int slot = (kb >> 2) % kMetaSlots;
+#pragma unroll
+        for (int i = 0; i < kTileRows * 2 / 32; ++i) {
+          const int id = i * 32 + lane, arr = id >> 7, t = id & (kTileRows - 1);
+          const int f = t / PR, prow = prow0 + t % PR;
+          const long long mrow = (prow < a.step) ? (long long)f * a.step + prow : 0;
+          const T* src = reinterpret_cast<const T*>(arr ? a.zero : a.scale) + mrow * a.Gk + (kb >> 2) * GPQ;
+          cp_async_b<GPQ * 2>(sM_u32 + slot * S::M_SLOT + (arr * kTileRows + t) * (GPQ * 2), src);
+        }
+      }
+      cp_async_mbar_arrive(&full_w[sw]);
+    }
+  } else {
+    // ================= dequant warps: shared-memory packed bytes -> swizzled fp16/bf16 A tile =================
+    static_assert(kStages == 4, "the dequant loop is unrolled over the 4 A stages");
+    const int td = threadIdx.x - 96;
+    const int pr = td / TPR, c = td % TPR;
+    uint32_t soff[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const int row = f * PR + pr;
+      if constexpr (BPT >= 8) soff[f] = (uint32_t)(row * 128) | ((uint32_t)(row & 7) << 16);
+      else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
+    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router)
+    for (int q = 0; q < num_quads; ++q) {
+      typename P2::T2 s2[4][F], z2[4][F];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int kb = 4 * q + d;
+        const int sw = kb % NW;
+        mbar_wait(&full_w[sw], (kb / NW) & 1);
+        if (d == 0) {  // this quad's scale/zero arrived with its first k-block
+          const uint8_t* slot = sM + (q % kMetaSlots) * S::M_SLOT;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const Vec<T, GPQ> sv = *reinterpret_cast<const Vec<T, GPQ>*>(slot + (0 * kTileRows + f * PR + pr) * (GPQ * 2));
+            const Vec<T, GPQ> zv = *reinterpret_cast<const Vec<T, GPQ>*>(slot + (1 * kTileRows + f * PR + pr) * (GPQ * 2));
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) { s2[dd][f] = P2::bcast(sv.v[(dd * kBlockK) / GS]); z2[dd][f] = P2::bcast(zv.v[(dd * kBlockK) / GS]); }
+          }
+        }
+        uint32_t wq[BPT / 4];
+        {
+          const uint8_t* p = sW + sw * S::W_STAGE + pr * kBlockK + c * BPT;
+          if constexpr (BPT == 32) { const uint4 v0 = *reinterpret_cast<const uint4*>(p), v1 = *reinterpret_cast<const uint4*>(p + 16); wq[0] = v0.x; wq[1] = v0.y; wq[2] = v0.z; wq[3] = v0.w; wq[4] = v1.x; wq[5] = v1.y; wq[6] = v1.z; wq[7] = v1.w; }
+          else if constexpr (BPT == 16) { const uint4 v = *reinterpret_cast<const uint4*>(p); wq[0] = v.x; wq[1] = v.y; wq[2] = v.z; wq[3] = v.w; }
+          else if constexpr (BPT == 8) { const uint2 v = *reinterpret_cast<const uint2*>(p); wq[0] = v.x; wq[1] = v.y; }
+          else { wq[0] = *reinterpret_cast<const uint32_t*>(p); }
+        }
+        mbar_wait(&empty_a[d], (uint32_t)(q & 1) ^ 1u);  // A stage index == d (four stages, four k-blocks per quad)
+        const uint32_t stage = sA_u32 + d * S::A_STAGE;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const int sh = 8 - NBITS * (f + 1);
+          uint32_t out[BPT / 2];
+#pragma unroll
+          for (int i = 0; i < BPT / 4; ++i) {
+            const uint32_t t = (wq[i] >> sh) & (MASK * 0x01010101u);
+            P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
+          }
+          if constexpr (BPT >= 8) {
+            const uint32_t rowbase = stage + (soff[f] & 0xFFFFu), rx = soff[f] >> 16;
+#pragma unroll
+            for (int ch = 0; ch < BPT / 8; ++ch) {
+              const uint32_t addr = rowbase + (((uint32_t)(c * (BPT / 8) + ch) ^ rx) << 4);
+              HQQ_STS_V4(addr, out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
+            }
+          } else {
+            HQQ_STS_V2(stage + soff[f], out[0], out[1]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&full_a[d]); mbar_arrive(&empty_w[sw]); }  // every lane's packed bytes (and meta) are in registers
+      }
+    }
+
+    // ================= epilogue: TMEM -> registers -> y =================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 3) >> 2;             // two warps share a quarter: split the token columns
+    const int t = quarter * 32 + lane;
+    const int tf = t / PR, tp = t % PR;
+    const bool n_ok = (prow0 + tp) < a.step;
+    const int n = tf * a.step + prow0 + tp;
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const bool has_bias = bias != nullptr;
+    T bn = cvt_out<T>(0.0f);
+    if (has_bias && n_ok) bn = bias[n];
+#pragma unroll 1
+    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + col + j;
+        if (n_ok && m < a.M) {
+          T o = cvt_out<T>(__uint_as_float(v[j]));
+          if (has_bias) o = __hadd(o, bn);
+          y[(long long)m * a.N + n] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<UN>(tmem_base);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1147,12 +1383,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // HQQ_B200_GEMM_VARIANT: "ld" = loader-warp kernel (linear_gemm_ld_kernel), "un512" = two accumulators per weight tile
-// (linear_gemm_un512_kernel, M > 256 only); both experimental
+// (linear_gemm_un512_kernel, M > 256 only), "ld512" = both (linear_gemm_ld512_kernel, M > 256 only); all experimental
 static int gemm_variant() {
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("HQQ_B200_GEMM_VARIANT");
-    variant = (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : 0;
+    variant = (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : (e && !strcmp(e, "ld512")) ? 3 : 0;
   }
   return variant;
 }
@@ -1209,6 +1445,26 @@ static int splitk_factor(int64_t M, int64_t N, int64_t K, int nbits) {
   return S < 1 ? 1 : (int)S;
 }
 static size_t splitk_counter_bytes(int64_t M, int64_t N) { return (size_t)((cdiv(N, kTileRows) * cdiv(M, 64) * 4 + 255) & ~(int64_t)255); }
+
+template <typename T, int NBITS, int GS>
+static int launch_ld512(const void* x, const Args& a, cudaStream_t st) {
+  CUtensorMap xmap;
+  const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  using S = SmemLd512<NBITS>;
+  int rc = encode_xmap(&xmap, x, a, dt, sizeof(T), S::UNH);
+  if (rc) return rc;
+  const dim3 grid((unsigned)cdiv(a.step, S::PR), (unsigned)cdiv(a.M, S::UN));
+  auto k = linear_gemm_ld512_kernel<T, NBITS, GS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", S::BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  k<<<grid, kLdThreads, S::BYTES, st>>>(xmap, a);
+  HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05-ld512");
+  return HQQ_OK;
+}
 
 template <typename T, int NBITS, int GS, int UN>
 static int launch_splitk(const void* x, const Args& a0, int S, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1291,6 +1547,7 @@ static int by_un(const void* x, const Args& a, void* ws, size_t ws_bytes, cudaSt
   static int un_cap = -1;  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
   if (un_cap < 0) { const char* e = getenv("HQQ_B200_GEMM_UN"); un_cap = e ? atoi(e) : 256; }
   if (a.M > 256 && gemm_variant() == 2) return launch_un512<T, NBITS, GS>(x, a, st);
+  if (a.M > 256 && gemm_variant() == 3) return launch_ld512<T, NBITS, GS>(x, a, st);
   if (a.M <= 64 || un_cap <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
   if (a.M <= 128 || un_cap <= 128) return launch<T, NBITS, GS, 128>(x, a, st);
   return launch<T, NBITS, GS, 256>(x, a, st);

@@ -17,6 +17,7 @@ echo "== GEMM M=4096: default / ld / un512 / UN caps"
 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=un512 timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
+HQQ_B200_GEMM_VARIANT=ld512 timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 echo "== 3-bit, one token: dequantise + GEMM (default) vs fused (HQQ_B200_FUSED_3BIT=1)"
