@@ -253,7 +253,7 @@ def _finite(o):
     return o
 
 
-def run_probes(budget_s=150.0, timeout_s=50.0):
+def run_probes(budget_s=165.0, timeout_s=50.0):
     """First GPU execution of the kernels written after round 1's GPU budget was spent: each knob runs
     tools/variant_probe.py in its OWN process under a timeout -- a crash or a hang there cannot reach this process -- on a fixed
     seeded workload, and is compared with the default kernels (sha256 of the outputs, relative error where the summation order
@@ -309,7 +309,7 @@ def run_probes(budget_s=150.0, timeout_s=50.0):
            "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
            "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
            "gemm_mid": against_default("gemm_mid", [("HQQ_B200_GEMM_SPLITK", "1")]),
-           "decode_8_blocks": against_default("decode", [("HQQ_B200_D1_VARIANT", "7042"), ("HQQ_B200_D1_VARIANT", "1042")])}
+           "decode_8_blocks": against_default("decode", [("HQQ_B200_D1_VARIANT", "7042"), ("HQQ_B200_WPF_MB", "16"), ("HQQ_B200_WPF_MB", "48")])}
     res["seconds"] = round(time.perf_counter() - t_start, 1)
     return res
 

@@ -63,7 +63,7 @@ class DecodeDesc(ctypes.Structure):
                 ("peer_data", c_void_p), ("red_data", c_void_p), ("y_tagged", c_void_p), ("x_tagged", c_void_p), ("x2_tagged", c_void_p),
                 ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int), ("skip_wait", c_int),
                 ("l2_hint", c_void_p * 2), ("l2_hint_rows", c_void_p), ("l2_hint_chunks", c_int), ("l2_hint_row_bytes", c_int),
-                ("l2_hint_chunk_stride", c_int64)]
+                ("l2_hint_chunk_stride", c_int64), ("pf_ptr", c_void_p * 4), ("pf_bytes", c_int64 * 4)]
 
 
 class HQQB200Error(RuntimeError):

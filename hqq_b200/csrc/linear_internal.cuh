@@ -19,6 +19,8 @@ struct TpExchange {
   const int64_t* l2_hint_rows;
   int l2_hint_chunks, l2_hint_row_bytes;
   int64_t l2_hint_chunk_stride;
+  const void* pf_ptr[4];  // weight prefetch spans for the following launches (hqq_b200_decode_desc::pf_*)
+  int64_t pf_bytes[4];
 };
 
 }  // namespace hqq

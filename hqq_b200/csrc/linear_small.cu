@@ -87,6 +87,9 @@ struct SKArgs {
   const long long* hint_rows;
   int hint_chunks, hint_row_lines;  // 128-byte lines per row
   long long hint_stride;
+  // optional weight prefetch for the following launches (hqq_b200_decode_desc::pf_*): spans of 128-byte lines, 0 lines = end
+  const char* pf_ptr[4];
+  long long pf_lines[4];
 };
 
 // L2 prefetch (a pure hint): nothing to do on the emulator
@@ -796,6 +799,12 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       if (a.hint[1]) HQQ_PREFETCH_L2(a.hint[1] + off);
     }
   }
+  if (a.pf_lines[0] > 0) {
+    // HBM is idle while this kernel waits for its inputs and the weights of the next launches depend on nothing: pull them into L2
+#pragma unroll 1
+    for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp)
+      for (long long i = (long long)blockIdx.x * 256 + tid; i < a.pf_lines[sp]; i += (long long)gridDim.x * 256) HQQ_PREFETCH_L2(a.pf_ptr[sp] + (i << 7));
+  }
   if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
   else { pdl_launch_dependents(); if (a.skip_wait == 0) pdl_wait(); }
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
@@ -1300,7 +1309,14 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     a.hint_rows = reinterpret_cast<const long long*>(tpx->l2_hint_rows); a.hint_chunks = tpx->l2_hint_chunks;
     a.hint_row_lines = tpx->l2_hint_row_bytes >> 7; a.hint_stride = tpx->l2_hint_chunk_stride;
   }
-  if (tpx && !tpx->step_ctr) tpx = nullptr;  // hint only
+  for (int i = 0; i < 4; ++i) { a.pf_ptr[i] = nullptr; a.pf_lines[i] = 0; }
+  if (tpx && tpx->pf_bytes[0] > 0) {
+    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
+    for (int i = 0, j = 0; i < 4 && tpx->pf_bytes[i] > 0; ++i) {
+      a.pf_ptr[j] = reinterpret_cast<const char*>(tpx->pf_ptr[i]); a.pf_lines[j] = (long long)(tpx->pf_bytes[i] >> 7); ++j;
+    }
+  }
+  if (tpx && !tpx->step_ctr) tpx = nullptr;  // hints only
   if (tpx) {
     HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
     HQQ_REQUIRE(tpx->tp >= 1 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,

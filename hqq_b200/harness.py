@@ -77,6 +77,9 @@ class DecodeModel:
         self.pair_silu = os.environ.get("HQQ_B200_PAIR_SILU", "1") != "0"
         # measured neutral at cache_len 256 (the attention kernel already prefetches under the q/k/v tail): opt-in
         self.kv_hint = os.environ.get("HQQ_B200_KV_HINT", "0") == "1"
+        # cross-launch weight prefetch into L2 (MiB per launch, how many following linear launches it may cover); 0 = off
+        self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
+        self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
         self.nbits = nbits
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -265,47 +268,47 @@ class DecodeModel:
             if chain:
                 # [residual add + RMSNorm] -> q/k/v; the delta is the sum of the ranks' down-proj partials of block bi-1
                 ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None, blk["norm1"], h_nxt, s.rms_eps,
-                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None), l2_hint=self._kv_hint(blk))
+                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None), l2_hint=self._kv_hint(blk), wpf=self._wpf(bi, "qkv"))
             else:
                 ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps,
-                                            l2_hint=self._kv_hint(blk))
+                                            l2_hint=self._kv_hint(blk), wpf=self._wpf(bi, "qkv"))
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
             if chain:
-                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc, skip_wait=2 if (self.chain_all and self.skip_wait) else 0))
+                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc, skip_wait=2 if (self.chain_all and self.skip_wait) else 0), wpf=self._wpf(bi, "o"))
                 # the next two kernels take everything the preceding kernel produces as tagged words: they skip the
                 # programmatic-dependency wait and start streaming their weights under its tail
                 if self.chain_all:
                     ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                                tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait))
+                                                tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait), wpf=self._wpf(bi, "gu"))
                     h_cur, h_nxt = h_nxt, h_cur
                     ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
-                                                tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait))
+                                                tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait), wpf=self._wpf(bi, "down"))
                 else:
                     if pair:  # act = silu(gate) * up leaves the gate/up launch's epilogue; down takes it as is
                         ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, None, blk["norm2"],
-                                                    h_nxt, s.rms_eps, tpx=self._tpx(bi, red_data=o_loc))
+                                                    h_nxt, s.rms_eps, tpx=self._tpx(bi, red_data=o_loc), wpf=self._wpf(bi, "gu"))
                         h_cur, h_nxt = h_nxt, h_cur
-                        ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], tpx=self._tpx(bi, peer_data=d_sc))
+                        ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], tpx=self._tpx(bi, peer_data=d_sc), wpf=self._wpf(bi, "down"))
                     else:
                         ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                                    tpx=self._tpx(bi, red_data=o_loc))
+                                                    tpx=self._tpx(bi, red_data=o_loc), wpf=self._wpf(bi, "gu"))
                         h_cur, h_nxt = h_nxt, h_cur
-                        ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc))
+                        ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc), wpf=self._wpf(bi, "down"))
             else:
-                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]])
+                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], wpf=self._wpf(bi, "o"))
                 if self.tp > 1:
                     torch.distributed.all_reduce(b["o"], group=self.pg)
                 if pair:
                     ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, b["o"], blk["norm2"],
-                                                h_nxt, s.rms_eps)
+                                                h_nxt, s.rms_eps, wpf=self._wpf(bi, "gu"))
                     h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]])
+                    ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], wpf=self._wpf(bi, "down"))
                 else:
-                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps)
+                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps, wpf=self._wpf(bi, "gu"))
                     h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"])
+                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], wpf=self._wpf(bi, "down"))
                 if self.tp > 1:
                     torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
@@ -319,6 +322,22 @@ class DecodeModel:
         torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
         check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
         self.pos.add_(1).remainder_(self.cache_len)
+
+    def _wpf(self, bi, stage):
+        """Weight prefetch spans for the launches that FOLLOW launch `stage` of block `bi` (hqq_b200_decode_desc::pf_*): the packed
+        weights of the next `wpf_ahead` linear launches, at most `wpf_mb` MiB and four spans, wrapping into the next block.
+        Off unless HQQ_B200_WPF_MB > 0 (experimental: not yet timed on a GPU)."""
+        if self.wpf_mb <= 0:
+            return None
+        order = ("qkv", "o", "gu", "down")
+        groups = {"qkv": ("q", "k", "v"), "o": ("o",), "gu": ("gate", "up"), "down": ("down",)}
+        i, blk, seq = order.index(stage), bi, []
+        for _ in range(self.wpf_ahead):
+            i += 1
+            if i == len(order):
+                i, blk = 0, (blk + 1) % len(self.blocks)
+            seq += [self.blocks[blk][n] for n in groups[order[i]]]
+        return wpf_spans([(l.W_q.data_ptr(), l.W_q.numel() * l.W_q.element_size()) for l in seq], int(self.wpf_mb * (1 << 20)))
 
     def _kv_hint(self, blk):
         """The q/k/v launch warms L2 with the cache rows the attention kernel behind it reads (they are evicted by the ~5 GB
@@ -367,6 +386,20 @@ class DecodeModel:
         self.graph.replay()
         if feed_back:
             self.tok.copy_(self.next_tok)
+
+
+def wpf_spans(tensors, budget_bytes: int, max_spans: int = 4):
+    """(address, bytes) prefetch spans over `tensors` [(address, nbytes), ...] in order: whole 128-byte lines, at most `budget_bytes`
+    in total and `max_spans` spans (the last one is cut to fit).  Pure host logic (unit-tested on CPU)."""
+    spans = []
+    for addr, nbytes in tensors:
+        if budget_bytes < 128 or len(spans) == max_spans:
+            break
+        take = min(int(nbytes), budget_bytes) & ~127
+        if take > 0:
+            spans.append((int(addr), take))
+            budget_bytes -= take
+    return spans or None
 
 
 # ---------------------------------------------------------------------------------------------- quantise-only sharding (SURVEY 8e)

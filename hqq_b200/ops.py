@@ -225,13 +225,15 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
 YOP_SILU_MUL_PAIR = 16  # HQQ_YOP_SILU_MUL_PAIR (include/hqq_b200.h): or-ed into x_op
 
 
-def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None, l2_hint=None) -> bool:
+def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None, l2_hint=None,
+                      wpf=None) -> bool:
     """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
     residual add + RMSNorm, 2 = SiLU(x) * x2.  `tpx` (dict) switches on the peer-memory exchange of
     `hqq_b200_decode_linear_fwd_desc`: keys tp, rank, step_ctr, x_index, x_per_step and any of peer_data (ctypes array of peer
     pointers), red_data, y_tagged (list of addresses), x_tagged, x2_tagged (addresses), skip_wait.  `l2_hint` (dict: ptrs (a, b),
     rows = device int64 address, chunks, row_bytes, chunk_stride) asks the grid to warm L2 with the next kernel's read-only rows
-    (the KV cache) before it waits for its own inputs.  Returns False when the configuration is outside the fused M = 1 kernel."""
+    (the KV cache) before it waits for its own inputs; `wpf` (up to four (address, bytes) pairs) does the same for the packed weights
+    of the FOLLOWING launches (hqq_b200_decode_desc::pf_*).  Returns False when the configuration is outside the fused M = 1 kernel."""
     import ctypes
     lib = load()
     n = len(layers)
@@ -244,7 +246,7 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
     VP = ctypes.c_void_p * n
     arr = lambda ts: VP(*[ptr(t) for t in ts])
     Narr = (ctypes.c_int64 * n)(*[int(l.meta["shape"][0]) for l in layers])
-    if tpx is None and l2_hint is None:
+    if tpx is None and l2_hint is None and not wpf:
         rc = lib.hqq_b200_decode_linear_fwd(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
                                             arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
                                             arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
@@ -263,6 +265,10 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
                             peer_data=cast(tpx.get("peer_data")), red_data=tpx.get("red_data"), y_tagged=cast(ytag_arr),
                             x_tagged=tpx.get("x_tagged"), x2_tagged=tpx.get("x2_tagged"), step_ctr=tpx["step_ctr"],
                             x_index=int(tpx["x_index"]), x_per_step=int(tpx["x_per_step"]), skip_wait=int(tpx.get("skip_wait", 0)))
+        if wpf:
+            spans = [(int(p), int(b)) for p, b in wpf if b > 0][:4]
+            d.pf_ptr = (ctypes.c_void_p * 4)(*([p for p, _ in spans] + [None] * (4 - len(spans))))
+            d.pf_bytes = (ctypes.c_int64 * 4)(*([b for _, b in spans] + [0] * (4 - len(spans))))
         if l2_hint is not None:
             d.l2_hint = (ctypes.c_void_p * 2)(*[int(p) if p else None for p in l2_hint["ptrs"]])
             d.l2_hint_rows = int(l2_hint["rows"])

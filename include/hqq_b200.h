@@ -192,6 +192,12 @@ typedef struct hqq_b200_decode_desc {
    * prefetched into L2 by the whole grid before it waits for its own inputs.  *l2_hint_rows must not be written by a kernel
    * launched with programmatic dependent launch in the same step.  All zero / NULL = off. */
   const void* l2_hint[2]; const int64_t* l2_hint_rows; int l2_hint_chunks; int l2_hint_row_bytes; int64_t l2_hint_chunk_stride;
+  /* optional weight prefetch for the FOLLOWING launches of the step: up to four read-only spans (packed weights of the next
+   * linears) that the whole grid pulls into L2 with prefetch.global.L2 before it waits for its own inputs.  One decoded token is a
+   * chain of dependent, latency-bound launches during which HBM sits idle, while the weights further down the chain depend on
+   * nothing: this keeps HBM busy ahead of the computation (the 126 MB L2 holds about one block's packed weights).  A pure hint --
+   * results never depend on it.  pf_bytes[i] == 0 ends the list. */
+  const void* pf_ptr[4]; int64_t pf_bytes[4];
 } hqq_b200_decode_desc;
 int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* desc, void* stream);
 /* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */

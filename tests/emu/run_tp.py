@@ -57,6 +57,10 @@ def run(tp, out):
                 d = DecodeDesc(x=xs[r].ctypes.data, x_op=0, count=1, W_q=keep[0][1], scale=keep[1][1], zero=keep[2][1], bias=keep[3][1], y=keep[4][1],
                                N=ctypes.cast(N, VP), K=Kr, group_size=64, nbits=nbits, dtype=R.F16, tp=tp, rank=r, peer_data=peer_ptr,
                                step_ctr=step_ctr.ctypes.data, x_index=blk + 1, x_per_step=nblocks)
+                # weight-prefetch spans for the launch that follows (a pure hint: the emulator ignores it, the descriptor must parse)
+                nxt = col[blk][r]["Wq"]
+                d.pf_ptr = (VP * 4)(nxt.ctypes.data, None, None, None)
+                d.pf_bytes = (ctypes.c_int64 * 4)(nxt.nbytes & ~127, 0, 0, 0)
                 assert lib.hqq_b200_decode_linear_fwd_desc(ctypes.byref(d), None) == 0, lib.hqq_b200_last_error()
             ex = step * nblocks + blk + 1
             tag, par = ex & 0xFFFF, ex & 1

@@ -9,6 +9,11 @@ echo "== decode step under each M = 1 kernel variant"
 for v in 0 1042 2042 3042 4042 7042 1033 7033; do
   echo -n "D1_VARIANT=$v: "; HQQ_B200_D1_VARIANT=$v timeout 120 python tools/step_time.py 2>&1 | tail -1
 done
+echo "== decode step with cross-launch weight prefetch (MiB per launch; > 24 covers two launches ahead)"
+for mb in 4 8 16 32 48 64; do
+  echo -n "WPF_MB=$mb: "; HQQ_B200_WPF_MB=$mb timeout 120 python tools/step_time.py 2>&1 | tail -1
+  echo -n "WPF_MB=$mb + D1 7042: "; HQQ_B200_WPF_MB=$mb HQQ_B200_D1_VARIANT=7042 timeout 120 python tools/step_time.py 2>&1 | tail -1
+done
 echo "== quantizer: default vs fast solver (HQQ_B200_SOLVER_VARIANT=1), Llama-3-8B and 70B layer shapes"
 timeout 200 python tools/prof_quantize.py 8b 4
 HQQ_B200_SOLVER_VARIANT=1 timeout 200 python tools/prof_quantize.py 8b 4,2
