@@ -52,6 +52,7 @@ SIGNATURES = {
     "hqq_b200_glue_argmax": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "hqq_b200_launch_count": (c_int64, []),
     "hqq_b200_launch_count_reset": (None, []),
+    "hqq_b200_reload_env": (None, []),
 }
 
 

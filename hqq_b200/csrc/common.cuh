@@ -14,6 +14,16 @@ namespace hqq {
 // ---- error plumbing -----------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+extern std::atomic<int> g_env_epoch;  // bumped by hqq_b200_reload_env(): cached HQQ_B200_* knobs are parsed again
+
+// `static int var`, parsed from the environment by `expr` on first use and again after every hqq_b200_reload_env()
+#define HQQ_ENV_KNOB(var, expr)                                                     \
+  static int var = 0;                                                               \
+  {                                                                                 \
+    static int epoch__ = -1;                                                        \
+    const int now__ = ::hqq::g_env_epoch.load(std::memory_order_relaxed);           \
+    if (epoch__ != now__) { var = (expr); epoch__ = now__; }                        \
+  }
 
 #define HQQ_REQUIRE(cond, code, ...)            \
   do {                                          \

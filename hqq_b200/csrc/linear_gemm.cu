@@ -1385,11 +1385,10 @@ static EncodeTiledFn get_encode() {
 // HQQ_B200_GEMM_VARIANT: "ld" = loader-warp kernel (linear_gemm_ld_kernel), "un512" = two accumulators per weight tile
 // (linear_gemm_un512_kernel, M > 256 only), "ld512" = both (linear_gemm_ld512_kernel, M > 256 only); all experimental
 static int gemm_variant() {
-  static int variant = -1;
-  if (variant < 0) {
+  HQQ_ENV_KNOB(variant, ([] {
     const char* e = getenv("HQQ_B200_GEMM_VARIANT");
-    variant = (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : (e && !strcmp(e, "ld512")) ? 3 : 0;
-  }
+    return (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : (e && !strcmp(e, "ld512")) ? 3 : 0;
+  })());
   return variant;
 }
 
@@ -1428,8 +1427,7 @@ static int launch_un512(const void* x, const Args& a, cudaStream_t st) {
 
 // ---- split-K selection (opt-in) ---------------------------------------------------------------------------------------
 static bool splitk_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("HQQ_B200_GEMM_SPLITK"); on = (e && e[0] == '1') ? 1 : 0; }
+  HQQ_ENV_KNOB(on, ([] { const char* e = getenv("HQQ_B200_GEMM_SPLITK"); return (e && e[0] == '1') ? 1 : 0; })());
   return on == 1;
 }
 static int un_for(int64_t M) { return M <= 64 ? 64 : (M <= 128 ? 128 : 256); }
@@ -1544,8 +1542,8 @@ static int by_un(const void* x, const Args& a, void* ws, size_t ws_bytes, cudaSt
     if (a.M <= 128) return launch_splitk<T, NBITS, GS, 128>(x, a, S, ws, ws_bytes, st);
     return launch_splitk<T, NBITS, GS, 256>(x, a, S, ws, ws_bytes, st);
   }
-  static int un_cap = -1;  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
-  if (un_cap < 0) { const char* e = getenv("HQQ_B200_GEMM_UN"); un_cap = e ? atoi(e) : 256; }
+  // HQQ_B200_GEMM_UN=128 (tuning knob): cap the token tile, e.g. to trade dequant work for wave efficiency
+  HQQ_ENV_KNOB(un_cap, ([] { const char* e = getenv("HQQ_B200_GEMM_UN"); return e ? atoi(e) : 256; })());
   if (a.M > 256 && gemm_variant() == 2) return launch_un512<T, NBITS, GS>(x, a, st);
   if (a.M > 256 && gemm_variant() == 3) return launch_ld512<T, NBITS, GS>(x, a, st);
   if (a.M <= 64 || un_cap <= 64) return launch<T, NBITS, GS, 64>(x, a, st);

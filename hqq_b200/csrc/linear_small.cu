@@ -1064,11 +1064,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------------------------------------
 static int magic_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("HQQ_B200_GEMV_MAGIC");
-    mode = (e && !strcmp(e, "subnormal")) ? MAGIC_SUBNORMAL : MAGIC_OFFSET;
-  }
+  HQQ_ENV_KNOB(mode, ([] { const char* e = getenv("HQQ_B200_GEMV_MAGIC"); return (e && !strcmp(e, "subnormal")) ? MAGIC_SUBNORMAL : MAGIC_OFFSET; })());
   return mode;
 }
 
@@ -1106,8 +1102,7 @@ static int grid_for_kernel(int* grid_out) {
 // tiles / (ceil(tiles/g) * g); ties go to the larger grid.
 static int balanced_grid(int tiles, int max_grid) {
   if (tiles <= max_grid) return tiles;
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("HQQ_B200_BALANCED_GRID"); mode = (e && e[0] == '1') ? 1 : 0; }
+  HQQ_ENV_KNOB(mode, ([] { const char* e = getenv("HQQ_B200_BALANCED_GRID"); return (e && e[0] == '1') ? 1 : 0; })());
   if (!mode) return max_grid;  // measured on B200: the kernel is bound per SM, so filling every CTA slot wins
   int best = max_grid;
   double best_eff = 0.0;
@@ -1120,11 +1115,7 @@ static int balanced_grid(int tiles, int max_grid) {
 }
 
 static bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("HQQ_B200_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
+  HQQ_ENV_KNOB(on, ([] { const char* e = getenv("HQQ_B200_PDL"); return (e && e[0] == '0') ? 0 : 1; })());
   return on == 1;
 }
 
@@ -1182,11 +1173,7 @@ static int launch_d1(SKArgs& a, cudaStream_t st) {
 }
 
 static bool d1_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("HQQ_B200_DECODE1");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
+  HQQ_ENV_KNOB(on, ([] { const char* e = getenv("HQQ_B200_DECODE1"); return (e && e[0] == '0') ? 0 : 1; })());
   return on == 1;
 }
 
@@ -1198,8 +1185,7 @@ static int sk_mt(SKArgs& a, cudaStream_t st) {
     // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 2042 = evict-first weight
     // stream, 3042 = both, 1033 = both with 3 stages and 3 CTAs per SM, 4042 = L2 prefetch under the dependency wait, 7042/7033 = all
     // (both experimental: written after round 1's GPU budget was spent, see D1Cfg)
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("HQQ_B200_D1_VARIANT"); variant = e ? atoi(e) : 0; }
+    HQQ_ENV_KNOB(variant, ([] { const char* e = getenv("HQQ_B200_D1_VARIANT"); return e ? atoi(e) : 0; })());
     if (variant == 32) return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
     if constexpr (GS == 64 && NBITS != 8) {
       if (variant == 1042 && a.K % 512 == 0) {

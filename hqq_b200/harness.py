@@ -381,6 +381,39 @@ class DecodeModel:
             step()
         return self.graph
 
+    # knobs that only select among bit-identical kernels / pure prefetch hints of the one-token path
+    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD")
+
+    def retune(self, knobs: dict | None = None, warmup: int = 2):
+        """Re-capture the decode graph under another choice of the TUNABLE knobs ({} = the default kernels).  The knobs select
+        among kernels that produce identical results (D1 variants) or add prefetch hints (WPF), so the token stream does not
+        change -- bench.py's autotuner checks exactly that before it keeps a choice."""
+        import os
+        from ._lib import load
+        knobs = dict(knobs or {})
+        unknown = set(knobs) - set(self.TUNABLE)
+        if unknown:
+            raise ValueError(f"retune: not a decode tuning knob: {sorted(unknown)}")
+        for k in self.TUNABLE:
+            os.environ.pop(k, None)
+        os.environ.update({k: str(v) for k, v in knobs.items()})
+        load().hqq_b200_reload_env()
+        self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
+        self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
+        self.graph = None
+        return self.capture(warmup=warmup)
+
+    def reset_state(self, token: int = 1):
+        """Position 0, empty KV caches, `token` as the first input: the state every token-stream comparison starts from."""
+        self.tok.fill_(token)
+        self.pos.zero_()
+        for blk in self.blocks:
+            blk["k_cache"].zero_()
+            blk["v_cache"].zero_()
+        if hasattr(self, "_bufs"):
+            for t in self._bufs.values():
+                t.zero_()
+
     def decode(self, feed_back: bool = True):
         """Replay one step; with feed_back the produced token becomes the next input (device-side copy)."""
         self.graph.replay()

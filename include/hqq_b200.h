@@ -225,6 +225,11 @@ int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, voi
 int64_t hqq_b200_launch_count(void);
 void hqq_b200_launch_count_reset(void);
 
+/* The HQQ_B200_* tuning knobs are parsed from the environment once and cached.  After changing them with setenv() call this
+ * to have the next launch parse them again (kernel selection only: results are identical across knobs; bench.py's decode
+ * autotuner and the tests use it to compare kernel variants inside one process).  Not thread-safe against concurrent launches. */
+void hqq_b200_reload_env(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -368,3 +368,18 @@ def test_emulated_gemm_pipelines_under_adversarial_timing(emu, tmp_path_factory,
         got = run_gemm_emu(tmp_path_factory, knob, async_seed=seed)
         for k in ref:
             assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), (k, seed)
+
+
+def test_emulated_reload_env_switches_cached_knobs_in_one_process(emu):
+    """`hqq_b200_reload_env()` (what DecodeModel.retune and bench.py's autotuner rely on): a changed HQQ_B200_* knob is ignored until
+    the reload, honoured after it, and the one-token kernel variants it selects stay bit-identical inside ONE process."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_reload.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RELOAD ")][-1][7:])
+    assert out["default_rc"] == 0
+    assert out["cached_rc"] == 0 and out["cached_same"]          # no reload: the cached choice stands
+    assert out["reloaded_rc"] == -2                              # HQQ_E_UNSUPPORTED once HQQ_B200_DECODE1=0 is seen
+    assert out["restored_rc"] == 0 and out["restored_same"]
+    for v in ("1042", "2042", "4042", "7042"):
+        assert out[f"variant_{v}"] == [0, True], v

@@ -1,0 +1,173 @@
+"""Host logic of the decode autotuner (hqq_b200/tune.py) without a GPU: the guard's bookkeeping over child processes that finish,
+crash, hang or run out of time is driven through its `run_child` seam, and the real child runner is exercised against a stand-in
+child script."""
+import json
+import os
+import sys
+import time
+
+import pytest
+
+from hqq_b200 import tune
+from hqq_b200.harness import DecodeModel
+
+CANDS = [{"HQQ_B200_D1_VARIANT": "1042"}, {"HQQ_B200_WPF_MB": "8"}, {"HQQ_B200_D1_VARIANT": "7042"}]
+
+
+def fake_child(script):
+    """script: knobs-label -> ("ok", us, digest) | ("crash",) | ("hang",); the default ("default") must be listed."""
+    calls = []
+
+    def run_child(cands, layers, first_line_s, per_line_s, deadline):
+        calls.append([tune.knob_label(c) for c in cands])
+        done = {}
+        for j, c in enumerate(cands):
+            what = script[tune.knob_label(c)]
+            if what[0] == "ok":
+                done[j] = {"i": j, "knobs": c, "us": what[1], "digest": what[2]}
+            elif what[0] == "crash":
+                return done, j, "child exited (code -6)"
+            else:
+                return done, j, "no progress for 20 s"
+        return done, None, None
+
+    run_child.calls = calls
+    return run_child
+
+
+def test_guard_all_candidates_finish():
+    rc = fake_child({"default": ("ok", 100.0, "aa"), "D1_VARIANT=1042": ("ok", 80.0, "aa"), "WPF_MB=8": ("ok", 125.0, "aa"),
+                     "D1_VARIANT=7042": ("ok", 50.0, "bb")})
+    out = tune.guard_decode(CANDS, run_child=rc)
+    assert len(rc.calls) == 1 and rc.calls[0][0] == "default"
+    assert out[0]["knobs"] == {} and out[0]["us"] == 100.0
+    assert out[1]["identical"] and out[1]["speedup"] == pytest.approx(1.25)
+    assert out[2]["identical"] and out[2]["speedup"] == pytest.approx(0.8)
+    assert out[3]["identical"] is False  # fast but different tokens: never a survivor
+
+
+def test_guard_drops_a_crashing_candidate_and_continues_in_a_new_child():
+    rc = fake_child({"default": ("ok", 100.0, "aa"), "D1_VARIANT=1042": ("crash",), "WPF_MB=8": ("ok", 90.0, "aa"),
+                     "D1_VARIANT=7042": ("hang",)})
+    out = tune.guard_decode(CANDS, run_child=rc)
+    assert rc.calls == [["default", "D1_VARIANT=1042", "WPF_MB=8", "D1_VARIANT=7042"], ["default", "WPF_MB=8", "D1_VARIANT=7042"]]
+    assert "exited" in out[1]["error"]
+    assert out[2]["identical"] and out[2]["speedup"] == pytest.approx(100.0 / 90.0)
+    assert "no progress" in out[3]["error"]
+
+
+def test_guard_stops_when_the_default_kernels_fail_in_the_child():
+    rc = fake_child({"default": ("crash",), "D1_VARIANT=1042": ("ok", 1.0, "aa"), "WPF_MB=8": ("ok", 1.0, "aa"), "D1_VARIANT=7042": ("ok", 1.0, "aa")})
+    out = tune.guard_decode(CANDS, run_child=rc)
+    assert len(rc.calls) == 1
+    assert all("error" in r for r in out)
+
+
+def test_guard_respects_its_time_budget():
+    def slow(cands, layers, first_line_s, per_line_s, deadline):
+        time.sleep(0.05)
+        return {0: {"i": 0, "knobs": {}, "us": 1.0, "digest": "aa"}}, 1, "time budget spent"
+
+    out = tune.guard_decode(CANDS, budget_s=0.01, run_child=slow)
+    assert out[0]["us"] == 1.0
+    assert all(r["error"] == "time budget spent" for r in out[1:])
+
+
+CHILD = r'''
+import json, sys, time, os
+cands = json.loads(sys.argv[sys.argv.index("--child") + 1])
+for i, c in enumerate(cands):
+    print("TRY " + json.dumps({"i": i}), flush=True)
+    v = c.get("HQQ_B200_D1_VARIANT")
+    if v == "1042":
+        os._exit(134)
+    if v == "7042":
+        time.sleep(60)
+    print("CAND " + json.dumps({"i": i, "knobs": c, "us": 10.0 + i, "digest": "aa"}), flush=True)
+print("DONE", flush=True)
+'''
+
+
+def test_real_child_runner_detects_exit_and_hang(tmp_path, monkeypatch):
+    """_run_child against a stand-in for `python -m hqq_b200.tune --child`: a fake package of the same name placed in a directory
+    the runner is pointed at."""
+    pkg = tmp_path / "hqq_b200"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "tune.py").write_text(CHILD)
+    monkeypatch.setattr(tune, "__file__", str(pkg / "tune.py"))
+    t0 = time.perf_counter()
+    done, running, why = tune._run_child([{}, {"HQQ_B200_WPF_MB": "8"}], 8, 30.0, 5.0, time.perf_counter() + 60)
+    assert why is None and running is None and sorted(done) == [0, 1]
+    done, running, why = tune._run_child([{}, {"HQQ_B200_D1_VARIANT": "1042"}, {"HQQ_B200_WPF_MB": "8"}], 8, 30.0, 5.0, time.perf_counter() + 60)
+    assert sorted(done) == [0] and running == 1 and "exited" in why
+    done, running, why = tune._run_child([{}, {"HQQ_B200_D1_VARIANT": "7042"}], 8, 30.0, 1.0, time.perf_counter() + 60)
+    assert sorted(done) == [0] and running == 1 and "no progress" in why
+    assert time.perf_counter() - t0 < 30
+
+
+def test_candidates_only_use_tunable_knobs():
+    for c in tune.DECODE_CANDIDATES:
+        assert set(c) <= set(DecodeModel.TUNABLE)
+    assert tune.knob_label({}) == "default"
+
+
+def test_autotune_is_off_when_a_knob_is_pinned_by_hand(monkeypatch):
+    for k in DecodeModel.TUNABLE + ("HQQ_B200_AUTOTUNE",):
+        monkeypatch.delenv(k, raising=False)
+    assert tune.autotune_enabled()
+    monkeypatch.setenv("HQQ_B200_WPF_MB", "16")
+    assert not tune.autotune_enabled()
+    monkeypatch.delenv("HQQ_B200_WPF_MB")
+    monkeypatch.setenv("HQQ_B200_AUTOTUNE", "0")
+    assert not tune.autotune_enabled()
+
+
+class FakeModel:
+    def __init__(self):
+        self.knobs, self.history = None, []
+
+    def retune(self, knobs=None, warmup=2):
+        self.knobs = dict(knobs or {})
+        self.history.append(tune.knob_label(self.knobs))
+
+
+def fake_measure(table):
+    import torch
+
+    def measure(model, steps=30, rounds=2, start_pos=20):
+        us, tok = table[tune.knob_label(model.knobs)]
+        return torch.full((tune.N_CHECK_TOKENS, 1), tok, dtype=torch.long), us
+
+    return measure
+
+
+GUARD = [{"knobs": {}, "us": 100.0, "digest": "aa"},
+         {"knobs": {"HQQ_B200_D1_VARIANT": "1042"}, "us": 90.0, "digest": "aa", "identical": True, "speedup": 1.11},
+         {"knobs": {"HQQ_B200_WPF_MB": "8"}, "us": 70.0, "digest": "aa", "identical": True, "speedup": 1.43},
+         {"knobs": {"HQQ_B200_D1_VARIANT": "7042"}, "us": 50.0, "digest": "bb", "identical": False, "speedup": 2.0},
+         {"knobs": {"HQQ_B200_D1_VARIANT": "2042"}, "us": 120.0, "digest": "aa", "identical": True, "speedup": 0.83},
+         {"knobs": {"HQQ_B200_D1_VARIANT": "4042"}, "error": "child exited (code -11)"}]
+
+
+def test_choose_keeps_the_fastest_identical_candidate():
+    m = FakeModel()
+    rep = tune.choose_decode(m, GUARD, measure_fn=fake_measure({"default": (400.0, 5), "WPF_MB=8": (300.0, 5), "D1_VARIANT=1042": (350.0, 5)}))
+    assert rep["selected"] == {"HQQ_B200_WPF_MB": "8"} and m.knobs == rep["selected"]
+    assert rep["gain"] == pytest.approx(400.0 / 300.0)
+    # only guard survivors that were identical AND faster are ever captured in this process, best first
+    assert m.history == ["default", "WPF_MB=8", "D1_VARIANT=1042", "WPF_MB=8"]
+
+
+def test_choose_rejects_a_candidate_whose_tokens_differ_on_the_real_model():
+    m = FakeModel()
+    rep = tune.choose_decode(m, GUARD, measure_fn=fake_measure({"default": (400.0, 5), "WPF_MB=8": (100.0, 6), "D1_VARIANT=1042": (399.0, 5)}))
+    assert rep["selected"] == {} and m.knobs == {}  # WPF_MB=8: wrong tokens; 1042: inside the noise margin
+    assert rep["gain"] == 1.0
+    assert [t["identical"] for t in rep["tried"]] == [False, True]
+
+
+def test_choose_with_nothing_to_try_leaves_the_default_captured():
+    m = FakeModel()
+    rep = tune.choose_decode(m, [GUARD[0], GUARD[3], GUARD[5]], measure_fn=fake_measure({"default": (400.0, 5)}))
+    assert rep["selected"] == {} and rep["tried"] == [] and m.history == ["default", "default"]

@@ -191,3 +191,18 @@ def test_fused_3bit_one_token_kernel(dt):
             os.environ.pop("HQQ_B200_FUSED_3BIT", None)
         assert torch.equal(a, b), (N, K)
         assert (a.float() - ref).norm() <= tol * ref.norm(), (N, K, float((a.float() - ref).norm() / ref.norm()))
+
+
+def test_autotuner_end_to_end_on_a_small_model():
+    """tune.guard_decode (child processes) + tune.choose_decode on a 2-block Llama-3-8B-shaped model: whatever it selects decodes
+    the default kernels' tokens."""
+    from hqq_b200 import harness, tune
+    guard = tune.guard_decode(layers=2, budget_s=150.0)
+    assert "us" in guard[0], guard[0]
+    m = harness.DecodeModel(harness.LLAMA3_8B, dtype=torch.float16, device=torch.device("cuda", 0), cache_len=128, n_layers=2)
+    m.capture()
+    ref, _ = tune.measure(m, steps=10)
+    rep = tune.choose_decode(m, guard, steps=20)
+    got, _ = tune.measure(m, steps=10)
+    assert torch.equal(ref, got), rep
+    m.retune({})
