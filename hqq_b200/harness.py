@@ -80,6 +80,7 @@ class DecodeModel:
         # cross-launch weight prefetch into L2 (MiB per launch, how many following linear launches it may cover); 0 = off
         self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
         self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
+        self.wpf_from = parse_wpf_from(os.environ.get("HQQ_B200_WPF_FROM", ""))
         self.nbits = nbits
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -326,10 +327,12 @@ class DecodeModel:
     def _wpf(self, bi, stage):
         """Weight prefetch spans for the launches that FOLLOW launch `stage` of block `bi` (hqq_b200_decode_desc::pf_*): the packed
         weights of the next `wpf_ahead` linear launches, at most `wpf_mb` MiB and four spans, wrapping into the next block.
-        Off unless HQQ_B200_WPF_MB > 0 (experimental: not yet timed on a GPU)."""
-        if self.wpf_mb <= 0:
+        Off unless HQQ_B200_WPF_MB > 0 (experimental: not yet timed on a GPU).  A launch issues its prefetch in its prologue, i.e.
+        while its PREDECESSOR runs: "o" prefetches under the attention kernel (HBM idle), "gu" under the short o launch, "qkv" and
+        "down" under the big down / gate+up launches (HBM busy) -- HQQ_B200_WPF_FROM=o,gu restricts the issuing launches."""
+        if self.wpf_mb <= 0 or stage not in self.wpf_from:
             return None
-        order = ("qkv", "o", "gu", "down")
+        order = WPF_STAGES
         groups = {"qkv": ("q", "k", "v"), "o": ("o",), "gu": ("gate", "up"), "down": ("down",)}
         i, blk, seq = order.index(stage), bi, []
         for _ in range(self.wpf_ahead):
@@ -382,7 +385,7 @@ class DecodeModel:
         return self.graph
 
     # knobs that only select among bit-identical kernels / pure prefetch hints of the one-token path
-    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD")
+    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD", "HQQ_B200_WPF_FROM")
 
     def retune(self, knobs: dict | None = None, warmup: int = 2):
         """Re-capture the decode graph under another choice of the TUNABLE knobs ({} = the default kernels).  The knobs select
@@ -400,6 +403,7 @@ class DecodeModel:
         load().hqq_b200_reload_env()
         self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
         self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
+        self.wpf_from = parse_wpf_from(os.environ.get("HQQ_B200_WPF_FROM", ""))
         self.graph = None
         return self.capture(warmup=warmup)
 
@@ -419,6 +423,18 @@ class DecodeModel:
         self.graph.replay()
         if feed_back:
             self.tok.copy_(self.next_tok)
+
+
+WPF_STAGES = ("qkv", "o", "gu", "down")  # the four linear launches of a block, in order
+
+
+def parse_wpf_from(text: str):
+    """HQQ_B200_WPF_FROM: comma-separated subset of WPF_STAGES naming the launches that issue weight prefetches ('' = all)."""
+    names = [t.strip() for t in text.split(",") if t.strip()]
+    bad = [n for n in names if n not in WPF_STAGES]
+    if bad:
+        raise ValueError(f"HQQ_B200_WPF_FROM: unknown launch {bad}; choose from {WPF_STAGES}")
+    return frozenset(names) if names else frozenset(WPF_STAGES)
 
 
 def wpf_spans(tensors, budget_bytes: int, max_spans: int = 4):

@@ -32,13 +32,20 @@ DECODE_CANDIDATES = [
     {"HQQ_B200_D1_VARIANT": "2042"},
     {"HQQ_B200_D1_VARIANT": "4042"},
     {"HQQ_B200_D1_VARIANT": "7042"},
+    # weight prefetch from every linear launch (each covers the next launch / the next two)
     {"HQQ_B200_WPF_MB": "8"},
     {"HQQ_B200_WPF_MB": "24"},
     {"HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_AHEAD": "1"},
     {"HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_AHEAD": "2"},
+    # only from the launches whose prologue runs while HBM idles: o (under attention) pulls gate/up, gate/up (under o) pulls down
+    {"HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o"},
+    {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o"},
+    {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o,gu"},
+    {"HQQ_B200_WPF_MB": "88", "HQQ_B200_WPF_AHEAD": "2", "HQQ_B200_WPF_FROM": "o"},
+    # prefetch on top of the kernel variants
     {"HQQ_B200_D1_VARIANT": "1042", "HQQ_B200_WPF_MB": "24"},
     {"HQQ_B200_D1_VARIANT": "7042", "HQQ_B200_WPF_MB": "24"},
-    {"HQQ_B200_D1_VARIANT": "7042", "HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_AHEAD": "1"},
+    {"HQQ_B200_D1_VARIANT": "7042", "HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o,gu"},
 ]
 
 N_CHECK_TOKENS = 16

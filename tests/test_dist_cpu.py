@@ -133,7 +133,7 @@ def test_weight_prefetch_spans_follow_the_launch_order():
 
     m = harness.DecodeModel.__new__(harness.DecodeModel)
     m.blocks = [{k: L(s) for k, s in (("q", 1024), ("k", 256), ("v", 256), ("o", 1024), ("gate", 4096), ("up", 4096), ("down", 4096))} for _ in range(2)]
-    m.wpf_mb, m.wpf_ahead = 0.0, 1
+    m.wpf_mb, m.wpf_ahead, m.wpf_from = 0.0, 1, harness.parse_wpf_from("")
     assert m._wpf(0, "qkv") is None  # off by default
     m.wpf_mb = 1.0
     ptr = lambda b, n: m.blocks[b][n].W_q.data_ptr()  # noqa: E731
@@ -145,3 +145,9 @@ def test_weight_prefetch_spans_follow_the_launch_order():
     assert m._wpf(0, "qkv") == [(ptr(0, "o"), 1024), (ptr(0, "gate"), 4096), (ptr(0, "up"), 4096)]
     m.wpf_mb = 5000 / (1 << 20)
     assert m._wpf(0, "o") == [(ptr(0, "gate"), 4096), (ptr(0, "up"), 896)]  # budget cut to whole lines
+    m.wpf_from = harness.parse_wpf_from("o, gu")  # only the launches whose prologue runs while HBM idles issue prefetches
+    assert m._wpf(0, "qkv") is None and m._wpf(0, "down") is None
+    assert m._wpf(0, "o") is not None and m._wpf(0, "gu") is not None
+    assert harness.parse_wpf_from("") == frozenset(harness.WPF_STAGES)
+    with pytest.raises(ValueError):
+        harness.parse_wpf_from("o,attention")
