@@ -318,7 +318,7 @@ def _finite(o):
     return o
 
 
-def run_probes(budget_s=110.0, timeout_s=45.0):
+def run_probes(budget_s=130.0, timeout_s=45.0):
     """First GPU execution of the kernels written after round 1's GPU budget was spent: each knob runs
     tools/variant_probe.py in its OWN process under a timeout -- a crash or a hang there cannot reach this process -- on a fixed
     seeded workload, and is compared with the default kernels (sha256 of the outputs, relative error where the summation order
@@ -330,7 +330,7 @@ def run_probes(budget_s=110.0, timeout_s=45.0):
     t_start = time.perf_counter()
     base_env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
 
-    def run(what, knob=None, both=None, save=None):
+    def run(what, knob=None, both=None, save=None, timeout_s=timeout_s):
         if time.perf_counter() - t_start > budget_s:
             return {"skipped": "probe time budget spent"}
         env = dict(base_env)
@@ -370,7 +370,8 @@ def run_probes(budget_s=110.0, timeout_s=45.0):
             out[f"{key}={val}"] = got
         return out
 
-    res = {"solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
+    res = {"gemm_sweep": run("gemm_sweep", timeout_s=80.0),
+           "solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
            "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
            "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
            "gemm_mid": against_default("gemm_mid", [("HQQ_B200_GEMM_SPLITK", "1")])}
@@ -518,6 +519,22 @@ def run_gpu(args, rank, world, local_rank):
                 line["experimental"] = run_probes()
             except Exception as e:  # noqa: BLE001
                 line["experimental"] = {"error": repr(e)[:200]}
+        sweep = (line.get("experimental") or {}).pop("gemm_sweep", None)
+        if isinstance(sweep, dict) and "per" in sweep:
+            # BASELINE configs[2] / metric (2): fused dequant-GEMM TFLOP/s against the measured dense bf16/fp16 tensor peak
+            peak_tf = None
+            try:
+                peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:  # noqa: BLE001
+                peak_tf = 2250.0
+            for e in sweep["per"].values():
+                e["frac_of_tensor_peak"] = round(e["TFLOPs"] / peak_tf, 4)
+            line["gemm_sweep"] = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "headline": "b4_4096x4096_M4096",
+                                  "achieved": sweep["per"]["b4_4096x4096_M4096"]["TFLOPs"],
+                                  "frac": sweep["per"]["b4_4096x4096_M4096"]["frac_of_tensor_peak"], "per": sweep["per"],
+                                  "note": "default kernels, event-timed alone (burst peak); route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit)"}
+        elif sweep is not None:
+            line["gemm_sweep"] = sweep
         if world == 1 and not big and B == 1:
             try:  # extra object, never allowed to cost the bench line
                 sf = (line.get("experimental") or {}).get("solver_fast") or {}

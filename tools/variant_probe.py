@@ -148,7 +148,43 @@ def probe_decode():
     return {"us": e0.elapsed_time(e1) * 1e3 / 30, "digest": digest(outs), "layers": 8}, outs
 
 
-PROBES = {"quant": probe_quant, "l3": probe_l3, "gemm": probe_gemm, "gemm_mid": probe_gemm_mid, "decode": probe_decode}
+def probe_gemm_sweep():
+    """BASELINE configs[2]: per-linear dequant-GEMM over (4096x4096, 11008x4096, 4096x11008) x nbits {8,4,3,2,1}, gs 64, fp16, at
+    M = 4096 (tensor leg) and M = 128, default kernels.  `route` 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM
+    (3-bit).  TFLOP/s = 2 M N K / time; `cublas_dequantised` times the library GEMM alone on the pre-dequantised fp16 matrix."""
+    torch.manual_seed(0)
+    per, outs = {}, []
+    for nbits in (8, 4, 3, 2, 1):
+        cfg = BaseQuantizeConfig(nbits=nbits, group_size=64, axis=1)
+        for N, K in ((4096, 4096), (11008, 4096), (4096, 11008)):
+            lin = HQQLinear.from_weights((torch.randn(N, K, device=DEV) * 0.02).half(), None, cfg, compute_dtype=torch.float16, device=DEV)
+            Wd = lin.dequantize()
+            for M in (4096, 128):
+                x = torch.randn(M, K, device=DEV).half()
+                y = torch.empty(M, N, device=DEV, dtype=torch.float16)
+                route = ops.linear_route(M, N, K, 64, nbits, 1, torch.float16)
+
+                def run():
+                    if route != 0:
+                        return ops.linear_fwd(x, lin.W_q, lin.meta["scale"], lin.meta["zero"], None, N, K, 64, nbits, 1, out=y)
+                    with torch.no_grad():
+                        return lin(x)
+
+                r = run()
+                torch.cuda.synchronize()
+                ref = torch.matmul(x, Wd.t())
+                err = float((r.float() - ref.float()).norm() / ref.float().norm())
+                us = timed(run, 10)
+                e = {"us": round(us, 1), "TFLOPs": round(2.0 * M * N * K / us / 1e6, 1), "route": route, "rel_err_vs_dequant_matmul": err}
+                if M == 4096:
+                    e["cublas_dequantised_TFLOPs"] = round(2.0 * M * N * K / timed(lambda: torch.matmul(x, Wd.t(), out=y), 10) / 1e6, 1)
+                per[f"b{nbits}_{N}x{K}_M{M}"] = e
+            del lin, Wd
+    head = per["b4_4096x4096_M4096"]
+    return {"us": head["us"], "per": per, "digest": "n/a"}, outs
+
+
+PROBES = {"gemm_sweep": probe_gemm_sweep, "quant": probe_quant, "l3": probe_l3, "gemm": probe_gemm, "gemm_mid": probe_gemm_mid, "decode": probe_decode}
 
 
 def compare(ref, got):
