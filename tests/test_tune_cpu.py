@@ -171,3 +171,50 @@ def test_choose_with_nothing_to_try_leaves_the_default_captured():
     m = FakeModel()
     rep = tune.choose_decode(m, [GUARD[0], GUARD[3], GUARD[5]], measure_fn=fake_measure({"default": (400.0, 5)}))
     assert rep["selected"] == {} and rep["tried"] == [] and m.history == ["default", "default"]
+
+
+def _fake_run(script):
+    """subprocess.run stand-in for bench.supervise: `script` is a list of outcomes, one per worker launch."""
+    import subprocess
+    calls = []
+
+    def run(cmd, stdout=None, text=None, timeout=None):
+        calls.append(cmd)
+        what = script[len(calls) - 1]
+        if what == "timeout":
+            raise subprocess.TimeoutExpired(cmd, timeout)
+        code, out = what
+        return subprocess.CompletedProcess(cmd, code, stdout=out)
+
+    run.calls = calls
+    return run
+
+
+LINE = json.dumps({"metric": "m", "value": 1.0, "config": {"autotune": {"selected": "WPF_MB=8"}}})
+
+
+def test_bench_supervisor_passes_the_worker_line_through(monkeypatch, capsys):
+    import bench
+    run = _fake_run([(0, "noise\n" + LINE + "\n")])
+    monkeypatch.setattr(bench.subprocess, "run", run)
+    assert bench.supervise(["--steps", "5"]) == 0
+    assert capsys.readouterr().out.strip() == LINE
+    assert run.calls[0][-1] == "--worker" and "--steps" in run.calls[0]
+
+
+@pytest.mark.parametrize("first", [(-11, ""), (1, "Traceback ...\n"), "timeout"])
+def test_bench_supervisor_measures_again_with_default_kernels_when_the_tuned_worker_fails(monkeypatch, capsys, first):
+    import bench
+    run = _fake_run([first, (0, LINE + "\n")])
+    monkeypatch.setattr(bench.subprocess, "run", run)
+    assert bench.supervise([]) == 0
+    d = json.loads(capsys.readouterr().out.strip())
+    assert d["value"] == 1.0 and "measured again with the default kernels" in d["config"]["autotune"]["error"]
+    assert run.calls[1][-2:] == ["--worker", "--no-autotune"]
+
+
+def test_bench_supervisor_reports_failure_when_both_workers_fail(monkeypatch, capsys):
+    import bench
+    monkeypatch.setattr(bench.subprocess, "run", _fake_run([(1, ""), (1, "")]))
+    assert bench.supervise([]) == 1
+    assert capsys.readouterr().out.strip() == ""
