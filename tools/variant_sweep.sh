@@ -14,6 +14,11 @@ for mb in 4 8 16 32 48 64; do
   echo -n "WPF_MB=$mb: "; HQQ_B200_WPF_MB=$mb timeout 120 python tools/step_time.py 2>&1 | tail -1
   echo -n "WPF_MB=$mb + D1 7042: "; HQQ_B200_WPF_MB=$mb HQQ_B200_D1_VARIANT=7042 timeout 120 python tools/step_time.py 2>&1 | tail -1
 done
+echo "== weight prefetch only from the launches whose prologue runs while HBM idles (o: under attention, gu: under o)"
+for cfg in "48 1 o" "64 1 o" "64 1 o,gu" "88 2 o" "64 1 o,gu,qkv"; do
+  set -- $cfg
+  echo -n "WPF_MB=$1 AHEAD=$2 FROM=$3: "; HQQ_B200_WPF_MB=$1 HQQ_B200_WPF_AHEAD=$2 HQQ_B200_WPF_FROM=$3 timeout 120 python tools/step_time.py 2>&1 | tail -1
+done
 echo "== quantizer: default vs fast solver (HQQ_B200_SOLVER_VARIANT=1), Llama-3-8B and 70B layer shapes"
 timeout 200 python tools/prof_quantize.py 8b 4
 HQQ_B200_SOLVER_VARIANT=1 timeout 200 python tools/prof_quantize.py 8b 4,2
@@ -34,3 +39,5 @@ HQQ_B200_GEMM_SPLITK=1 timeout 200 python tools/prof_gemm.py 64,128,256,512 4 2>
 } 2>&1 | tee gpurun_out/variant_sweep.log
 # BASELINE configs[2]: the per-linear sweep (M x nbits x 3 shapes), kept under profiles/ afterwards
 timeout 900 python tools/prof_gemm.py 1,16,32,128,1024,4096 8,4,3,2,1 > gpurun_out/gemm_sweep.log 2>&1; grep -c fused gpurun_out/gemm_sweep.log
+# the bench with its decode autotuner (child-process guard + in-process choice): config.autotune lists every candidate's verdict
+timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_autotune.json 2> gpurun_out/bench_autotune.err; head -c 1500 gpurun_out/bench_autotune.json; echo
