@@ -178,7 +178,9 @@ def proximal_step(W_f, scale, zero, min_max, beta, lp_norm, axis):
     W_q = np.clip(np.round(W_f * scale + zero), f32(min_max[0]), f32(min_max[1])).astype(f32)
     W_r = ((W_q - zero) / scale).astype(f32)
     W_e = shrink_lp_op(W_f - W_r, beta, lp_norm)
-    zero = np.mean(W_q - (W_f - W_e) * scale, axis=axis, keepdims=True, dtype=f32)
+    # group mean: float64 accumulation rounded once -- on the golden fixtures this reproduces torch.mean (float32, vectorised
+    # partial sums) level for level, where a float32 pairwise sum flips 2 of 393 216 levels
+    zero = np.mean((W_q - (W_f - W_e) * scale).astype(f32), axis=axis, keepdims=True, dtype=np.float64)
     return W_r, W_q, zero.astype(f32)
 
 

@@ -69,7 +69,7 @@ def fast_trajectory(W, s, z, maxv, beta, p, iters, groups_per_warp=4):
             if not (ad.max() < thr):   # warp-uniform fallback to the full formula
                 _, _, znew = O.proximal_step(Ww, sw, zw, [0, maxv], beta, p, 1)
             else:
-                znew = np.mean(q - ws, axis=1, keepdims=True, dtype=f32).astype(f32)
+                znew = np.mean((q - ws).astype(f32), axis=1, keepdims=True, dtype=np.float64).astype(f32)  # the oracle's group mean
             e_last = ad.sum(axis=1, dtype=f32)
             errs[it, sl] = e_last
             hist[it + 1, sl] = znew[:, 0]
