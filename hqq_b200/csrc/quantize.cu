@@ -67,6 +67,18 @@ __device__ __forceinline__ void init_group(float mn, float mx, int maxv, int rou
   st.z = z;
 }
 
+// Group mean of the zero-point terms: float64 accumulation (the terms are float32 values of magnitude <= 2^nbits, so the sum of a
+// group is exact or within one float64 ulp), rounded to float32 once -- torch.mean's result on the reference's CPU path
+// (vectorised float32 partial sums) equals this level for level on every golden fixture, where a float32 shuffle tree lands one
+// ulp away in about half of the groups and flips a rounding tie now and then.  The order of the float64 additions is fixed
+// (lane-local sequence, then xor-shuffle tree), so results stay deterministic and identical across the solver variants.
+__device__ __forceinline__ float zero_mean(double zs, int gs) {
+  // sum / n: for a power-of-two n the product with 1/n is exact (no double division; n is a compile-time constant on the
+  // register-resident paths), otherwise the float64 quotient, rounded to float32 once either way
+  if ((gs & (gs - 1)) == 0) return (float)(zs * (1.0 / (double)gs));
+  return (float)(zs / (double)gs);
+}
+
 // One solver update for one element; returns its contribution to the zero-point sum.
 __device__ __forceinline__ float solver_elem(float w, const GroupState& st, float fmaxv, float inv_beta, float pm1,
                                              int lp_is_one, float& errsum) {
@@ -183,12 +195,13 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis1_kernel(SolverArgs
     else init_group(mn, mx, a.maxv, a.round_zero, st);
     if (valid && l == 0) { a.s_inv[g] = st.s; a.hist[g] = st.z; }
     for (int it = 0; it < a.iters; ++it) {
-      float errsum = 0.0f, zs = 0.0f;
+      float errsum = 0.0f;
+      double zs = 0.0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
+      for (int j = 0; j < 8; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
 #pragma unroll
       for (int o = 1; o < L; o <<= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
-      st.z = __fdiv_rn(zs, (float)a.gs);  // torch.mean = sum / n
+      st.z = zero_mean(zs, 8 * L);  // torch.mean = sum / n (gs = 8 L on this path)
       if (valid && l == 0) a.hist[(long long)(it + 1) * a.G + g] = st.z;
       acc.add(it, valid ? errsum : 0.0f);
     }
@@ -249,7 +262,8 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis1_fast_kernel(Solve
     float ew = 0.0f;  // warp-wide error sum of the last iteration executed
     int it = 0;
     while (it < a.iters) {
-      float errsum = 0.0f, zs = 0.0f, amax = 0.0f;
+      float errsum = 0.0f, amax = 0.0f;
+      double zs = 0.0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float q = rint_magic(__fadd_rn(ws[j], st.z));
@@ -258,18 +272,17 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis1_fast_kernel(Solve
         const float ad = fabsf(__fsub_rn(w[j], wr));
         errsum += ad;
         amax = fmaxf(amax, ad);
-        zs += __fsub_rn(q, ws[j]);
+        zs += (double)__fsub_rn(q, ws[j]);
       }
       if (__any_sync(0xffffffffu, !(amax < thr))) {  // some |W - W_r| may survive the shrinkage: full formula for the warp
-        zs = 0.0f;
+        zs = 0.0;
         float unused = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
+        for (int j = 0; j < 8; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
       }
 #pragma unroll
       for (int o = 1; o < L; o <<= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
-      // torch.mean = sum / n; n = 8L is a power of two, so the correctly rounded product with 1/n IS the correctly rounded quotient
-      const float znew = __fmul_rn(zs, 1.0f / (float)(8 * L));
+      const float znew = zero_mean(zs, 8 * L);  // torch.mean = sum / n, exactly as solver_axis1_kernel
       if (valid && l == 0) a.hist[(long long)(it + 1) * a.G + g] = znew;
       ew = valid ? errsum : 0.0f;
 #pragma unroll
@@ -317,10 +330,11 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis0_kernel(SolverArgs
     else init_group(mn, mx, a.maxv, a.round_zero, st);
     if (valid) { a.s_inv[g] = st.s; a.hist[g] = st.z; }
     for (int it = 0; it < a.iters; ++it) {
-      float errsum = 0.0f, zs = 0.0f;
+      float errsum = 0.0f;
+      double zs = 0.0;
 #pragma unroll
-      for (int j = 0; j < GS; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
-      st.z = __fdiv_rn(zs, (float)GS);
+      for (int j = 0; j < GS; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
+      st.z = zero_mean(zs, GS);
       if (valid) a.hist[(long long)(it + 1) * a.G + g] = st.z;
       acc.add(it, valid ? errsum : 0.0f);
     }
@@ -359,7 +373,8 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis0_fast_kernel(Solve
     float ew = 0.0f;
     int it = 0;
     while (it < a.iters) {
-      float errsum = 0.0f, zs = 0.0f, amax = 0.0f;
+      float errsum = 0.0f, amax = 0.0f;
+      double zs = 0.0;
 #pragma unroll
       for (int j = 0; j < GS; ++j) {
         const float ws = __fmul_rn(w[j], st.s);
@@ -369,15 +384,15 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis0_fast_kernel(Solve
         const float ad = fabsf(__fsub_rn(w[j], wr));
         errsum += ad;
         amax = fmaxf(amax, ad);
-        zs += __fsub_rn(q, ws);
+        zs += (double)__fsub_rn(q, ws);
       }
       if (__any_sync(0xffffffffu, !(amax < thr))) {
-        zs = 0.0f;
+        zs = 0.0;
         float unused = 0.0f;
 #pragma unroll
-        for (int j = 0; j < GS; ++j) zs += solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
+        for (int j = 0; j < GS; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
       }
-      const float znew = __fmul_rn(zs, 1.0f / (float)GS);  // GS is a power of two: identical to the division
+      const float znew = zero_mean(zs, GS);
       if (valid) a.hist[(long long)(it + 1) * a.G + g] = znew;
       ew = valid ? errsum : 0.0f;
 #pragma unroll
@@ -427,14 +442,15 @@ __global__ void __launch_bounds__(kSolverThreads) solver_generic_kernel(SolverAr
     else init_group(mn, mx, a.maxv, a.round_zero, st);
     if (lane == 0) { a.s_inv[g] = st.s; a.hist[g] = st.z; }
     for (int it = 0; it < a.iters; ++it) {
-      float errsum = 0.0f, zs = 0.0f;
+      float errsum = 0.0f;
+      double zs = 0.0;
       for (int e = lane; e < a.gs; e += 32) {
         float w = to_f32<TIn>(base[(long long)e * estride]);
-        zs += solver_elem(w, st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
+        zs += (double)solver_elem(w, st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, errsum);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
-      st.z = __fdiv_rn(zs, (float)a.gs);
+      st.z = zero_mean(zs, a.gs);
       if (lane == 0) a.hist[(long long)(it + 1) * a.G + g] = st.z;
       acc.add(it, errsum);
     }

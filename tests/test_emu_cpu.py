@@ -104,8 +104,32 @@ def test_emulated_default_solver_matches_the_oracle(emu, oracle, nbits, gs, shap
     ref_q = oracle.UNPACK[ref_meta["packing"]](ref_Wq)[: W.size // gs]
     got_q = oracle.UNPACK[ref_meta["packing"]](Wq)[: W.size // gs]
     assert np.array_equal(s, ref_meta["scale"].ravel())
-    assert np.mean(got_q != ref_q) <= 2e-3 and np.abs(got_q.astype(int) - ref_q.astype(int)).max() <= 1
-    assert np.allclose(z, ref_meta["zero"].ravel(), rtol=0, atol=2.0 / gs + 1e-5)
+    # float64 zero-point sums in the kernel and in the oracle: identical levels, zero-points equal to the last bit (the residual
+    # arithmetic differences -- (W_q - z) * (1/s) for the division, ex2/lg2 for pow -- only touch the error sums and W_e != 0)
+    assert np.array_equal(got_q, ref_q)
+    assert np.allclose(z, ref_meta["zero"].ravel(), rtol=0, atol=1e-6 * max(1.0, float(np.abs(z).max())))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emulated_solver_reproduces_every_level_of_the_reference_fixtures(emu, oracle, golden, variant):
+    """The solver kernels' own source on the emulator against the fixtures the REAL reference produced (tests/golden): identical
+    iteration counts and identical levels on all 14 configurations (both axes, five widths, three group sizes), for the default
+    and the fast solver.  (Before the zero-point means were accumulated in float64 the kernels differed in 2 of 393 216 levels.)"""
+    q = golden.quant
+    for nbits in (8, 4, 3, 2, 1):
+        for axis in (0, 1):
+            for gs in ((64,) if nbits != 4 else (64, 32, 128)):
+                if variant == 1 and (nbits, axis, gs) not in ((4, 1, 64), (4, 0, 64), (3, 1, 64), (8, 0, 64), (4, 1, 128)):
+                    continue  # the fast solver is bit-identical to the default one (separate test): a subset keeps the suite short
+                key = f"b{nbits}_a{axis}_g{gs}"
+                Wq, s, z, info, err, _ = quantize(emu, q["W"], F32, nbits, gs, variant, axis=axis)
+                pk = oracle.BIT_TO_PACKING[nbits]
+                rows = q["W"].size // gs if axis == 1 else gs
+                assert int(info[0]) == int(q[key + "/iters"]), key
+                assert np.array_equal(oracle.UNPACK[pk](Wq)[:rows], oracle.UNPACK[pk](q[key + "/W_q"])[:rows]), key
+                assert np.array_equal(s, q[key + "/scale"].ravel()), key
+                zr = q[key + "/zero"].ravel()
+                assert np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1.0)) <= 1e-6, key
 
 
 CASES = [(4, 64, (32, 256), 0.02, F16), (4, 64, (30, 128), 1.0, F16),   # std 1.0: |W - W_r| above the threshold, the fallback runs
