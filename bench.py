@@ -371,6 +371,7 @@ def run_probes(budget_s=130.0, timeout_s=45.0):
         return out
 
     res = {"gemm_sweep": run("gemm_sweep", timeout_s=80.0),
+           "bitpack": run("bitpack"),
            "solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
            "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
            "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
@@ -557,6 +558,16 @@ def run_gpu(args, rank, world, local_rank):
                                   "note": "default kernels, event-timed alone (burst peak); route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit)"}
         elif sweep is not None:
             line["gemm_sweep"] = sweep
+        bp = (line.get("experimental") or {}).pop("bitpack", None)
+        if isinstance(bp, dict) and "per" in bp:
+            # pack / unpack / dequantize against the measured HBM peak (default kernels, own process)
+            for e in bp["per"].values():
+                e["frac_of_hbm_peak"] = round(e["GBps"] / peaks["hbm_gbs"], 4)
+            line["bitpack"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "headline": "b4_dequantize_f16",
+                               "achieved": bp["per"]["b4_dequantize_f16"]["GBps"], "frac": bp["per"]["b4_dequantize_f16"]["frac_of_hbm_peak"],
+                               "per": bp["per"], "note": "one 14336x4096 matrix per call, inputs cycled (cold L2), algorithmic bytes = input + output"}
+        elif bp is not None:
+            line["bitpack"] = bp
         if world == 1 and not big and B == 1:
             try:  # extra object, never allowed to cost the bench line
                 sf = (line.get("experimental") or {}).get("solver_fast") or {}

@@ -184,7 +184,54 @@ def probe_gemm_sweep():
     return {"us": head["us"], "per": per, "digest": "n/a"}, outs
 
 
-PROBES = {"gemm_sweep": probe_gemm_sweep, "quant": probe_quant, "l3": probe_l3, "gemm": probe_gemm, "gemm_mid": probe_gemm_mid, "decode": probe_decode}
+def probe_bitpack():
+    """pack / unpack / dequantize are HBM-bound streaming kernels.  One 14336 x 4096 matrix (58.7 M weights, gs 64, axis 1)
+    per call through the C ABI with preallocated outputs, cycling over four input copies so that no call finds its input in the
+    126 MB L2; algorithmic bytes = input + output (+ scale/zero) per call; event-timed over 24 back-to-back launches."""
+    from hqq_b200._lib import DTYPE_CODE, check, load, ptr, stream_ptr
+    lib, st = load(), stream_ptr(DEV)
+    N, K, gs = 14336, 4096, 64
+    R = N * K // gs
+    g = torch.Generator(device=DEV)
+    g.manual_seed(9)
+    per, outs = {}, []
+    for nbits in (4, 2, 8, 3, 1):
+        f = 10 if nbits == 3 else 8 // nbits
+        prow = -(-R // 10) if nbits == 3 else R // f
+        levels = [torch.randint(0, 2 ** nbits, (R, gs), device=DEV, dtype=torch.uint8, generator=g) for _ in range(4)]
+        packed = [torch.empty((prow, gs), device=DEV, dtype=torch.int32 if nbits == 3 else torch.uint8) for _ in range(4)]
+        scale = (torch.rand(R, device=DEV, generator=g) * 0.01 + 1e-3).half()
+        zero = (torch.rand(R, device=DEV, generator=g) * (2 ** nbits - 1)).half()
+        unp = torch.empty((prow * f, gs), device=DEV, dtype=torch.uint8)
+        deq = torch.empty((N, K), device=DEV, dtype=torch.float16)
+        i = [0]
+
+        def do_pack():
+            j = i[0] = (i[0] + 1) % 4
+            check(lib.hqq_b200_pack(nbits, ptr(levels[j]), DTYPE_CODE[torch.uint8], ptr(packed[j]), R, gs, st))
+
+        def do_unpack():
+            j = i[0] = (i[0] + 1) % 4
+            check(lib.hqq_b200_unpack(nbits, ptr(packed[j]), ptr(unp), DTYPE_CODE[torch.uint8], prow, gs, st))
+
+        def do_deq():
+            j = i[0] = (i[0] + 1) % 4
+            check(lib.hqq_b200_dequantize(ptr(packed[j]), ptr(scale), ptr(zero), ptr(deq), N, K, gs, nbits, 1, DTYPE_CODE[torch.float16], st))
+
+        for _ in range(4):
+            do_pack()
+        torch.cuda.synchronize()
+        assert torch.equal(ops.unpack(packed[0], nbits)[:R], levels[0])  # round trip through the public ops
+        pbytes = packed[0].numel() * packed[0].element_size()
+        for name, fn, nbytes in (("pack", do_pack, R * gs + pbytes), ("unpack", do_unpack, pbytes + prow * f * gs),
+                                 ("dequantize_f16", do_deq, pbytes + 2 * N * K + 4 * R)):
+            us = timed(fn, 24)
+            per[f"b{nbits}_{name}"] = {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1), "bytes": nbytes}
+        del levels, packed, unp, deq
+    return {"us": per["b4_dequantize_f16"]["us"], "per": per, "digest": "n/a", "shape": [N, K]}, outs
+
+
+PROBES = {"bitpack": probe_bitpack, "gemm_sweep": probe_gemm_sweep, "quant": probe_quant, "l3": probe_l3, "gemm": probe_gemm, "gemm_mid": probe_gemm_mid, "decode": probe_decode}
 
 
 def compare(ref, got):
