@@ -90,13 +90,17 @@ struct SKArgs {
   // optional weight prefetch for the following launches (hqq_b200_decode_desc::pf_*): spans of 128-byte lines, 0 lines = end
   const char* pf_ptr[4];
   long long pf_lines[4];
+  int pf_chunk;  // HQQ_B200_WPF_BULK (KiB): > 0 = one bulk prefetch (TMA unit) per `pf_chunk` bytes instead of one prefetch per line
 };
 
 // L2 prefetch (a pure hint): nothing to do on the emulator
 #ifdef HQQ_EMU
 #define HQQ_PREFETCH_L2(p) ((void)(p))
+#define HQQ_PREFETCH_L2_BULK(p, n) ((void)(p), (void)(n))
 #else
 #define HQQ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// `n` bytes (a multiple of 16) from the 16-byte aligned `p` through the bulk-copy (TMA) unit: one instruction per chunk
+#define HQQ_PREFETCH_L2_BULK(p, n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n))
 #endif
 
 #ifdef HQQ_EMU
@@ -801,9 +805,21 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   }
   if (a.pf_lines[0] > 0) {
     // HBM is idle while this kernel waits for its inputs and the weights of the next launches depend on nothing: pull them into L2
+    if (a.pf_chunk > 0) {
 #pragma unroll 1
-    for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp)
-      for (long long i = (long long)blockIdx.x * 256 + tid; i < a.pf_lines[sp]; i += (long long)gridDim.x * 256) HQQ_PREFETCH_L2(a.pf_ptr[sp] + (i << 7));
+      for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp) {
+        // the bulk prefetch is a warp-level (uniform-datapath) instruction: one chunk per warp and trip, issued by lane 0
+        const long long bytes = a.pf_lines[sp] << 7, nch = (bytes + a.pf_chunk - 1) / a.pf_chunk;
+        for (long long i = (long long)blockIdx.x * 8 + (tid >> 5); i < nch; i += (long long)gridDim.x * 8) {
+          const long long off = i * a.pf_chunk, left = bytes - off;
+          if ((tid & 31) == 0) HQQ_PREFETCH_L2_BULK(a.pf_ptr[sp] + off, (uint32_t)(left < a.pf_chunk ? left : a.pf_chunk));
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp)
+        for (long long i = (long long)blockIdx.x * 256 + tid; i < a.pf_lines[sp]; i += (long long)gridDim.x * 256) HQQ_PREFETCH_L2(a.pf_ptr[sp] + (i << 7));
+    }
   }
   if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
   else { pdl_launch_dependents(); if (a.skip_wait == 0) pdl_wait(); }
@@ -1296,6 +1312,11 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     a.hint_row_lines = tpx->l2_hint_row_bytes >> 7; a.hint_stride = tpx->l2_hint_chunk_stride;
   }
   for (int i = 0; i < 4; ++i) { a.pf_ptr[i] = nullptr; a.pf_lines[i] = 0; }
+  {
+    // HQQ_B200_WPF_BULK=<KiB per bulk prefetch> (tuning knob, 1..1024; 0 / unset = one prefetch.global.L2 per 128-byte line)
+    HQQ_ENV_KNOB(bulk_kib, ([] { const char* e = getenv("HQQ_B200_WPF_BULK"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 1024 ? 1024 : v); })());
+    a.pf_chunk = bulk_kib << 10;
+  }
   if (tpx && tpx->pf_bytes[0] > 0) {
     HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
     for (int i = 0, j = 0; i < 4 && tpx->pf_bytes[i] > 0; ++i) {

@@ -385,7 +385,7 @@ class DecodeModel:
         return self.graph
 
     # knobs that only select among bit-identical kernels / pure prefetch hints of the one-token path
-    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD", "HQQ_B200_WPF_FROM")
+    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD", "HQQ_B200_WPF_FROM", "HQQ_B200_WPF_BULK")
 
     def retune(self, knobs: dict | None = None, warmup: int = 2):
         """Re-capture the decode graph under another choice of the TUNABLE knobs ({} = the default kernels).  The knobs select

@@ -42,6 +42,10 @@ DECODE_CANDIDATES = [
     {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o"},
     {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o,gu"},
     {"HQQ_B200_WPF_MB": "88", "HQQ_B200_WPF_AHEAD": "2", "HQQ_B200_WPF_FROM": "o"},
+    # the same volumes through the bulk-copy unit (one cp.async.bulk.prefetch.L2 per 16 / 64 KiB instead of one prefetch per line)
+    {"HQQ_B200_WPF_MB": "24", "HQQ_B200_WPF_BULK": "16"},
+    {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o,gu", "HQQ_B200_WPF_BULK": "16"},
+    {"HQQ_B200_WPF_MB": "64", "HQQ_B200_WPF_AHEAD": "1", "HQQ_B200_WPF_FROM": "o,gu", "HQQ_B200_WPF_BULK": "64"},
     # prefetch on top of the kernel variants
     {"HQQ_B200_D1_VARIANT": "1042", "HQQ_B200_WPF_MB": "24"},
     {"HQQ_B200_D1_VARIANT": "7042", "HQQ_B200_WPF_MB": "24"},
