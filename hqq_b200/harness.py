@@ -407,6 +407,17 @@ class DecodeModel:
         self.graph = None
         return self.capture(warmup=warmup)
 
+    def autotune(self, budget_s: float = 90.0, **kw):
+        """Measure, on this GPU, which of the result-preserving decode knobs pays (hqq_b200/tune.py: child-process guard, then
+        in-process timing on this model) and leave the model captured under the winner.  Returns the tuner's report.  One GPU,
+        one sequence, the five-launch step only: the guard runs an 8-block Llama-3-8B-shaped stand-in with the same kernels."""
+        from . import tune
+        if self.tp != 1 or self.batch != 1 or self.fused != 5:
+            raise ValueError("autotune: single-GPU, batch-1, fused=5 decode only")
+        if self.graph is None:
+            self.capture()
+        return tune.choose_decode(self, tune.guard_decode(budget_s=budget_s), **kw)
+
     def reset_state(self, token: int = 1):
         """Position 0, empty KV caches, `token` as the first input: the state every token-stream comparison starts from."""
         self.tok.fill_(token)
