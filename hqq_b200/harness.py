@@ -81,7 +81,7 @@ class DecodeModel:
         self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
         self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
         self.wpf_from = parse_wpf_from(os.environ.get("HQQ_B200_WPF_FROM", ""))
-        self.nbits = nbits
+        self.nbits, self.group_size = nbits, group_size
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
         self.n_layers = n_layers if n_layers is not None else shape.n_layers
@@ -416,7 +416,9 @@ class DecodeModel:
             raise ValueError("autotune: single-GPU, batch-1, fused=5 decode only")
         if self.graph is None:
             self.capture()
-        return tune.choose_decode(self, tune.guard_decode(budget_s=budget_s), **kw)
+        import dataclasses
+        margs = {"shape": dataclasses.asdict(self.shape), "nbits": self.nbits, "group_size": self.group_size}
+        return tune.choose_decode(self, tune.guard_decode(budget_s=budget_s, layers=min(8, self.n_layers), model_args=margs), **kw)
 
     def reset_state(self, token: int = 1):
         """Position 0, empty KV caches, `token` as the first input: the state every token-stream comparison starts from."""

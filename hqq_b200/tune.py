@@ -88,11 +88,12 @@ def measure(model, steps: int = 30, rounds: int = 2, start_pos: int = 20):
 
 
 # ---------------------------------------------------------------------------------------------------------- guard (child process)
-def _child(candidates, layers: int):
+def _child(candidates, layers: int, shape: dict | None = None, nbits: int = 4, group_size: int = 64):
     import torch
     from . import harness
     dev = torch.device("cuda", 0)
-    m = harness.DecodeModel(harness.LLAMA3_8B, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=64, n_layers=layers)
+    shp = harness.LlamaShape(**shape) if shape else harness.LLAMA3_8B
+    m = harness.DecodeModel(shp, nbits=nbits, group_size=group_size, dtype=torch.float16, device=dev, cache_len=64, n_layers=layers)
     for i, knobs in enumerate(candidates):
         print("TRY " + json.dumps({"i": i}), flush=True)
         m.retune(knobs, warmup=2)
@@ -101,14 +102,16 @@ def _child(candidates, layers: int):
     print("DONE", flush=True)
 
 
-def _run_child(candidates, layers, first_line_s, per_line_s, deadline):
+def _run_child(candidates, layers, first_line_s, per_line_s, deadline, model_args=None):
     """One child over `candidates`.  Returns ({position: result}, running, why): `why` is None when the child finished the list;
     otherwise `running` is the position it had announced (TRY) and not completed, or None if it died outside a candidate."""
     env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
-    proc = subprocess.Popen([sys.executable, "-m", "hqq_b200.tune", "--child", json.dumps(candidates), "--layers", str(layers)],
-                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=root)
+    cmd = [sys.executable, "-m", "hqq_b200.tune", "--child", json.dumps(candidates), "--layers", str(layers)]
+    if model_args:
+        cmd += ["--model", json.dumps(model_args)]
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=root)
     q: queue.Queue = queue.Queue()
 
     def reader():
@@ -152,13 +155,15 @@ def _run_child(candidates, layers, first_line_s, per_line_s, deadline):
 
 
 def guard_decode(candidates=None, layers: int = 8, budget_s: float = 90.0, first_line_s: float = 75.0, per_line_s: float = 20.0,
-                 run_child=None):
+                 run_child=None, model_args=None):
     """Run the default kernels and every candidate in child processes.  Returns one entry per configuration, entry 0 being the
     default kernels: {"knobs", "us", "digest", "identical", "speedup"} for a candidate that ran, {"knobs", "error"} for one that
-    crashed, hung or was not reached.  A candidate that kills its child is dropped and the rest continue in a new child (which
+    crashed, hung or was not reached.  `model_args` = {"shape": LlamaShape fields, "nbits", "group_size"} makes the child build another
+    shape than Llama-3-8B.  A candidate that kills its child is dropped and the rest continue in a new child (which
     starts with the default kernels again, so speed-ups are always relative to the same process).  `run_child` is the seam the
     CPU tests use."""
-    run_child = run_child or _run_child
+    if run_child is None:
+        run_child = (lambda *a: _run_child(*a, model_args=model_args)) if model_args else _run_child
     cands = [{}] + [dict(c) for c in (DECODE_CANDIDATES if candidates is None else candidates)]
     out = [None] * len(cands)
     deadline = time.perf_counter() + budget_s
@@ -244,4 +249,5 @@ def autotune_enabled() -> bool:
 
 if __name__ == "__main__":
     if "--child" in sys.argv:
-        _child(json.loads(sys.argv[sys.argv.index("--child") + 1]), int(sys.argv[sys.argv.index("--layers") + 1]))
+        margs = json.loads(sys.argv[sys.argv.index("--model") + 1]) if "--model" in sys.argv else {}
+        _child(json.loads(sys.argv[sys.argv.index("--child") + 1]), int(sys.argv[sys.argv.index("--layers") + 1]), **margs)
