@@ -32,6 +32,8 @@ DECODE_CANDIDATES = [
     {"HQQ_B200_D1_VARIANT": "2042"},
     {"HQQ_B200_D1_VARIANT": "4042"},
     {"HQQ_B200_D1_VARIANT": "7042"},
+    {"HQQ_B200_D1_VARIANT": "3042"},
+    {"HQQ_B200_D1_VARIANT": "7033"},
     # weight prefetch from every linear launch (each covers the next launch / the next two)
     {"HQQ_B200_WPF_MB": "8"},
     {"HQQ_B200_WPF_MB": "24"},
