@@ -69,6 +69,7 @@ void run_block(std::function<void()> body, dim3 block) {
   const int n = (int)(block.x * block.y * block.z);
   if (n > 2048) { fprintf(stderr, "emu: block of %d threads\n", n); abort(); }
   g_block_threads = n;
+  if (getenv("EMU_TRACE") && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) fprintf(stderr, "emu: launch with %d threads per block\n", n);
   g_body = body;
   for (auto& b : g_warp_bar) b = Barrier();
   g_block_bar = Barrier();
