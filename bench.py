@@ -374,7 +374,7 @@ def run_probes(budget_s=170.0, timeout_s=45.0):
            "bitpack": run("bitpack"),
            "solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
            "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
-           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
+           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld512"), ("HQQ_B200_GEMM_VARIANT", "ld")]),
            "gemm_mid": against_default("gemm_mid", [("HQQ_B200_GEMM_SPLITK", "1")])}
     res["seconds"] = round(time.perf_counter() - t_start, 1)
     return res

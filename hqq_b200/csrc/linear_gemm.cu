@@ -437,11 +437,13 @@ struct Smem512 {
   static constexpr int BYTES = kStages * A_STAGE + kStagesB * B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <typename T, int NBITS, int GS>
-__global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+// DQ = 512 (HQQ_B200_GEMM_VARIANT=un512dq): sixteen dequant warps, as in linear_gemm_kernel<..., 512>
+template <typename T, int NBITS, int GS, int DQ = kDequantThreads>
+__global__ void __launch_bounds__(64 + DQ, 1) linear_gemm_un512_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   constexpr int F = 8 / NBITS;             // slabs per byte
   constexpr int PR = kTileRows / F;        // packed rows per tile
-  constexpr int BPT = 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
+  constexpr int BPT = 64 * PR / DQ;        // packed bytes per dequant thread and k-block (32 / F with 256 threads)
+  static_assert(BPT >= 4 && (DQ == 256 || DQ == 512), "a dequant thread expands at least four packed bytes per k-block");
   constexpr int TPR = 64 / BPT;            // dequant threads per packed row
   constexpr uint32_t MASK = (1u << NBITS) - 1u;
   using S = Smem512;
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], DQ / 32); mbar_init(&empty[s], 1); }
       for (int s = 0; s < S::kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
       mbar_init(accum_full, 1);
       fence_barrier_init();
@@ -611,7 +613,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
-    const int half = (warp - 2) >> 2;             // two warps share a quarter: split the token columns
+    constexpr int NPART = DQ / 128;               // warps sharing a quarter (2 or 4): they split the token columns
+    const int half = (warp - 2) >> 2;
     const int t = quarter * 32 + lane;            // tile row = weight row inside the tile
     const int tf = t / PR, tp = t % PR;
     const bool n_ok = (prow0 + tp) < a.step;
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_un512_kernel(const __
     T bn = cvt_out<T>(0.0f);
     if (has_bias && n_ok) bn = bias[n];
 #pragma unroll 1
-    for (int col = half * (UN / 2); col < (half + 1) * (UN / 2); col += 32) {
+    for (int col = half * (UN / NPART); col < (half + 1) * (UN / NPART); col += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
 #pragma unroll
@@ -1390,11 +1393,12 @@ static EncodeTiledFn get_encode() {
 
 // HQQ_B200_GEMM_VARIANT: "ld" = loader-warp kernel (linear_gemm_ld_kernel), "un512" = two accumulators per weight tile
 // (linear_gemm_un512_kernel, M > 256 only), "ld512" = both (linear_gemm_ld512_kernel, M > 256 only), "dq16" = the default kernel with
-// sixteen dequant warps (M > 128, not 1-bit); all experimental
+// sixteen dequant warps (M > 128, not 1-bit), "un512dq" = un512 with sixteen dequant warps (M > 256; dq16 for 128 < M <= 256); all
+// experimental
 static int gemm_variant() {
   HQQ_ENV_KNOB(variant, ([] {
     const char* e = getenv("HQQ_B200_GEMM_VARIANT");
-    return (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : (e && !strcmp(e, "ld512")) ? 3 : (e && !strcmp(e, "dq16")) ? 4 : 0;
+    return (e && !strcmp(e, "ld")) ? 1 : (e && !strcmp(e, "un512")) ? 2 : (e && !strcmp(e, "ld512")) ? 3 : (e && !strcmp(e, "dq16")) ? 4 : (e && !strcmp(e, "un512dq")) ? 5 : 0;
   })());
   return variant;
 }
@@ -1412,7 +1416,7 @@ static int encode_xmap(CUtensorMap* xmap, const void* x, const Args& a, CUtensor
   return HQQ_OK;
 }
 
-template <typename T, int NBITS, int GS>
+template <typename T, int NBITS, int GS, int DQ = kDequantThreads>
 static int launch_un512(const void* x, const Args& a, cudaStream_t st) {
   CUtensorMap xmap;
   const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -1420,14 +1424,14 @@ static int launch_un512(const void* x, const Args& a, cudaStream_t st) {
   if (rc) return rc;
   constexpr int PR = kTileRows / (8 / NBITS);
   const dim3 grid((unsigned)cdiv(a.step, PR), (unsigned)cdiv(a.M, Smem512::UN));
-  auto k = linear_gemm_un512_kernel<T, NBITS, GS>;
+  auto k = linear_gemm_un512_kernel<T, NBITS, GS, DQ>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem512::BYTES);
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem512::BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  k<<<grid, kThreads, Smem512::BYTES, st>>>(xmap, a);
+  k<<<grid, 64 + DQ, Smem512::BYTES, st>>>(xmap, a);
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05-un512");
   return HQQ_OK;
 }
@@ -1554,7 +1558,8 @@ static int by_un(const void* x, const Args& a, void* ws, size_t ws_bytes, cudaSt
   if (a.M > 256 && gemm_variant() == 2) return launch_un512<T, NBITS, GS>(x, a, st);
   if (a.M > 256 && gemm_variant() == 3) return launch_ld512<T, NBITS, GS>(x, a, st);
   if constexpr (NBITS != 1) {  // 1-bit: 16 packed rows per tile leave only two bytes per thread and k-block
-    if (a.M > 128 && gemm_variant() == 4 && un_cap > 128) return launch<T, NBITS, GS, 256, 512>(x, a, st);
+    if (a.M > 256 && gemm_variant() == 5) return launch_un512<T, NBITS, GS, 512>(x, a, st);
+    if (a.M > 128 && (gemm_variant() == 4 || gemm_variant() == 5) && un_cap > 128) return launch<T, NBITS, GS, 256, 512>(x, a, st);
   }
   if (a.M <= 64 || un_cap <= 64) return launch<T, NBITS, GS, 64>(x, a, st);
   if (a.M <= 128 || un_cap <= 128) return launch<T, NBITS, GS, 128>(x, a, st);

@@ -310,7 +310,7 @@ def test_emulated_tcgen05_gemm_matches_the_oracle(emu, tmp_path_factory):
 
 
 @pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_VARIANT", "ld512"),
-                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_UN", "128")])
+                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_UN", "128")])
 def test_emulated_gemm_variants_are_bit_identical(emu, tmp_path_factory, knob):
     """un512 (two accumulators per dequantised weight tile), ld (loader warp + cp.async rings), dq16 (sixteen dequant warps) and the UN cap issue the same MMAs in
     the same k order as the default kernel: identical outputs, and no barrier protocol that stalls."""
@@ -381,7 +381,7 @@ def test_emulated_forward_random_shapes(emu, oracle):
 
 
 @pytest.mark.parametrize("knob", [None, ("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_VARIANT", "ld512"),
-                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_SPLITK", "1")])
+                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_SPLITK", "1")])
 def test_emulated_gemm_pipelines_under_adversarial_timing(emu, tmp_path_factory, knob):
     """The emulator as a protocol checker: TMA copies, tensor-core operations (operands read when they EXECUTE, commits after them)
     and mbarrier-tied cp.async land a random number of scheduler passes after issue, and threads are resumed in random order.  A

@@ -97,7 +97,7 @@ def run_gemm(variant, path):
     return torch.load(path, weights_only=True)
 
 
-@pytest.mark.parametrize("variant", ["ld", "un512", "ld512", "dq16"])
+@pytest.mark.parametrize("variant", ["ld", "un512", "ld512", "dq16", "un512dq"])
 def test_gemm_variants_are_bit_identical(tmp_path, variant):
     """ld: loader warp + cp.async rings; un512: two accumulators (512 tokens) per dequantised weight tile, taken for M > 256.
     Both issue the same MMAs in the same k order as the default kernel, so the outputs must match bit for bit."""

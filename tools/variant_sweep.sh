@@ -27,6 +27,7 @@ echo "== GEMM M=4096: default / ld / un512 / UN caps"
 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=un512 timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=dq16 timeout 200 python tools/prof_gemm.py 256,1024,4096 4,2,8 2>&1 | grep fused
+HQQ_B200_GEMM_VARIANT=un512dq timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld512 timeout 200 python tools/prof_gemm.py 1024,4096,8192 4 2>&1 | grep fused
 HQQ_B200_GEMM_VARIANT=ld HQQ_B200_GEMM_UN=128 timeout 200 python tools/prof_gemm.py 4096 4 2>&1 | grep fused
