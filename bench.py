@@ -318,7 +318,7 @@ def _finite(o):
     return o
 
 
-def run_probes(budget_s=170.0, timeout_s=45.0):
+def run_probes(budget_s=200.0, timeout_s=45.0):
     """First GPU execution of the kernels written after round 1's GPU budget was spent: each knob runs
     tools/variant_probe.py in its OWN process under a timeout -- a crash or a hang there cannot reach this process -- on a fixed
     seeded workload, and is compared with the default kernels (sha256 of the outputs, relative error where the summation order
@@ -637,7 +637,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probes", action="store_true", help="skip the experimental-kernel probes (sub-processes, N=1 only)")
-    ap.add_argument("--extras-deadline", type=float, default=360.0, help="seconds the objects added after the measurement (probes, quantizer, "
+    ap.add_argument("--extras-deadline", type=float, default=400.0, help="seconds the objects added after the measurement (probes, quantizer, "
                     "CPU baselines) may take before the line is printed without the unfinished ones")
     ap.add_argument("--worker", action="store_true", help=argparse.SUPPRESS)  # internal: the measuring process of a supervised N=1 run
     ap.add_argument("--no-autotune", action="store_true", help="time the default kernels only (no decode autotuner; N=1 only anyway)")
