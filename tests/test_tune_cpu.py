@@ -218,3 +218,35 @@ def test_bench_supervisor_reports_failure_when_both_workers_fail(monkeypatch, ca
     monkeypatch.setattr(bench.subprocess, "run", _fake_run([(1, ""), (1, "")]))
     assert bench.supervise([]) == 1
     assert capsys.readouterr().out.strip() == ""
+
+
+def test_retune_sets_the_environment_reloads_the_library_and_recaptures(monkeypatch):
+    """DecodeModel.retune without a GPU: capture() and the library are stubbed; the knobs of the previous choice must not leak."""
+    import os
+    from hqq_b200 import _lib, harness
+
+    class Lib:
+        reloads = 0
+
+        def hqq_b200_reload_env(self):
+            Lib.reloads += 1
+
+    monkeypatch.setattr(_lib, "load", lambda path=None: Lib())
+    for k in DecodeModel.TUNABLE:
+        monkeypatch.delenv(k, raising=False)
+    m = harness.DecodeModel.__new__(harness.DecodeModel)
+    captured = []
+    m.capture = lambda warmup=3: captured.append((warmup, {k: os.environ.get(k) for k in DecodeModel.TUNABLE})) or "graph"
+    assert m.retune({"HQQ_B200_D1_VARIANT": "7042", "HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_FROM": "o,gu"}) == "graph"
+    assert (m.wpf_mb, m.wpf_ahead, m.wpf_from) == (48.0, 2, frozenset({"o", "gu"}))
+    assert captured[-1][1]["HQQ_B200_D1_VARIANT"] == "7042" and Lib.reloads == 1
+    m.retune({"HQQ_B200_WPF_MB": "8", "HQQ_B200_WPF_BULK": "16"}, warmup=3)
+    assert captured[-1] == (3, {"HQQ_B200_D1_VARIANT": None, "HQQ_B200_WPF_MB": "8", "HQQ_B200_WPF_AHEAD": None, "HQQ_B200_WPF_FROM": None,
+                                "HQQ_B200_WPF_BULK": "16"})
+    assert (m.wpf_mb, m.wpf_ahead, m.wpf_from) == (8.0, 1, frozenset(harness.WPF_STAGES))
+    m.retune({})
+    assert all(v is None for v in captured[-1][1].values()) and m.wpf_mb == 0.0 and Lib.reloads == 3
+    with pytest.raises(ValueError):
+        m.retune({"HQQ_B200_PDL": "0"})
+    for k in DecodeModel.TUNABLE:
+        os.environ.pop(k, None)
