@@ -2,7 +2,7 @@
 torch.set_num_threads(all cores)) beside the C/OpenMP oracle port on the same layer, so that the port which bench.py times as the
 CPU baseline on the GPU box (where the reference does not exist) is calibrated against the thing it stands in for.
 
-    python tools/ref_cpu_calibration.py            # prints one JSON line
+    python tests/golden/ref_cpu_calibration.py            # prints one JSON line
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.environ.get("HQQ_REFERENCE", "/root/reference")
 shim = tempfile.mkdtemp()
 with open(os.path.join(shim, "termcolor.py"), "w") as f:
