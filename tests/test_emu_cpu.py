@@ -407,3 +407,39 @@ def test_emulated_reload_env_switches_cached_knobs_in_one_process(emu):
     assert out["restored_rc"] == 0 and out["restored_same"]
     for v in ("1042", "2042", "4042", "7042"):
         assert out[f"variant_{v}"] == [0, True], v
+
+
+def test_emulated_solver_equals_the_c_oracle_on_random_layers(emu, oracle):
+    """Random layers (both axes, four widths, three group sizes): the solver kernels' source, run on the emulator, against the
+    C oracle (which reproduces the reference's fixtures level for level, tests/test_oracle_c.py).  Weight-like data (the shrinkage
+    is exactly zero): identical iteration counts and levels.  Heavy-tailed data (W_e != 0, where the kernel's ex2/lg2 and
+    reciprocal differ from powf and the division at the 1e-7 level): the GPU tests' tolerance."""
+    try:
+        from oracle import hqq_oracle_c as C
+        C.lib()
+    except (RuntimeError, OSError) as e:
+        pytest.skip(f"C oracle cannot be built here: {e}")
+    rng = np.random.default_rng(2024)
+    exact = 0
+    for case in range(14):
+        nbits = (4, 2, 8, 1, 3, 4, 4)[case % 7]
+        gs = (64, 32, 128)[case % 3]
+        axis = case % 2
+        heavy = case >= 11
+        N, K = int(rng.integers(2, 6)) * 16, int(rng.integers(1, 4)) * 128
+        W = (rng.standard_normal((N, K)) * (1.5 if heavy else 0.02) + (0.01 if case % 4 == 0 else 0.0)).astype(np.float32)
+        rows = N * K // gs if axis == 1 else gs
+        if nbits != 3 and rows % (8 // nbits):
+            continue
+        Wq, s, z, info, err, _ = quantize(emu, W, F32, nbits, gs, case % 2, axis=axis)
+        Wq_c, meta_c, tr_c = C.quantize(W, nbits=nbits, group_size=gs, axis=axis, round_zero=(nbits == 4), return_trace=True)
+        pk = oracle.BIT_TO_PACKING[nbits]
+        a, b = oracle.UNPACK[pk](Wq)[:rows].astype(int), oracle.UNPACK[pk](Wq_c)[:rows].astype(int)
+        assert np.array_equal(s, meta_c["scale"].ravel()), case
+        if heavy:
+            assert abs(int(info[0]) - tr_c["iters"]) <= 1 and (a != b).mean() <= 2e-3 and np.abs(a - b).max() <= 1, case
+        else:
+            assert int(info[0]) == tr_c["iters"], case
+            assert np.array_equal(a, b), case
+            exact += 1
+    assert exact >= 8
