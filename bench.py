@@ -380,6 +380,36 @@ def run_probes(budget_s=200.0, timeout_s=45.0):
     return res
 
 
+def _attach_sweeps(line, peaks):
+    """Move the gemm_sweep / bitpack probe results out of `experimental` into objects of their own, with fractions of the measured peaks."""
+    sweep = (line.get("experimental") or {}).pop("gemm_sweep", None)
+    if isinstance(sweep, dict) and "per" in sweep:
+        # BASELINE configs[2] / metric (2): fused dequant-GEMM TFLOP/s against the measured dense bf16/fp16 tensor peak
+        peak_tf = None
+        try:
+            peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:  # noqa: BLE001
+            peak_tf = 2250.0
+        for e in sweep["per"].values():
+            e["frac_of_tensor_peak"] = round(e["TFLOPs"] / peak_tf, 4)
+        line["gemm_sweep"] = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "headline": "b4_4096x4096_M4096",
+                              "achieved": sweep["per"]["b4_4096x4096_M4096"]["TFLOPs"],
+                              "frac": sweep["per"]["b4_4096x4096_M4096"]["frac_of_tensor_peak"], "per": sweep["per"],
+                              "note": "default kernels, event-timed alone (burst peak); route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit)"}
+    elif sweep is not None:
+        line["gemm_sweep"] = sweep
+    bp = (line.get("experimental") or {}).pop("bitpack", None)
+    if isinstance(bp, dict) and "per" in bp:
+        # SURVEY 8(d): pack / unpack / dequantize against the measured HBM peak (default kernels, own process)
+        for e in bp["per"].values():
+            e["frac_of_hbm_peak"] = round(e["GBps"] / peaks["hbm_gbs"], 4)
+        line["bitpack"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "headline": "b4_dequantize_f16",
+                           "achieved": bp["per"]["b4_dequantize_f16"]["GBps"], "frac": bp["per"]["b4_dequantize_f16"]["frac_of_hbm_peak"],
+                           "per": bp["per"], "note": "one 14336x4096 matrix per call, inputs cycled (cold L2), algorithmic bytes = input + output"}
+    elif bp is not None:
+        line["bitpack"] = bp
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -542,32 +572,10 @@ def run_gpu(args, rank, world, local_rank):
                 line["experimental"] = run_probes()
             except Exception as e:  # noqa: BLE001
                 line["experimental"] = {"error": repr(e)[:200]}
-        sweep = (line.get("experimental") or {}).pop("gemm_sweep", None)
-        if isinstance(sweep, dict) and "per" in sweep:
-            # BASELINE configs[2] / metric (2): fused dequant-GEMM TFLOP/s against the measured dense bf16/fp16 tensor peak
-            peak_tf = None
-            try:
-                peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-            except Exception:  # noqa: BLE001
-                peak_tf = 2250.0
-            for e in sweep["per"].values():
-                e["frac_of_tensor_peak"] = round(e["TFLOPs"] / peak_tf, 4)
-            line["gemm_sweep"] = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "headline": "b4_4096x4096_M4096",
-                                  "achieved": sweep["per"]["b4_4096x4096_M4096"]["TFLOPs"],
-                                  "frac": sweep["per"]["b4_4096x4096_M4096"]["frac_of_tensor_peak"], "per": sweep["per"],
-                                  "note": "default kernels, event-timed alone (burst peak); route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit)"}
-        elif sweep is not None:
-            line["gemm_sweep"] = sweep
-        bp = (line.get("experimental") or {}).pop("bitpack", None)
-        if isinstance(bp, dict) and "per" in bp:
-            # pack / unpack / dequantize against the measured HBM peak (default kernels, own process)
-            for e in bp["per"].values():
-                e["frac_of_hbm_peak"] = round(e["GBps"] / peaks["hbm_gbs"], 4)
-            line["bitpack"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "headline": "b4_dequantize_f16",
-                               "achieved": bp["per"]["b4_dequantize_f16"]["GBps"], "frac": bp["per"]["b4_dequantize_f16"]["frac_of_hbm_peak"],
-                               "per": bp["per"], "note": "one 14336x4096 matrix per call, inputs cycled (cold L2), algorithmic bytes = input + output"}
-        elif bp is not None:
-            line["bitpack"] = bp
+        try:
+            _attach_sweeps(line, peaks)
+        except Exception as e:  # noqa: BLE001 -- formatting of an extra object must not cost the line
+            line["extras_error"] = repr(e)[:200]
         if world == 1 and not big and B == 1:
             try:  # extra object, never allowed to cost the bench line
                 sf = (line.get("experimental") or {}).get("solver_fast") or {}
