@@ -250,3 +250,45 @@ def test_retune_sets_the_environment_reloads_the_library_and_recaptures(monkeypa
         m.retune({"HQQ_B200_PDL": "0"})
     for k in DecodeModel.TUNABLE:
         os.environ.pop(k, None)
+
+
+def test_measure_runs_the_token_check_and_the_timed_loops(monkeypatch):
+    """tune.measure with the CUDA calls stubbed: 16 tokens from the reset state, then `rounds` timed loops that restart at `start_pos`."""
+    import torch
+
+    class Ev:
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+        def elapsed_time(self, other):
+            return 3.0  # ms
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda d=None: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: object())
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+
+    class M:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.pos, self.next_tok, self.steps, self.resets, self.starts = torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long), 0, 0, []
+
+        def reset_state(self):
+            self.resets += 1
+            self.pos.zero_()
+
+        def decode(self):
+            if int(self.pos) == 20:
+                self.starts.append(self.steps)
+            self.steps += 1
+            self.next_tok.fill_(self.steps)
+            self.pos.add_(1)
+
+    m = M()
+    toks, us = tune.measure(m, steps=30, rounds=2, start_pos=20)
+    assert m.resets == 1 and m.steps == tune.N_CHECK_TOKENS + 60 and m.starts == [16, 46]
+    assert toks.shape == (tune.N_CHECK_TOKENS, 1) and toks[:, 0].tolist() == list(range(1, 17))
+    assert us == pytest.approx(3.0 * 1e3 / 30)
