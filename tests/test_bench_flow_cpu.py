@@ -67,7 +67,11 @@ REPORT = {"selected": {"HQQ_B200_WPF_MB": "48", "HQQ_B200_WPF_FROM": "o"}, "trie
           "identical": True, "guard_speedup": 1.25}], "default_us": 1900.0, "selected_us": 1600.0, "gain": 1900.0 / 1600.0}
 PROBES = {"gemm_sweep": {"us": 120.0, "per": {"b4_4096x4096_M4096": {"us": 120.0, "TFLOPs": 1145.0, "route": 2}}, "digest": "n/a"},
           "bitpack": {"us": 30.0, "per": {"b4_dequantize_f16": {"us": 30.0, "GBps": 5000.0, "bytes": 150e6}}, "digest": "n/a"},
-          "solver_fast": {"bit_identical": True, "speedup": 4.0}}
+          "solver_fast": {"bit_identical": True, "speedup": 4.0},
+          "gemm": {"default": {"us": 120.0, "per": {"4096x4096xM4096": {"us": 120.0, "TFLOPs": 1145.0}}, "digest": "d"},
+                   "HQQ_B200_GEMM_VARIANT=dq16": {"per": {"4096x4096xM4096": {"TFLOPs": 1400.0}}, "bit_identical": True, "speedup": 1.22},
+                   "HQQ_B200_GEMM_VARIANT=ld": {"per": {"4096x4096xM4096": {"TFLOPs": 1600.0}}, "bit_identical": False},
+                   "HQQ_B200_GEMM_VARIANT=un512": {"error": "timeout after 45 s"}}}
 
 
 @pytest.fixture
@@ -112,6 +116,7 @@ def test_run_gpu_assembles_the_line_with_the_autotuner(fake_gpu, capsys):
     assert at["in_process"][0]["knobs"] == "WPF_FROM=o,WPF_MB=48"
     assert FakeModel.built[0].retuned[-1] == REPORT["selected"]           # the timed region runs under the selection
     assert d["gemm_sweep"]["frac"] == pytest.approx(1145.0 / d["gemm_sweep"]["peak"], rel=1e-3) and "gemm_sweep" not in d["experimental"]
+    assert d["gemm_sweep"]["best_bit_identical_variant"]["knob"] == "HQQ_B200_GEMM_VARIANT=dq16"   # faster, but not identical: ignored
     assert d["bitpack"]["frac"] == pytest.approx(5000.0 / d["bitpack"]["peak"], rel=1e-3)
     assert d["quantizer"]["fast_ok"] is True and d["quantizer"]["cpu_baseline"]["kind"] == "port"
     assert d["cpu_baseline"]["cores"] == 8 and d["roofline"]["frac"] == 0.45 and d["clocks"]["reasons"] == []
