@@ -129,6 +129,34 @@ def gen_quantize_small():
     np.savez_compressed(os.path.join(HERE, "quantize_small.npz"), **out)
 
 
+def gen_quantize_heavy():
+    """Heavy-tailed weights: |W - W_r| exceeds the shrinkage threshold beta^(-1/(2-p)) = 0.170, so the |x|^(p-1) branch of
+    shrink_lp_op (optimize.py:96-108) -- identically zero on weight-like data such as quantize_small -- shapes the zero-points.
+    Also known-answer vectors of shrink_lp_op itself (p = 0.7 and the p = 1 branch, with 0, tiny, threshold-sized, large inputs)."""
+    rng = np.random.RandomState(5)
+    W = (rng.standard_t(3, size=(64, 256)) * 1.5).astype(np.float32)
+    out = {"W": W}
+    for nbits in [4, 2, 1]:
+        for axis in [0, 1]:
+            rz = nbits == 4
+            W_q, meta = Quantizer.quantize(torch.from_numpy(W), nbits=nbits, group_size=64, axis=axis, round_zero=rz, optimize=True, device="cpu")
+            key = f"b{nbits}_a{axis}_g64"
+            iters, errs, zero_chk = solver_trace(torch.from_numpy(W), nbits, 64, axis, rz)
+            assert np.array_equal(zero_chk, npy(meta["zero"])), key
+            out[key + "/W_q"] = npy(W_q)
+            out[key + "/scale"] = npy(meta["scale"])
+            out[key + "/zero"] = npy(meta["zero"])
+            out[key + "/iters"] = np.int32(iters)
+            out[key + "/errors"] = errs
+    x = np.concatenate([[0.0, -0.0, 1e-30, -1e-30, 1e-6, 0.05, -0.05, 0.1699, 0.17, 0.1701, -0.1702, 0.2, -0.3, 1.0, -7.5, 100.0, 1e6],
+                        rng.randn(200) * 0.2, rng.randn(200) * 3.0]).astype(np.float32)
+    out["shrink/x"] = x
+    out["shrink/p0.7_beta10"] = npy(ref_opt.shrink_lp_op(torch.from_numpy(x), 1e1, 0.7))
+    out["shrink/p1_beta10"] = npy(ref_opt.shrink_lp_op(torch.from_numpy(x), 1e1, 1))
+    out["shrink/p0.5_beta4"] = npy(ref_opt.shrink_lp_op(torch.from_numpy(x), 4.0, 0.5))
+    np.savez_compressed(os.path.join(HERE, "quantize_heavy.npz"), **out)
+
+
 def gen_config1():
     """BASELINE config 0: single HQQLinear 1024x1024 nbits=4 gs=64 axis=1, PYTORCH backend, CPU."""
     torch.manual_seed(42)  # the reference tests' seed, tests/test_quantize.py:22
@@ -170,10 +198,10 @@ def gen_state_dict_keys():
 
 
 if __name__ == "__main__":
-    gen_bitpack()
-    gen_quantize_small()
-    gen_config1()
-    gen_state_dict_keys()
+    gens = {"bitpack": gen_bitpack, "quantize_small": gen_quantize_small, "quantize_heavy": gen_quantize_heavy, "config1": gen_config1,
+            "state_dict": gen_state_dict_keys}
+    for name in (sys.argv[1:] or list(gens)):  # python make_golden.py [name ...] regenerates only the named fixtures
+        gens[name]()
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -409,6 +409,22 @@ def test_emulated_reload_env_switches_cached_knobs_in_one_process(emu):
         assert out[f"variant_{v}"] == [0, True], v
 
 
+@pytest.mark.parametrize("variant,cases", [(0, [(4, 0), (4, 1), (2, 0), (2, 1), (1, 0), (1, 1)]), (1, [(4, 1), (2, 0)])])
+def test_emulated_solver_on_the_heavy_tailed_reference_fixture(emu, oracle, golden, variant, cases):
+    """Weights whose quantisation error exceeds the shrinkage threshold (the full formula with ex2/lg2 runs, the fast solver takes
+    its fallback): the kernels' source still reproduces the reference's iteration counts and every level."""
+    h = golden.heavy
+    for nbits, axis in cases:
+        key = f"b{nbits}_a{axis}_g64"
+        Wq, s, z, info, err, _ = quantize(emu, h["W"], F32, nbits, 64, variant, axis=axis)
+        pk = oracle.BIT_TO_PACKING[nbits]
+        rows = h["W"].size // 64 if axis == 1 else 64
+        assert int(info[0]) == int(h[key + "/iters"]), key
+        assert np.array_equal(oracle.UNPACK[pk](Wq)[:rows], oracle.UNPACK[pk](h[key + "/W_q"])[:rows]), key
+        zr = h[key + "/zero"].ravel()
+        assert np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1.0)) <= 2e-6, key
+
+
 def test_emulated_solver_equals_the_c_oracle_on_random_layers(emu, oracle):
     """Random layers (both axes, four widths, three group sizes): the solver kernels' source, run on the emulator, against the
     C oracle (which reproduces the reference's fixtures level for level, tests/test_oracle_c.py).  Weight-like data (the shrinkage
