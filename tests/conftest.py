@@ -35,6 +35,7 @@ def golden():
         quant = np.load(os.path.join(GOLDEN, "quantize_small.npz"))
         config1 = np.load(os.path.join(GOLDEN, "config1.npz"))
         state_dict = np.load(os.path.join(GOLDEN, "state_dict.npz"))
+        degenerate = np.load(os.path.join(GOLDEN, "quantize_degenerate.npz"))  # groups on the guards of the init (quantize.py:126-131)
         heavy = np.load(os.path.join(GOLDEN, "quantize_heavy.npz"))  # heavy-tailed weights: the shrinkage's |x|^(p-1) branch is active
     return G
 

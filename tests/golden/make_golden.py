@@ -157,6 +157,33 @@ def gen_quantize_heavy():
     np.savez_compressed(os.path.join(HERE, "quantize_heavy.npz"), **out)
 
 
+def gen_quantize_degenerate():
+    """Groups that hit the guards of the init (quantize.py:126-131): constant groups (|max - min| <= 1e-4 -> scale 1), ranges around
+    the 1e-4 boundary, a range so small that the inverse scale is clamped to 2e4, huge ranges, all-zero groups, single outliers."""
+    W = np.zeros((12, 64), dtype=np.float32)
+    W[1] = 3.25
+    W[2] = np.linspace(-1e-6, 1e-6, 64)
+    W[3] = np.linspace(-1e4, 1e4, 64)
+    W[4, ::2] = 1e-3
+    W[5] = -7.0
+    W[6] = np.linspace(0, 1, 64)
+    W[7, 0] = 100.0
+    W[8] = np.linspace(0, 1.0e-4, 64)        # denom == 1e-4 (float32): still "constant"
+    W[9] = np.linspace(0, 1.01e-4, 64)       # just above: scale = 15 / 1.01e-4 > 2e4 -> clamped
+    W[10] = np.linspace(-3e-4, 5e-4, 64)     # scale 18750: below the clamp
+    W[11, 5] = -1e-30
+    out = {"W": W}
+    for nbits in (4, 2, 8):
+        for optimize in (False, True):
+            W_q, meta = Quantizer.quantize(torch.from_numpy(W), nbits=nbits, group_size=64, axis=1, round_zero=(nbits == 4), optimize=optimize,
+                                           device="cpu")
+            key = f"b{nbits}_opt{int(optimize)}"
+            out[key + "/W_q"] = npy(W_q)
+            out[key + "/scale"] = npy(meta["scale"])
+            out[key + "/zero"] = npy(meta["zero"])
+    np.savez_compressed(os.path.join(HERE, "quantize_degenerate.npz"), **out)
+
+
 def gen_config1():
     """BASELINE config 0: single HQQLinear 1024x1024 nbits=4 gs=64 axis=1, PYTORCH backend, CPU."""
     torch.manual_seed(42)  # the reference tests' seed, tests/test_quantize.py:22
@@ -198,7 +225,8 @@ def gen_state_dict_keys():
 
 
 if __name__ == "__main__":
-    gens = {"bitpack": gen_bitpack, "quantize_small": gen_quantize_small, "quantize_heavy": gen_quantize_heavy, "config1": gen_config1,
+    gens = {"bitpack": gen_bitpack, "quantize_small": gen_quantize_small, "quantize_heavy": gen_quantize_heavy, "quantize_degenerate": gen_quantize_degenerate,
+            "config1": gen_config1,
             "state_dict": gen_state_dict_keys}
     for name in (sys.argv[1:] or list(gens)):  # python make_golden.py [name ...] regenerates only the named fixtures
         gens[name]()

@@ -49,7 +49,7 @@ def to_bf16_bits(x):
     return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
 
 
-def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20, axis=1):
+def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20, axis=1, optimize=1):
     N, K = W.shape
     if src == F16:
         Wd = aligned(W.shape, np.float16); Wd[...] = W.astype(np.float16)
@@ -69,7 +69,7 @@ def quantize(lib, W, src, nbits, gs, variant, lp=0.7, iters=20, axis=1):
     ws = aligned((nb,), np.uint8)
     os.environ["HQQ_B200_SOLVER_VARIANT"] = str(variant)
     try:
-        rc = lib.hqq_b200_quantize(P(Wd), src, ctypes.c_int64(N), ctypes.c_int64(K), gs, nbits, axis, int(nbits == 4), 1, ctypes.c_float(lp),
+        rc = lib.hqq_b200_quantize(P(Wd), src, ctypes.c_int64(N), ctypes.c_int64(K), gs, nbits, axis, int(nbits == 4), int(optimize), ctypes.c_float(lp),
                                    ctypes.c_float(10.0), iters, P(Wq), P(s), P(z), P(info), P(err), P(ws), ctypes.c_size_t(nb), None)
     finally:
         os.environ.pop("HQQ_B200_SOLVER_VARIANT", None)
@@ -423,6 +423,25 @@ def test_emulated_solver_on_the_heavy_tailed_reference_fixture(emu, oracle, gold
         assert np.array_equal(oracle.UNPACK[pk](Wq)[:rows], oracle.UNPACK[pk](h[key + "/W_q"])[:rows]), key
         zr = h[key + "/zero"].ravel()
         assert np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1.0)) <= 2e-6, key
+
+
+@pytest.mark.parametrize("nbits", (4, 2, 8))
+def test_emulated_quantizer_on_the_degenerate_reference_fixture(emu, oracle, golden, nbits):
+    """Groups on the guards of the init (constant, boundary of the 1e-4 test, clamped inverse scale, huge range, zeros): the
+    kernels' init + rounding path is bit-exact against the reference; with the solver on, the scale stays bit-exact, at most one
+    level of the 768 moves and the zero-points agree to 2e-6 -- the same statement as for the oracles."""
+    d = golden.degenerate
+    pk = oracle.BIT_TO_PACKING[nbits]
+    Wq, s, z, info, err, _ = quantize(emu, d["W"], F32, nbits, 64, 0, optimize=0)
+    assert np.array_equal(Wq, d[f"b{nbits}_opt0/W_q"])
+    assert np.array_equal(s, d[f"b{nbits}_opt0/scale"].ravel()) and np.array_equal(z, d[f"b{nbits}_opt0/zero"].ravel())
+    for variant in (0, 1):
+        Wq, s, z, info, err, _ = quantize(emu, d["W"], F32, nbits, 64, variant)
+        a, b = oracle.UNPACK[pk](Wq).astype(int), oracle.UNPACK[pk](d[f"b{nbits}_opt1/W_q"]).astype(int)
+        assert np.abs(a - b).max() <= 1 and (a != b).sum() <= 1, variant
+        assert np.array_equal(s, d[f"b{nbits}_opt1/scale"].ravel())
+        zr = d[f"b{nbits}_opt1/zero"].ravel()
+        assert np.all(np.isfinite(z)) and np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1.0)) <= 2e-6, variant
 
 
 def test_emulated_solver_equals_the_c_oracle_on_random_layers(emu, oracle):
