@@ -624,8 +624,13 @@ def supervise(argv, first_timeout_s=900.0, retry_timeout_s=900.0):
     for extra, timeout_s in ((["--worker"], first_timeout_s), (["--worker", "--no-autotune"], retry_timeout_s)):
         why = None
         try:
-            r = subprocess.run([sys.executable, me, *argv, *extra], stdout=subprocess.PIPE, text=True, timeout=timeout_s)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"metric"' in ln]
+            try:
+                r = subprocess.run([sys.executable, me, *argv, *extra], stdout=subprocess.PIPE, text=True, timeout=timeout_s)
+                out, why = r.stdout or "", f"worker exited with code {r.returncode} without a result line"
+            except subprocess.TimeoutExpired as e:  # a worker that printed its line and then hung (teardown) still counts
+                out = e.stdout.decode("utf-8", "replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+                why = f"worker timed out after {timeout_s:.0f} s"
+            lines = [ln for ln in out.splitlines() if ln.startswith("{") and '"metric"' in ln]
             if lines:
                 line = lines[-1]
                 if "--no-autotune" in extra:
@@ -637,9 +642,8 @@ def supervise(argv, first_timeout_s=900.0, retry_timeout_s=900.0):
                         pass
                 print(line, flush=True)
                 return 0
-            why = f"worker exited with code {r.returncode} without a result line"
-        except subprocess.TimeoutExpired:
-            why = f"worker timed out after {timeout_s:.0f} s"
+        except Exception as e:  # noqa: BLE001 -- could not even start the worker
+            why = repr(e)[:200]
         sys.stderr.write(f"bench.py: {why}\n")
         first_why = why
     return 1

@@ -183,6 +183,8 @@ def _fake_run(script):
         what = script[len(calls) - 1]
         if what == "timeout":
             raise subprocess.TimeoutExpired(cmd, timeout)
+        if isinstance(what, tuple) and what[0] == "timeout_after_line":
+            raise subprocess.TimeoutExpired(cmd, timeout, output=what[1].encode())
         code, out = what
         return subprocess.CompletedProcess(cmd, code, stdout=out)
 
@@ -292,3 +294,11 @@ def test_measure_runs_the_token_check_and_the_timed_loops(monkeypatch):
     assert m.resets == 1 and m.steps == tune.N_CHECK_TOKENS + 60 and m.starts == [16, 46]
     assert toks.shape == (tune.N_CHECK_TOKENS, 1) and toks[:, 0].tolist() == list(range(1, 17))
     assert us == pytest.approx(3.0 * 1e3 / 30)
+
+
+def test_bench_supervisor_accepts_the_line_of_a_worker_that_hangs_afterwards(monkeypatch, capsys):
+    import bench
+    run = _fake_run([("timeout_after_line", LINE + "\n")])
+    monkeypatch.setattr(bench.subprocess, "run", run)
+    assert bench.supervise([]) == 0 and len(run.calls) == 1
+    assert capsys.readouterr().out.strip() == LINE
