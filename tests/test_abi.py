@@ -71,3 +71,28 @@ def test_missing_library_fails_loudly(tmp_path):
     from hqq_b200 import _lib
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_decode_desc_ctypes_mirror_matches_the_c_struct(tmp_path):
+    """`hqq_b200_decode_desc` (include/hqq_b200.h) against its ctypes mirror (hqq_b200/_lib.py): same size, same field names and
+    offsets -- compiled with the system C compiler, so a drifting header or mirror fails here and not as a wild pointer on the GPU."""
+    import ctypes
+    import shutil
+    import subprocess
+    from hqq_b200._lib import DecodeDesc
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = [f[0] for f in DecodeDesc._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "hqq_b200.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(hqq_b200_decode_desc));\n'
+                   + "".join(f'  printf("{n} %zu\\n", offsetof(hqq_b200_decode_desc, {n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run([cc, "-x", "c", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(DecodeDesc)
+    for n in names:
+        assert int(out[n]) == getattr(DecodeDesc, n).offset, n
