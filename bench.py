@@ -552,6 +552,10 @@ def run_gpu(args, rank, world, local_rank):
             line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
         if roof is not None:
             line["roofline"] = roof
+        if args.worker:
+            # supervised run: hand the finished measurement to the supervisor right away (it keeps the LAST line it receives), so
+            # that nothing below can cost it even if this process were killed
+            print(json.dumps(_finite(dict(line, extras="preliminary line: the worker did not finish its extra objects"))), flush=True)
         # Everything below adds objects to the line that is already complete (probes in sub-processes, quantizer, CPU baselines).
         # A watchdog prints the line as it stands if they ever exceed their deadline, so they cannot cost the measurement.
         printed = threading.Event()
@@ -614,7 +618,7 @@ def run_gpu(args, rank, world, local_rank):
         os._exit(0)
 
 
-def supervise(argv, first_timeout_s=900.0, retry_timeout_s=900.0):
+def supervise(argv, first_timeout_s=720.0, retry_timeout_s=600.0):
     """N = 1 with the autotuner on: the measurement runs in a worker process.  The tuner re-captures the decode graph under kernel
     variants inside the measuring process (after each has survived its own guard process); should that process still die or hang,
     the measurement is repeated once with the default kernels only, so a tuner failure can never cost the bench line."""

@@ -106,8 +106,9 @@ def _args(**kw):
 def test_run_gpu_assembles_the_line_with_the_autotuner(fake_gpu, capsys):
     bench.run_gpu(_args(), 0, 1, 0)
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
-    assert len(out) == 1
-    d = json.loads(out[0])
+    assert len(out) == 2 and "preliminary" in json.loads(out[0])["extras"]   # worker mode: the measurement first, the full line last
+    assert json.loads(out[0])["value"] == json.loads(out[1])["value"] and "extras" not in json.loads(out[1])
+    d = json.loads(out[-1])
     assert d["metric"] == bench.METRIC and d["n_gpus"] == 1 and d["steps"] == 20 and d["higher_is_better"] is True
     assert d["value"] == pytest.approx(20 / 0.4) and d["e2e"]["value"] == pytest.approx(20 / 0.4)
     at = d["config"]["autotune"]
@@ -138,3 +139,8 @@ def test_run_gpu_survives_a_failing_tuner(fake_gpu, capsys, monkeypatch):
     d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
     assert "recapture failed" in d["config"]["autotune"]["error"] and d["value"] > 0
     assert FakeModel.built[0].retuned[-1] == {}                           # back on the default kernels
+
+
+def test_run_gpu_prints_exactly_one_line_when_it_is_not_a_supervised_worker(fake_gpu, capsys):
+    bench.run_gpu(_args(worker=False, no_autotune=True, no_probes=True, no_cpu_baseline=True), 0, 1, 0)
+    assert len([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]) == 1

@@ -302,3 +302,12 @@ def test_bench_supervisor_accepts_the_line_of_a_worker_that_hangs_afterwards(mon
     monkeypatch.setattr(bench.subprocess, "run", run)
     assert bench.supervise([]) == 0 and len(run.calls) == 1
     assert capsys.readouterr().out.strip() == LINE
+
+
+def test_bench_supervisor_prefers_the_final_line_and_falls_back_to_the_preliminary_one(monkeypatch, capsys):
+    import bench
+    pre = json.dumps({"metric": "m", "value": 1.0, "extras": "preliminary line", "config": {"autotune": None}})
+    monkeypatch.setattr(bench.subprocess, "run", _fake_run([(0, pre + "\n" + LINE + "\n")]))
+    assert bench.supervise([]) == 0 and capsys.readouterr().out.strip() == LINE
+    monkeypatch.setattr(bench.subprocess, "run", _fake_run([("timeout_after_line", pre + "\n")]))
+    assert bench.supervise([]) == 0 and json.loads(capsys.readouterr().out.strip())["extras"] == "preliminary line"
