@@ -59,7 +59,7 @@ def shard_dims(shape: LlamaShape, tp: int):
 class DecodeModel:
     def __init__(self, shape: LlamaShape = LLAMA3_8B, nbits: int = 4, group_size: int = 64, dtype=torch.float16,
                  device="cuda", cache_len: int = 256, tp: int = 1, rank: int = 0, seed: int = 0, process_group=None,
-                 n_layers: int | None = None, fused=5, tp_mode: str | None = None, batch: int = 1):
+                 n_layers: int | None = None, fused=5, tp_mode: str | None = None, batch: int = 1, shard_from_full: bool = False):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
         # batch > 1 (BASELINE configs[4], bs = 32): `batch` sequences decode in lock-step at the same position; the linears then
         # run the fused small-M kernel (M = batch <= 32) between framework glue ops -- the one-token glue kernels and the fused
@@ -100,10 +100,23 @@ class DecodeModel:
         self.final_norm = torch.ones(shape.hidden, device=self.device, dtype=dtype)
         self.blocks = []
         self.quantized_weights = 0
+        # shard_from_full: every rank draws the FULL matrices from the shared generator, quantises them unsharded and cuts its shard out
+        # of the quantised tensors (models/tp.py) -- the tensor-parallel model then computes the very function of the one-GPU model
+        # (same levels, scales, zeros), which per-shard quantisation of per-rank random weights (the default, cheaper) does not
+        full_dims = shard_dims(shape, 1)
+        par = {"q": "column", "k": "column", "v": "column", "gate": "column", "up": "column", "o": "row", "down": "row"}
         for _ in range(self.n_layers):
             blk = {}
             for name, (n, k) in dims.items():
-                blk[name] = HQQLinear.from_weights(rnd(n, k, g), None, cfg, compute_dtype=dtype, device=str(self.device))
+                if shard_from_full and tp > 1:
+                    from .models.tp import shard_hqq_linear
+                    fn, fk = full_dims[name]
+                    full = HQQLinear.from_weights(rnd(fn, fk, gshared), None, cfg, compute_dtype=dtype, device=str(self.device))
+                    blk[name] = shard_hqq_linear(full, tp, rank, par[name])
+                    del full
+                else:
+                    blk[name] = HQQLinear.from_weights(rnd(n, k, gshared if shard_from_full else g), None, cfg, compute_dtype=dtype,
+                                                       device=str(self.device))
                 self.quantized_weights += n * k
             blk["norm1"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)
             blk["norm2"] = torch.ones(shape.hidden, device=self.device, dtype=dtype)

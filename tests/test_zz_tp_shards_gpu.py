@@ -36,3 +36,19 @@ def test_shards_dequantise_to_slices_and_recombine(nbits):
     assert (y_row.float() - y_full.float()).norm() / y_full.float().norm() <= 2e-3
     sd = shard_hqq_linear(layer, tp, 1, "column").state_dict()             # a shard serialises like any HQQLinear
     assert tuple(int(v) for v in sd["shape"]) == (N // tp, K)
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; not yet seen on a GPU")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tensor_parallel_model_equals_the_one_gpu_model_on_the_same_quantised_weights():
+    """tools/tp_vs_single.py: shards cut out of the unsharded quantisation -> TP = 2 decodes the one-GPU model's tokens."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29547", os.path.join(root, "tools", "tp_vs_single.py")], capture_output=True, text=True, timeout=300)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("AGREE")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    agree = int(line[-1].split()[1])
+    assert agree >= 14 and "first4 True" in line[-1], line[-1]
