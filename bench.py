@@ -39,8 +39,8 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(d["hbm_gbs"]), "tensor_tflops": float(d.get("bf16_tflops", 1590.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -84,14 +84,43 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def host_topology():
+    """(physical cores of ONE socket, sockets, logical cpus) from /proc/cpuinfo; falls back to os.cpu_count()."""
+    try:
+        cores, phys, cur = set(), set(), {}
+        for ln in open("/proc/cpuinfo"):
+            if ":" in ln:
+                k, v = [t.strip() for t in ln.split(":", 1)]
+                cur[k] = v
+            elif cur:
+                if "physical id" in cur and "core id" in cur:
+                    cores.add((cur["physical id"], cur["core id"])); phys.add(cur["physical id"])
+                cur = {}
+        if cores:
+            return max(1, len(cores) // max(1, len(phys))), max(1, len(phys)), os.cpu_count() or 1
+    except OSError:
+        pass
+    n = os.cpu_count() or 1
+    return n, 1, n
+
+
+def pin_openmp_env():
+    """Called before anything loads libgomp: one thread per physical core, packed (the CPU arm's team stays on one socket's cores)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
 def _cpu_oracle():
-    """(forward factory, cores, label): the C/OpenMP restatement (oracle/hqq_oracle_c.c, all host threads) when it builds here,
-    else the numpy port (element-wise passes single-threaded, BLAS matmul).  bench.py's cpu_baseline / --impl reference legs are
-    the only product-side places that may execute oracle/ (it is the thing timed here, never the thing shipped)."""
+    """(forward factory, cores, label, module): the C/OpenMP restatement (oracle/hqq_oracle_c.c) with its team pinned to the physical
+    cores of ONE socket -- the same team in `--impl reference` and in the GPU arm's cpu_baseline leg, whatever OMP_NUM_THREADS the
+    launcher exported (torchrun sets 1) -- else the numpy port.  bench.py's cpu_baseline / --impl reference legs are the only
+    product-side places that may execute oracle/ (it is the thing timed here, never the thing shipped)."""
     try:
         from oracle import hqq_oracle_c as c
-        cores = c.threads()
-        return (lambda W_q, meta: c.Forward(W_q, meta)), cores, f"C/OpenMP port (oracle/hqq_oracle_c.c, {cores} threads)", c
+        per_socket, sockets, logical = host_topology()
+        cores = c.set_threads(per_socket)
+        return ((lambda W_q, meta: c.Forward(W_q, meta)), cores,
+                f"C/OpenMP port (oracle/hqq_oracle_c.c, {cores} threads = one socket's physical cores of {sockets} x {per_socket}, {logical} logical cpus)", c)
     except Exception:  # noqa: BLE001 -- no C compiler / no OpenMP: the numpy port
         from oracle import hqq_oracle as o
         return (lambda W_q, meta: (lambda x: o.linear_forward_f32_fast(x, W_q, meta))), 1, "numpy port (oracle/hqq_oracle.py; BLAS matmul may use more threads)", None
@@ -100,11 +129,11 @@ def _cpu_oracle():
 class CpuReference:
     """HQQBackend.PYTORCH on the host: per linear, dequantise the whole matrix (unpack, subtract, multiply: three passes over an
     N x K float32 matrix) then matmul (quantize.py:184-199, 880-898), float32 compute dtype (the reference's CPU path), through the
-    oracle port.  One `sample()` = a bounded number of passes over ONE of the 32 blocks (7 linears, bs=1) plus 1/8 of the fp32
-    lm_head GEMV; the per-token figure extrapolates x32 blocks."""
+    oracle port.  One `step()` = ONE of the 32 blocks (7 linears, bs=1) plus 1/32 of the fp32 lm_head GEMV, i.e. 1/32 of a token."""
 
     SHAPES = {"q": (4096, 4096), "k": (1024, 4096), "v": (1024, 4096), "o": (4096, 4096), "gate": (14336, 4096), "up": (14336, 4096),
               "down": (4096, 14336)}
+    STEPS_PER_TOKEN = 32
 
     def __init__(self):
         import numpy as np
@@ -117,35 +146,39 @@ class CpuReference:
             meta = {"nbits": 4, "group_size": 64, "shape": (n, k), "axis": 1, "packing": "4bit_u8",
                     "scale": (rng.rand(R, 1) * 0.01 + 1e-3).astype(np.float32), "zero": (rng.rand(R, 1) * 15).astype(np.float32)}
             self.layers.append((make(W_q, meta), rng.randn(1, k).astype(np.float32)))
-        self.lm = rng.randn(16032, 4096).astype(np.float32)  # 1/8 of the 128256-row fp32 lm_head
+        self.lm = rng.randn(128256 // self.STEPS_PER_TOKEN, 4096).astype(np.float32)  # 1/32 of the 128256-row fp32 lm_head
         self.xv = rng.randn(4096).astype(np.float32)
-        self.block()  # untimed pass: page the scratch matrices in
+        self.step()  # untimed pass: page the scratch matrices in
 
-    def block(self):
+    def step(self):
         for f, x in self.layers:
             f(x)
+        self.lm @ self.xv
 
-    def sample(self, budget_s: float = 6.0):
-        t0 = time.perf_counter()
-        reps = 0
-        while True:
-            self.block()
-            reps += 1
-            el = time.perf_counter() - t0
-            if el > budget_s or reps >= 64 or (reps >= 3 and el > min(budget_s, 4.0)):
+    def run(self, steps: int, warmup: int, budget_s: float):
+        """`warmup` untimed + up to `steps` timed steps (stops early once `budget_s` is spent, never before 10 steps); returns
+        (tokens/s over the timed steps, info with min / median / max of five chunk means and the stability verdict)."""
+        for _ in range(max(0, warmup)):
+            self.step()
+        times = []
+        t_all = time.perf_counter()
+        for i in range(max(1, steps)):
+            t0 = time.perf_counter()
+            self.step()
+            times.append(time.perf_counter() - t0)
+            if i + 1 >= 10 and time.perf_counter() - t_all > budget_s:
                 break
-        block_s = (time.perf_counter() - t0) / reps
-        t1 = time.perf_counter()
-        for _ in range(3):
-            self.lm @ self.xv
-        lm_s = (time.perf_counter() - t1) / 3 * 8
-        tok_s = 1.0 / (block_s * 32 + lm_s)
-        return tok_s, {"block_s": block_s, "lm_head_s": lm_s, "cores": self.cores, "port": self.label,
-                       "sample": f"{reps}x one block (7 HQQ linears, dequantise+matmul, fp32, bs=1) + 1/8 lm_head; x32 blocks extrapolated; {self.label}"}
-
-
-def cpu_reference_tokens_per_s(budget_s: float = 15.0):
-    return CpuReference().sample(budget_s)
+        n = len(times)
+        tok_s = n / (sum(times) * self.STEPS_PER_TOKEN)
+        k = max(1, n // 5)
+        chunks = [sum(times[i:i + k]) / len(times[i:i + k]) for i in range(0, n - n % k if n >= 5 else n, k)][:5]
+        lo, hi = min(chunks), max(chunks)
+        info = {"steps_timed": n, "cores": self.cores, "port": self.label,
+                "tokens_per_s_min_median_max": [1.0 / (hi * self.STEPS_PER_TOKEN), 1.0 / (statistics.median(chunks) * self.STEPS_PER_TOKEN),
+                                                1.0 / (lo * self.STEPS_PER_TOKEN)],
+                "stable": (hi / lo) <= 1.3,
+                "sample": f"{n} steps, each ONE block (7 HQQ linears, dequantise+matmul, fp32, bs=1) + 1/32 of the lm_head GEMV = 1/32 token; {self.label}"}
+        return tok_s, info
 
 
 def cpu_quantizer_baseline():
@@ -164,29 +197,51 @@ def cpu_quantizer_baseline():
 
 
 def run_reference(args, rank, world):
-    """--impl reference: rank 0 times the reference's CPU path (the oracle port, every host thread it can use) on bounded samples
-    of the workload; at most 1 warm-up and 3 timed samples so that the default --steps/--warmup finish within a minute or two."""
+    """--impl reference: rank 0 times the reference's CPU path (the oracle port, team pinned to one socket's physical cores) on the
+    arm's own --steps / --warmup, a step being 1/32 of a token (one block + 1/32 of the lm_head).  Unstable timings (max/min of five
+    chunk means > 1.3) are measured again, up to three times; the line says whether the last attempt was stable."""
     if rank != 0:
         return
     ref = CpuReference()
-    warm, steps = min(args.warmup, 1), max(1, min(args.steps, 3))
-    vals, info = [], None
-    for i in range(warm + steps):
-        v, info = ref.sample(budget_s=6.0)
-        if i >= warm:
-            vals.append(v)
-    value = statistics.median(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-            "warmup": warm, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+    for attempt in range(3):
+        value, info = ref.run(args.steps, args.warmup if attempt == 0 else 1, budget_s=100.0)
+        if info["stable"]:
+            break
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps_timed"],
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value / ref.STEPS_PER_TOKEN, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "path": "HQQBackend.PYTORCH data flow (dequantise + matmul) on the host cores: " + info["port"]},
+            "config": {"workload": WORKLOAD, "path": "HQQBackend.PYTORCH data flow (dequantise + matmul) on the host cores: " + info["port"],
+                       "step": "1/32 token (one of the 32 blocks + 1/32 of the lm_head); value = steps / (32 x time)", "attempts": attempt + 1},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "host_cores": os.cpu_count() or 1, "kind": "port",
-                             "sample": info["sample"]},
+                             "sample": info["sample"], "min_median_max": info["tokens_per_s_min_median_max"], "stable": info["stable"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def _time_graph(torch, dev, fn, reps):
+    """Capture `reps` x fn() into a CUDA graph, replay once untimed, then time one replay with CUDA events on the launching stream."""
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    g.replay()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
 def kernel_roofline(model, torch, peaks, reps=4):
     """Average duration of the fused forward kernel for each of the four launch groups a decode step issues per block
     (q+k+v, o, gate+up, down -- the matrices that share an activation go out in ONE launch).  All launches of one group over
@@ -205,57 +260,41 @@ def kernel_roofline(model, torch, peaks, reps=4):
         Ns = [l.meta["shape"][0] for l in sets[0]]
         x = torch.randn(1, K, device=dev).to(model.dtype)
         outs = [torch.empty(1, N, device=dev, dtype=model.dtype) for N in Ns]
-
         # the MLP launch ships with the silu*mul epilogue (gate and up rows paired per tile, one output vector)
-        x_op = ops.YOP_SILU_MUL_PAIR if (gname == "gate_up" and model.pair_silu and model.nbits < 8) else 0
+        x_op = ops.YOP_SILU_MUL_PAIR if (gname == "gate_up" and model.nbits < 8) else 0
 
         def run_all():
             for ls in sets:
                 if not ops.decode_linear_fwd(x, ls, outs, x_op):
                     ops.linear_fwd_multi(x, ls, outs)
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            run_all()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(reps):
-                run_all()
-        g.replay()
-        torch.cuda.synchronize(dev)
-        stream = torch.cuda.current_stream(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        g.replay()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / (reps * len(sets))
+        ms = _time_graph(torch, dev, run_all, reps) / len(sets)
         nbytes = sum(N * K * 0.5 + 2 * (N * K // 64) * 2 for N in Ns) + (Ns[0] if x_op else sum(Ns)) * 2 + K * 2
         per[gname] = {"N": Ns, "K": K, "us": round(ms * 1e3, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         tot_bytes += nbytes
         tot_ms += ms
     achieved = tot_bytes / tot_ms / 1e6
-    # dram bytes per launch (average over the four launch groups) from the committed `ncu --set full` capture of these kernels
-    traffic = None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_decode1_traffic.json")) as fh:
-            traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
-    except (OSError, KeyError, ValueError):
-        pass
+    # dram bytes per launch (average over the four launch groups) from the committed `ncu --set full` capture of the shipped kernel
+    traffic, traffic_src = None, None
+    for name in ("r2_decode1_traffic.json", "r1_decode1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                traffic, traffic_src = json.load(fh)["traffic_bytes_per_launch_avg"], "profiles/" + name
+            break
+        except (OSError, KeyError, ValueError):
+            continue
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": traffic, "algorithmic_bytes_per_launch": tot_bytes / len(groups), "kernel": "hqq::linear_decode1_kernel<half,4,64> (4 launches/block, 128/step; D1_VARIANT=" + os.environ.get("HQQ_B200_D1_VARIANT", "0") + ")", "peak_source": peaks["source"],
-            "per_launch_group": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
-            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: profiles/r1_decode1_traffic.json (ncu dram bytes)"}
+            "traffic": traffic, "algorithmic_bytes_per_launch": tot_bytes / len(groups),
+            "kernel": "hqq::linear_decode1_kernel<half,4,64,...,MR=1> (scale/zero on the cp.async ring; 4 launches/block, 128/step)",
+            "peak_source": peaks["source"], "per_launch_group": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
+            "note": f"event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: {traffic_src} (ncu dram bytes)"}
 
 
-def quantizer_roofline(torch, peaks, dev, reps=3, fast_ok=False):
+def quantizer_roofline(torch, peaks, dev, reps=3):
     """North-star path (a): Quantizer.quantize (min/max init + proximal solver + round + pack) of ONE Llama-3-8B block's seven
     matrices (218 M weights, fp16 source, 4-bit gs=64 axis=1, 20 iterations max), timed with CUDA events on the launching stream.
-    Algorithmic bytes: N*K*(2 + 0.5) + 2*(N*K/64)*4 per matrix.  Reported next to the decode roofline; the solver is
-    instruction-bound by construction, so the HBM fraction is a ceiling statement, not a tuning target."""
+    Algorithmic bytes: N*K*(2 + 0.5) + 2*(N*K/64)*4 per matrix.  The solver is bound by instruction issue, not HBM
+    (ncu 75 % issue-active), so the HBM fraction is reported as SURVEY 8d asks and explained there."""
     from hqq_b200 import ops
     shapes = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
     g = torch.Generator(device=dev)
@@ -267,44 +306,74 @@ def quantizer_roofline(torch, peaks, dev, reps=3, fast_ok=False):
         for W in Ws:
             ops.quantize(W, 4, 64, 1, True, True)
 
-    def timed():
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
         run()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            run()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / reps
-
-    ms = timed()
-    extra = {}
-    pinned = "HQQ_B200_SOLVER_VARIANT" in os.environ
-    if fast_ok and not pinned:
-        # the fast solver (exact shortcuts) was bit-identical to the default one in its own probe process: check
-        # that again here on this workload, time it, and report the faster of the two as this object's figure
-        ref = [ops.quantize(W, 4, 64, 1, True, True) for W in Ws[:4]]
-        os.environ["HQQ_B200_SOLVER_VARIANT"] = "1"
-        try:
-            got = [ops.quantize(W, 4, 64, 1, True, True) for W in Ws[:4]]
-            same = all(torch.equal(x, y) for r, g_ in zip(ref, got) for x, y in zip(r[:3], g_[:3]))
-            ms_fast = timed() if same else None
-        finally:
-            os.environ.pop("HQQ_B200_SOLVER_VARIANT", None)
-        extra = {"default_ms_per_block": ms, "fast_ms_per_block": ms_fast, "fast_bit_identical": same}
-        if same and ms_fast < ms:
-            ms = ms_fast
-            extra["selected"] = "HQQ_B200_SOLVER_VARIANT=1"
-        else:
-            extra["selected"] = "default"
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
     weights = sum(n * k for n, k in shapes)
     nbytes = sum(n * k * 2.5 + 2 * (n * k // 64) * 4 for n, k in shapes)
     achieved = nbytes / ms / 1e6
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "ms_per_block": ms, "gweights_per_s": weights / ms / 1e6, "algorithmic_bytes_per_block": nbytes,
-            "solver_variant": os.environ.get("HQQ_B200_SOLVER_VARIANT", extra.get("selected", "0")), **extra,
-            "workload": "one Llama-3-8B block (7 matrices, 218 M weights) fp16 -> 4-bit gs=64 axis=1, solver + pack, 3 launches per matrix"}
+            "kernel": "solver_axis1_kernel + stop_kernel + quant_pack_kernel (3 launches per matrix)",
+            "workload": "one Llama-3-8B block (7 matrices, 218 M weights) fp16 -> 4-bit gs=64 axis=1, solver + pack"}
+
+
+def gemm_sweep(torch, peaks, dev, quick=False):
+    """BASELINE configs[2] / the second half of `metric`: the fused dequant-GEMM (hqq_b200_linear_fwd, tcgen05 route) on the
+    per-linear sweep -- (N, K) in {4096x4096, 11008x4096, 4096x11008} x nbits {8,4,3,2,1}, gs 64, fp16 -- at M = 4096 (tensor
+    roofline) and M = 128, event-timed alone, against the measured dense tensor peak; cuBLAS on the pre-dequantised matrix
+    beside it.  3-bit has no tcgen05 route yet: its figure is our dequantize kernel + the library GEMM."""
+    from hqq_b200 import ops
+    from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
+    peak_tf = peaks["tensor_tflops"]
+    per = {}
+    torch.manual_seed(0)
+    shapes = [(4096, 4096)] if quick else [(4096, 4096), (11008, 4096), (4096, 11008)]
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    for nbits in ((4,) if quick else (8, 4, 3, 2, 1)):
+        for N, K in shapes:
+            layer = HQQLinear.from_weights((torch.randn(N, K, device=dev) * 0.02).half(), None, BaseQuantizeConfig(nbits=nbits, group_size=64, axis=1),
+                                           compute_dtype=torch.float16, device=str(dev))
+            Wd = layer.dequantize()
+            for M in (4096, 128):
+                x = torch.randn(M, K, device=dev).half()
+                y = torch.empty(M, N, device=dev, dtype=torch.float16)
+                route = ops.linear_route(M, N, K, 64, nbits, 1, x.dtype)
+                if route != 0:
+                    fn = lambda: ops.linear_fwd(x, layer.W_q, layer.meta["scale"], layer.meta["zero"], None, N, K, 64, nbits, 1, out=y)
+                else:
+                    fn = lambda: layer(x)
+                with torch.no_grad():
+                    ms = timed(fn, 5)
+                    ms_lib = timed(lambda: torch.matmul(x, Wd.t(), out=y), 5)
+                tf = 2.0 * M * N * K / ms / 1e9
+                per[f"b{nbits}_{N}x{K}_M{M}"] = {"us": round(ms * 1e3, 1), "TFLOPs": round(tf, 1), "frac_of_tensor_peak": round(tf / peak_tf, 4), "route": route,
+                                               "cublas_on_dequantised_TFLOPs": round(2.0 * M * N * K / ms_lib / 1e9, 1)}
+            del layer, Wd
+    head = per["b4_4096x4096_M4096"]
+    return {"bound": "tensor", "achieved": head["TFLOPs"], "peak": peak_tf, "unit": "TFLOP/s", "frac": head["frac_of_tensor_peak"],
+            "shape": "M=4096 N=4096 K=4096 nbits=4 gs=64 fp16", "kernel": "hqq::gemm::linear_gemm_kernel (persistent tcgen05 / TMA / TMEM)",
+            "peak_source": peaks["source"] + " bf16_tflops (burst: kernel timed alone)", "per": per,
+            "note": "route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit); cuBLAS runs on the 16-bit matrix our dequantize kernel wrote"}
 
 
 def _finite(o):
@@ -318,106 +387,32 @@ def _finite(o):
     return o
 
 
-def run_probes(budget_s=150.0, timeout_s=45.0):
-    """First GPU execution of the kernels written after round 1's GPU budget was spent: each knob runs
-    tools/variant_probe.py in its OWN process under a timeout -- a crash or a hang there cannot reach this process -- on a fixed
-    seeded workload, and is compared with the default kernels (sha256 of the outputs, relative error where the summation order
-    differs by design).  Reported under "experimental"; nothing here touches the timed regions or the default kernels."""
-    import tempfile
-    import torch
-    probe = os.path.join(ROOT, "tools", "variant_probe.py")
-    tmp = tempfile.mkdtemp(prefix="hqq_probe_")
-    t_start = time.perf_counter()
-    base_env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
-
-    def run(what, knob=None, both=None, save=None, timeout_s=timeout_s):
-        if time.perf_counter() - t_start > budget_s:
-            return {"skipped": "probe time budget spent"}
-        env = dict(base_env)
-        if knob:
-            env[knob[0]] = knob[1]
-        cmd = [sys.executable, probe, what]
-        if both:
-            cmd += ["--both", both]
-        if save:
-            cmd += ["--save", save]
-        try:
-            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
-        except subprocess.TimeoutExpired:
-            return {"error": f"timeout after {timeout_s:.0f} s"}
-        for ln in r.stdout.splitlines():
-            if ln.startswith("PROBE "):
-                return json.loads(ln[6:])
-        return {"error": (r.stderr or r.stdout)[-300:].replace("\n", " | ")}
-
-    def against_default(what, knobs):
-        ref_path = os.path.join(tmp, what + "_default.pt")
-        ref = run(what, save=ref_path)
-        out = {"default": ref}
-        for key, val in knobs:
-            path = os.path.join(tmp, f"{what}_{key}_{val}.pt")
-            got = run(what, knob=(key, val), save=path)
-            if "digest" in ref and "digest" in got:
-                got["bit_identical"] = got["digest"] == ref["digest"]
-                got["speedup"] = ref["us"] / got["us"]
-                if not got["bit_identical"]:
-                    try:
-                        a, b = torch.load(ref_path, weights_only=True), torch.load(path, weights_only=True)
-                        got["rel_err"] = max(float((x.double() - y.double()).norm() / x.double().norm().clamp_min(1e-30)) if x.shape == y.shape
-                                             else float("inf") for x, y in zip(a, b))
-                    except Exception as e:  # noqa: BLE001
-                        got["rel_err"] = repr(e)[:100]
-            out[f"{key}={val}"] = got
-        return out
-
-    res = {"gemm_sweep": run("gemm_sweep", timeout_s=80.0),
-           "bitpack": run("bitpack"),
-           "solver_fast": run("quant", both="HQQ_B200_SOLVER_VARIANT=1"),
-           "fused_3bit": run("l3", both="HQQ_B200_FUSED_3BIT=1"),
-           # the three cheapest GEMM experiments; ld / ld512 / split-K are timed by tools/variant_sweep.sh (the bench must stay short)
-           "gemm": against_default("gemm", [("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_VARIANT", "un512")])}
-    res["seconds"] = round(time.perf_counter() - t_start, 1)
-    return res
-
-
-def _attach_sweeps(line, peaks):
-    """Move the gemm_sweep / bitpack probe results out of `experimental` into objects of their own, with fractions of the measured peaks."""
-    sweep = (line.get("experimental") or {}).pop("gemm_sweep", None)
-    if isinstance(sweep, dict) and "per" in sweep:
-        # BASELINE configs[2] / metric (2): fused dequant-GEMM TFLOP/s against the measured dense bf16/fp16 tensor peak
-        peak_tf = None
-        try:
-            peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-        except Exception:  # noqa: BLE001
-            peak_tf = 2250.0
-        for e in sweep["per"].values():
-            e["frac_of_tensor_peak"] = round(e["TFLOPs"] / peak_tf, 4)
-        line["gemm_sweep"] = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "headline": "b4_4096x4096_M4096",
-                              "achieved": sweep["per"]["b4_4096x4096_M4096"]["TFLOPs"],
-                              "frac": sweep["per"]["b4_4096x4096_M4096"]["frac_of_tensor_peak"], "per": sweep["per"],
-                              "note": "default kernels, event-timed alone (burst peak); route 2 = fused tcgen05 kernel, 0 = dequantize kernel + library GEMM (3-bit)"}
-        # the opt-in GEMM kernels that reproduced the default kernel's outputs bit for bit in their probes: report the fastest
-        # beside the default figure (same shape, same process-per-knob protocol); the headline stays the default kernel's
-        best = None
-        for name, r in ((line.get("experimental") or {}).get("gemm") or {}).items():
-            tf = ((r.get("per") or {}).get("4096x4096xM4096") or {}).get("TFLOPs") if isinstance(r, dict) else None
-            if name != "default" and isinstance(r, dict) and r.get("bit_identical") and tf and (best is None or tf > best[1]):
-                best = (name, tf)
-        if best is not None:
-            line["gemm_sweep"]["best_bit_identical_variant"] = {"knob": best[0], "TFLOPs": best[1], "frac": round(best[1] / peak_tf, 4),
-                                                                "shape": "4096x4096xM4096"}
-    elif sweep is not None:
-        line["gemm_sweep"] = sweep
-    bp = (line.get("experimental") or {}).pop("bitpack", None)
-    if isinstance(bp, dict) and "per" in bp:
-        # SURVEY 8(d): pack / unpack / dequantize against the measured HBM peak (default kernels, own process)
-        for e in bp["per"].values():
-            e["frac_of_hbm_peak"] = round(e["GBps"] / peaks["hbm_gbs"], 4)
-        line["bitpack"] = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "headline": "b4_dequantize_f16",
-                           "achieved": bp["per"]["b4_dequantize_f16"]["GBps"], "frac": bp["per"]["b4_dequantize_f16"]["frac_of_hbm_peak"],
-                           "per": bp["per"], "note": "one 14336x4096 matrix per call, inputs cycled (cold L2), algorithmic bytes = input + output"}
-    elif bp is not None:
-        line["bitpack"] = bp
+def tokens_agree(model, torch, n_tokens=16):
+    """N > 1: before anything is timed, decode `n_tokens` greedy tokens from the same state with the fused NVLink exchange ("p2p") and
+    with NCCL all-reduce between the kernels ("nccl"); the streams must be identical on every rank.  Leaves the model captured in the
+    mode it came with.  Returns (agree, tokens)."""
+    import torch.distributed as dist
+    want = model.tp_mode
+    streams = {}
+    for mode in ("nccl", "p2p") if want == "p2p" else ("p2p", "nccl"):
+        model.tp_mode = mode
+        model.graph = None
+        model.capture(warmup=2)
+        model.reset_state(token=1)
+        toks = []
+        for _ in range(n_tokens):
+            model.decode()
+            toks.append(model.next_tok.clone())
+        torch.cuda.synchronize(model.device)
+        streams[mode] = torch.stack(toks).view(-1)
+    same = torch.equal(streams["p2p"], streams["nccl"])
+    flag = torch.tensor([1 if same else 0], device=model.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if model.tp_mode != want:
+        model.tp_mode = want
+        model.graph = None
+        model.capture(warmup=2)
+    return bool(flag.item()), streams[want].tolist()
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -432,7 +427,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     lib = _lib.load()
-    big = args.model == "70b"  # BASELINE configs[4] (bs = 1 leg): needs --gpus 8 (4.8 GB of packed weights per rank); not the default line
+    big = args.model == "70b"  # BASELINE configs[4]: needs --gpus 8 (4.8 GB of packed weights per rank); not the default line
     shape = harness.LLAMA3_70B if big else harness.LLAMA3_8B
     metric = "llama3_70b_4bit_gs64_decode_tokens_per_s" if big else METRIC
     workload = ("Llama-3-70B-shaped decode bs=1 seq=1, 80 blocks x 7 HQQLinear 4-bit gs=64 axis=1, fp16 lm_head (BASELINE configs[4], bs=1)"
@@ -444,43 +439,18 @@ def run_gpu(args, rank, world, local_rank):
     if B > 1:  # BASELINE configs[4] bs = 32 leg: not the default line
         metric += f"_bs{B}"
         workload = workload.replace("bs=1", f"bs={B}")
-    # Decode autotuner (hqq_b200/tune.py): kernel variants and prefetch hints that leave every result unchanged are first run in a
-    # child process (crash / hang / token guard), the survivors are then timed on this very model and the fastest stays captured.
-    from hqq_b200 import tune
-    autotune = None
-    do_tune = world == 1 and not big and B == 1 and not args.no_autotune and tune.autotune_enabled()
-    guard = None
-    if do_tune:
-        t_tune = time.perf_counter()
-        try:
-            guard = tune.guard_decode(budget_s=args.autotune_budget)
-        except Exception as e:  # noqa: BLE001 -- the tuner must never cost the bench line
-            autotune = {"error": repr(e)[:200]}
+    lib.hqq_b200_launch_count_reset()
     model = harness.DecodeModel(shape, nbits=4, group_size=64, dtype=torch.float16, device=dev, cache_len=args.cache_len, tp=world,
                                 rank=rank, process_group=pg, n_layers=n_layers, batch=B)
-    selected = {}
-    if guard is not None:
-        try:
-            model.capture(warmup=3)
-            rep = tune.choose_decode(model, guard)
-            selected = rep["selected"]
-            autotune = {"selected": tune.knob_label(selected), "gain_vs_default": rep["gain"], "default_us": rep["default_us"],
-                        "selected_us": rep["selected_us"],
-                        "guard": [{"knobs": tune.knob_label(r["knobs"]), **{k: v for k, v in r.items() if k in ("us", "identical", "speedup", "error")}}
-                                  for r in guard],
-                        "in_process": [{**t, "knobs": tune.knob_label(t["knobs"])} for t in rep["tried"]],
-                        "seconds": round(time.perf_counter() - t_tune, 1),
-                        "note": "candidates select bit-identical kernels / add L2 prefetch hints; kept only if the token stream equals the default's"}
-        except Exception as e:  # noqa: BLE001
-            autotune = {"error": repr(e)[:200]}
-            selected = {}
     lib.hqq_b200_launch_count_reset()
-    if do_tune:
-        model.retune(selected, warmup=3)
-    else:
-        model.capture(warmup=3)
+    model.capture(warmup=3)
     # launches of OUR kernels in one step = those issued while capturing one step (3 warm-up steps + 1 captured)
     launches_per_step = int(lib.hqq_b200_launch_count()) // 4
+    agree = None
+    if world > 1 and B == 1 and not args.no_token_check:
+        agree, _ = tokens_agree(model, torch)
+        if not agree:
+            raise RuntimeError("bench.py: the fused NVLink exchange and the NCCL all-reduce decode different tokens -- refusing to time a wrong model")
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -489,9 +459,10 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident loop -------------------------------------------------------------------
-    model.tok.fill_(1); model.pos.zero_()
+    model.reset_state(token=1)
     for _ in range(max(args.warmup, 3)):
         model.decode()
+    model.pos.zero_()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -511,6 +482,7 @@ def run_gpu(args, rank, world, local_rank):
     model.pos.zero_()
     for _ in range(3):
         model.tok.copy_(h_in, non_blocking=True); model.graph.replay(); h_out.copy_(model.next_tok, non_blocking=True); torch.cuda.synchronize(dev)
+    model.pos.zero_()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(stream)
@@ -531,33 +503,30 @@ def run_gpu(args, rank, world, local_rank):
         dev_ms, e2e_ms = t.tolist()
 
     peaks = load_peaks()
-    roof = kernel_roofline(model, torch, peaks) if (rank == 0 and world == 1 and B == 1) else None
+    roof = kernel_roofline(model, torch, peaks) if (rank == 0 and B == 1) else None
     if rank == 0:
-        scale_layers = shape.n_layers / n_layers
         value = args.steps * B / (dev_ms / 1e3)
         e2e = args.steps * B / (e2e_ms / 1e3)
-        bytes_tok = model.bytes_per_token() * world  # whole-job bytes (each rank streams 1/world of the blocks + full lm_head)
+        bytes_rank = model.bytes_per_token()  # per rank: its shard of every block + its vocabulary shard of the lm_head
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic",
                 "config": {"workload": workload,
-                           "path": f"fused sm_100a kernels, kv cache {args.cache_len}, CUDA graph; {model.bytes_per_token() / 1e9:.2f} GB streamed per step "
+                           "path": f"fused sm_100a kernels, kv cache {args.cache_len}, CUDA graph; {bytes_rank / 1e9:.2f} GB streamed per step and rank "
                                    ">> 126 MB L2 (inputs larger than L2, no flush needed)",
-                           "parallelism": f"tp{world}", "layers": n_layers, "global_batch": B, "autotune": autotune},
+                           "parallelism": f"tp{world}", "layers": n_layers, "global_batch": B,
+                           "tp_mode": (model.tp_mode if (world > 1 and B == 1) else ("nccl" if world > 1 else None)), "tokens_agree": agree},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B},
                 "gpu_launches": launches_per_step * args.steps,
-                "step_hbm_GBps": bytes_tok / world / (dev_ms / args.steps) / 1e6}
-        if scale_layers != 1.0:
+                "step_hbm_GBps_per_rank": bytes_rank / (dev_ms / args.steps) / 1e6}
+        if n_layers != shape.n_layers:
             line["config"]["note"] = "REDUCED layer count (debug run) -- not the BASELINE configuration"
         if roof is not None:
+            roof["step_frac_of_hbm_peak"] = line["step_hbm_GBps_per_rank"] / peaks["hbm_gbs"]
             line["roofline"] = roof
-        if args.worker:
-            # supervised run: hand the finished measurement to the supervisor right away (it keeps the LAST line it receives), so
-            # that nothing below can cost it even if this process were killed
-            print(json.dumps(_finite(dict(line, extras="preliminary line: the worker did not finish its extra objects"))), flush=True)
-        # Everything below adds objects to the line that is already complete (probes in sub-processes, quantizer, CPU baselines).
-        # A watchdog prints the line as it stands if they ever exceed their deadline, so they cannot cost the measurement.
+        # Everything below adds objects to the line that is already complete (GEMM sweep, quantizer, CPU baselines).  A watchdog
+        # prints the line as it stands if they ever exceed their deadline, so they cannot cost the measurement.
         printed = threading.Event()
 
         def emit():
@@ -578,34 +547,30 @@ def run_gpu(args, rank, world, local_rank):
                 os._exit(0)
 
         threading.Thread(target=watchdog, daemon=True).start()
-        if world == 1 and not big and B == 1:
+        extras = world == 1 and not big and B == 1 and not args.no_extras
+        if extras:
             del model
             torch.cuda.empty_cache()
-        if world == 1 and not big and B == 1 and not args.no_probes:
+            # the driver keeps `roofline` / `cpu_baseline` / `config` of the line: the second half of BASELINE's metric (fused
+            # dequant-GEMM against the tensor roofline) and the quantizer (north-star path a) therefore live INSIDE `roofline`
             try:
-                line["experimental"] = run_probes()
+                line["roofline"]["gemm"] = gemm_sweep(torch, peaks, dev, quick=args.quick_extras)
+            except Exception as e:  # noqa: BLE001 -- an extra object must never cost the bench line
+                line["roofline"]["gemm"] = {"error": repr(e)[:200]}
+            try:
+                line["roofline"]["quantizer"] = quantizer_roofline(torch, peaks, dev)
             except Exception as e:  # noqa: BLE001
-                line["experimental"] = {"error": repr(e)[:200]}
-        try:
-            _attach_sweeps(line, peaks)
-        except Exception as e:  # noqa: BLE001 -- formatting of an extra object must not cost the line
-            line["extras_error"] = repr(e)[:200]
-        if world == 1 and not big and B == 1:
-            try:  # extra object, never allowed to cost the bench line
-                sf = (line.get("experimental") or {}).get("solver_fast") or {}
-                line["quantizer"] = quantizer_roofline(torch, peaks, dev, fast_ok=bool(sf.get("bit_identical")))
-            except Exception as e:  # noqa: BLE001
-                line["quantizer"] = {"error": repr(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and not big and B == 1 and isinstance(line.get("quantizer"), dict) and "ms_per_block" in line["quantizer"]:
+                line["roofline"]["quantizer"] = {"error": repr(e)[:200]}
+        if extras and not args.no_cpu_baseline:
             try:  # the reference's CPU solver (float32, optimize.py:201-255) beside the quantizer object, on a bounded sample
-                line["quantizer"]["cpu_baseline"] = cpu_quantizer_baseline()
+                if "ms_per_block" in line["roofline"].get("quantizer", {}):
+                    line["roofline"]["quantizer"]["cpu_baseline"] = cpu_quantizer_baseline()
             except Exception as e:  # noqa: BLE001
-                line["quantizer"]["cpu_baseline"] = {"error": repr(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and not big and B == 1:
+                line["roofline"]["quantizer"]["cpu_baseline"] = {"error": repr(e)[:200]}
             try:
-                v, info = cpu_reference_tokens_per_s(budget_s=15.0)
+                v, info = CpuReference().run(steps=160, warmup=2, budget_s=20.0)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "host_cores": os.cpu_count() or 1, "kind": "port",
-                                        "sample": info["sample"]}
+                                        "sample": info["sample"], "min_median_max": info["tokens_per_s_min_median_max"], "stable": info["stable"]}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": repr(e)[:200]}
         emit()
@@ -618,41 +583,6 @@ def run_gpu(args, rank, world, local_rank):
         os._exit(0)
 
 
-def supervise(argv, first_timeout_s=720.0, retry_timeout_s=600.0):
-    """N = 1 with the autotuner on: the measurement runs in a worker process.  The tuner re-captures the decode graph under kernel
-    variants inside the measuring process (after each has survived its own guard process); should that process still die or hang,
-    the measurement is repeated once with the default kernels only, so a tuner failure can never cost the bench line."""
-    from hqq_b200 import _lib
-    _lib.load()  # this process reports through the same library (no CUDA work here)
-    me = os.path.abspath(__file__)
-    for extra, timeout_s in ((["--worker"], first_timeout_s), (["--worker", "--no-autotune"], retry_timeout_s)):
-        why = None
-        try:
-            try:
-                r = subprocess.run([sys.executable, me, *argv, *extra], stdout=subprocess.PIPE, text=True, timeout=timeout_s)
-                out, why = r.stdout or "", f"worker exited with code {r.returncode} without a result line"
-            except subprocess.TimeoutExpired as e:  # a worker that printed its line and then hung (teardown) still counts
-                out = e.stdout.decode("utf-8", "replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
-                why = f"worker timed out after {timeout_s:.0f} s"
-            lines = [ln for ln in out.splitlines() if ln.startswith("{") and '"metric"' in ln]
-            if lines:
-                line = lines[-1]
-                if "--no-autotune" in extra:
-                    try:
-                        d = json.loads(line)
-                        d["config"]["autotune"] = {"error": f"autotuned worker failed ({first_why}); measured again with the default kernels"}
-                        line = json.dumps(d)
-                    except Exception:  # noqa: BLE001
-                        pass
-                print(line, flush=True)
-                return 0
-        except Exception as e:  # noqa: BLE001 -- could not even start the worker
-            why = repr(e)[:200]
-        sys.stderr.write(f"bench.py: {why}\n")
-        first_why = why
-    return 1
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -662,19 +592,19 @@ def main():
     ap.add_argument("--cache-len", type=int, default=0, help="KV-cache length; 0 = large enough that the timed loops never wrap (>= 256)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (marks the line as reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-probes", action="store_true", help="skip the experimental-kernel probes (sub-processes, N=1 only)")
-    ap.add_argument("--extras-deadline", type=float, default=330.0, help="seconds the objects added after the measurement (probes, quantizer, "
-                    "CPU baselines) may take before the line is printed without the unfinished ones")
-    ap.add_argument("--worker", action="store_true", help=argparse.SUPPRESS)  # internal: the measuring process of a supervised N=1 run
-    ap.add_argument("--no-autotune", action="store_true", help="time the default kernels only (no decode autotuner; N=1 only anyway)")
-    ap.add_argument("--autotune-budget", type=float, default=90.0, help="seconds the autotuner's guard processes may take")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GEMM sweep / quantizer / CPU baseline objects (N=1 only anyway)")
+    ap.add_argument("--quick-extras", action="store_true", help="GEMM sweep: the 4096^3 4-bit headline only")
+    ap.add_argument("--no-token-check", action="store_true", help="N>1: skip the p2p-vs-nccl token agreement check before timing")
+    ap.add_argument("--extras-deadline", type=float, default=240.0, help="seconds the objects added after the measurement (GEMM sweep, "
+                    "quantizer, CPU baselines) may take before the line is printed without the unfinished ones")
     ap.add_argument("--batch", type=int, default=1, help="sequences decoded in lock-step (BASELINE configs[4]: 32); > 1 uses the fused small-M "
                     "kernel between framework glue ops and NCCL all-reduce")
-    ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] at bs=1 (use with --gpus 8)")
+    ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] (use with --gpus 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    pin_openmp_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -683,10 +613,6 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    if world == 1 and args.gpus <= 1 and not args.worker and not args.no_autotune and args.model == "8b" and args.batch <= 1:
-        from hqq_b200 import tune
-        if tune.autotune_enabled():
-            sys.exit(supervise(sys.argv[1:]))
     run_gpu(args, rank, world, local_rank)
 
 

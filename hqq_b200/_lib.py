@@ -50,6 +50,7 @@ SIGNATURES = {
     "hqq_b200_glue_rope_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hqq_b200_glue_argmax": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "hqq_b200_glue_argmax_key": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     "hqq_b200_launch_count": (c_int64, []),
     "hqq_b200_launch_count_reset": (None, []),
     "hqq_b200_reload_env": (None, []),
@@ -62,9 +63,7 @@ class DecodeDesc(ctypes.Structure):
                 ("count", c_int), ("W_q", c_void_p), ("scale", c_void_p), ("zero", c_void_p), ("bias", c_void_p), ("y", c_void_p),
                 ("N", c_void_p), ("K", c_int64), ("group_size", c_int), ("nbits", c_int), ("dtype", c_int), ("tp", c_int), ("rank", c_int),
                 ("peer_data", c_void_p), ("red_data", c_void_p), ("y_tagged", c_void_p), ("x_tagged", c_void_p), ("x2_tagged", c_void_p),
-                ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int), ("skip_wait", c_int),
-                ("l2_hint", c_void_p * 2), ("l2_hint_rows", c_void_p), ("l2_hint_chunks", c_int), ("l2_hint_row_bytes", c_int),
-                ("l2_hint_chunk_stride", c_int64), ("pf_ptr", c_void_p * 4), ("pf_bytes", c_int64 * 4)]
+                ("step_ctr", c_void_p), ("x_index", c_int), ("x_per_step", c_int)]
 
 
 class HQQB200Error(RuntimeError):

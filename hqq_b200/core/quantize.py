@@ -279,7 +279,9 @@ class HQQLinear(nn.Module):
         dummy = torch.nn.Linear(1, 1)
         dummy.in_features, dummy.out_features = weight.shape[1], weight.shape[0]
         dummy.weight.data = weight
-        dummy.bias = bias
+        # the reference assigns `bias` as is (quantize.py:826), which nn.Module only accepts for None / nn.Parameter; a plain tensor is
+        # wrapped here instead of raising
+        dummy.bias = bias if (bias is None or isinstance(bias, nn.Parameter)) else nn.Parameter(bias, requires_grad=False)
         return cls(dummy, quant_config=quant_config, compute_dtype=compute_dtype, device=device, del_orig=del_orig)
 
     def extra_repr(self) -> str:

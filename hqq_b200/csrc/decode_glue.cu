@@ -229,9 +229,14 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
 
 // argmax over n logits -> int64 index (first index on ties).  One thread-block cluster of 8 CTAs: each scans an
 // interleaved eighth of the row, the eight candidates meet in CTA 0's shared memory over DSMEM (no workspace, one launch).
+// key_offset >= 0 (vocabulary-sharded lm_head under tensor parallelism): out[0] = (ordered(max) >> 1) << 32 | (0xFFFFFFFF -
+// (key_offset + index)) -- a signed 64-bit key whose MAX over the ranks is the global argmax with the first index on ties
+// (ordered() is the usual monotone float -> uint32 map; fp16/bf16 values leave the low mantissa bits of the float zero, so the
+// shift that keeps the sign bit clear loses nothing).
 constexpr int kArgmaxCtas = 8;
 template <typename T>
-__global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out) {
+__global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out,
+                                                                                            long long key_offset) {
   namespace cg = cooperative_groups;
   __shared__ float bv[32];
   __shared__ int bi[32];
@@ -271,7 +276,13 @@ __global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argm
     best = cv[0]; idx = ci[0];
     for (int i = 1; i < kArgmaxCtas; ++i)
       if (cv[i] > best || (cv[i] == best && ci[i] < idx)) { best = cv[i]; idx = ci[i]; }
-    out[0] = idx;
+    if (key_offset < 0) {
+      out[0] = idx;
+    } else {
+      const uint32_t u = __float_as_uint(best);
+      const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      out[0] = (long long)(((unsigned long long)(ord >> 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(key_offset + idx)));
+    }
   }
 }
 
@@ -351,8 +362,17 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
 extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {
   HQQ_REQUIRE(logits && out && n > 0, HQQ_E_INVALID, "hqq_b200_glue_argmax: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out);
-  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out);
+  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out, -1LL);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out, -1LL);
   set_error("hqq_b200_glue_argmax: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_argmax_key(const void* logits, int n, int64_t index_offset, int64_t* out_key, int dtype, void* stream) {
+  HQQ_REQUIRE(logits && out_key && n > 0 && index_offset >= 0 && index_offset + n <= 0xFFFFFFFFll, HQQ_E_INVALID, "hqq_b200_glue_argmax_key: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == HQQ_F16) return launch_pdl("argmax_key", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out_key, (long long)index_offset);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax_key", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out_key, (long long)index_offset);
+  set_error("hqq_b200_glue_argmax_key: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }

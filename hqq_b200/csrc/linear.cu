@@ -112,15 +112,8 @@ extern "C" int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* d, vo
       return HQQ_E_UNSUPPORTED;
     }
   }
-  TpExchange t{d->tp, d->rank, d->peer_data, d->red_data, d->y_tagged, d->x_tagged, d->x2_tagged, d->step_ctr, d->x_index, d->x_per_step, d->skip_wait,
-               {d->l2_hint[0], d->l2_hint[1]}, d->l2_hint_rows, d->l2_hint_chunks, d->l2_hint_row_bytes, d->l2_hint_chunk_stride,
-               {d->pf_ptr[0], d->pf_ptr[1], d->pf_ptr[2], d->pf_ptr[3]}, {d->pf_bytes[0], d->pf_bytes[1], d->pf_bytes[2], d->pf_bytes[3]}};
-  for (int i = 0; i < 4; ++i)
-    HQQ_REQUIRE(d->pf_bytes[i] >= 0 && (d->pf_bytes[i] == 0 || d->pf_ptr[i] != nullptr), HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: bad prefetch span %d", i);
-  if (d->l2_hint_rows)
-    HQQ_REQUIRE(d->l2_hint[0] && d->l2_hint_chunks > 0 && d->l2_hint_row_bytes >= 128 && d->l2_hint_row_bytes % 128 == 0 && d->l2_hint_chunk_stride > 0,
-                HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: bad L2 hint (rows of a multiple of 128 bytes, chunks > 0)");
-  const bool exchange = d->step_ctr != nullptr || d->l2_hint_rows != nullptr || d->pf_bytes[0] > 0;
+  TpExchange t{d->tp, d->rank, d->peer_data, d->red_data, d->y_tagged, d->x_tagged, d->x2_tagged, d->step_ctr, d->x_index, d->x_per_step};
+  const bool exchange = d->step_ctr != nullptr;
   // a tagged x still needs a mapped pointer for the alignment checks / unused plain path: reuse the tagged buffer itself
   const void* x = d->x ? d->x : d->x_tagged;
   return linear_small_multi(x, d->count, d->W_q, d->scale, d->zero, d->bias, d->y, d->N, 1, d->K, d->group_size, d->nbits, d->dtype, nullptr, 0,

@@ -14,13 +14,7 @@ struct TpExchange {
   const void* x_tagged;
   const void* x2_tagged;
   const int* step_ctr;
-  int x_index, x_per_step, skip_wait;
-  const void* l2_hint[2];
-  const int64_t* l2_hint_rows;
-  int l2_hint_chunks, l2_hint_row_bytes;
-  int64_t l2_hint_chunk_stride;
-  const void* pf_ptr[4];  // weight prefetch spans for the following launches (hqq_b200_decode_desc::pf_*)
-  int64_t pf_bytes[4];
+  int x_index, x_per_step;
 };
 
 }  // namespace hqq

@@ -72,8 +72,7 @@ struct SKArgs {
   //   consumer (xop 1): red_data != null, the residual delta is sum_r red_data[parity][r][k]
   // The same tagged words chain kernels on ONE GPU: a producer may keep a tagged copy of its outputs (SKProb::ytag) and a
   // consumer may take x / x2 of the SiLU*mul prologue from tagged buffers (xtag / x2tag) or its residual delta from
-  // red_data with tp == 1.  A consumer whose only inputs from the preceding kernel are tagged can skip griddepcontrol.wait
-  // (skip_wait) and overlap that kernel's tail: the polling is the synchronisation.
+  // red_data with tp == 1.
   int tp, rank;
   uint32_t* peer_data[8];
   const uint32_t* red_data;
@@ -81,27 +80,7 @@ struct SKArgs {
   const uint32_t* x2tag;
   const int* step_ctr;
   int x_index, x_per_step;
-  int skip_wait;
-  // optional L2 warm-up for the next kernel (hqq_b200_decode_desc::l2_hint*): rows [0, *hint_rows) of hint_chunks chunks
-  const char* hint[2];
-  const long long* hint_rows;
-  int hint_chunks, hint_row_lines;  // 128-byte lines per row
-  long long hint_stride;
-  // optional weight prefetch for the following launches (hqq_b200_decode_desc::pf_*): spans of 128-byte lines, 0 lines = end
-  const char* pf_ptr[4];
-  long long pf_lines[4];
-  int pf_chunk;  // HQQ_B200_WPF_BULK (KiB): > 0 = one bulk prefetch (TMA unit) per `pf_chunk` bytes instead of one prefetch per line
 };
-
-// L2 prefetch (a pure hint): nothing to do on the emulator
-#ifdef HQQ_EMU
-#define HQQ_PREFETCH_L2(p) ((void)(p))
-#define HQQ_PREFETCH_L2_BULK(p, n) ((void)(p), (void)(n))
-#else
-#define HQQ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
-// `n` bytes (a multiple of 16) from the 16-byte aligned `p` through the bulk-copy (TMA) unit: one instruction per chunk
-#define HQQ_PREFETCH_L2_BULK(p, n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n))
-#endif
 
 #ifdef HQQ_EMU
 #define HQQ_ST_RELAXED_SYS(p, v) (*reinterpret_cast<volatile uint32_t*>(p) = (v))
@@ -290,26 +269,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
 #else
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
-#endif
-}
-// the same copy, marked evict-first in L2: a stream that is read once should not push the step's reusable lines (KV cache,
-// activations, norm weights) out of the 126 MB L2
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-#ifdef HQQ_EMU
-  return 0;
-#else
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-#endif
-}
-__device__ __forceinline__ void cp_async16_hint(void* smem, const void* g, uint64_t pol) {
-#ifdef HQQ_EMU
-  (void)pol;
-  ::emu::cp_async(smem, g, 16);
-#else
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "l"(pol) : "memory");
 #endif
 }
 template <int BYTES>
@@ -684,8 +643,6 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     }
   };
 
-  uint64_t wpol = 0;
-  if constexpr ((MR & 2) != 0) wpol = l2_evict_first_policy();
   int i_tile = 0, i_k = 0;
   const uint8_t *iw_a, *iw_b;
   const T* im = nullptr;  // MR: this lane's meta vector (c = 0: scale of row a, 1: zero of row a, 2: scale of row b, 3: zero of row b)
@@ -734,20 +691,11 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   meta_fetch();
   auto issue = [&](int stage) {
     if (to_issue > 0) {
-      if constexpr ((MR & 2) != 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cp_async16_hint(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64, wpol);
-        if (F == 1) {
+      for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
+      if (F == 1) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) cp_async16_hint(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64, wpol);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + i) * 256 + tid], iw_a + i * 64);
-        if (F == 1) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
-        }
+        for (int i = 0; i < 4; ++i) cp_async16(&wring[(stage * NWV + 4 + i) * 256 + tid], iw_b + i * 64);
       }
       if constexpr ((MR & 1) != 0)  // the aligned 16 bytes holding this unit's GPB values (rows are 16-byte aligned: host check)
         cp_async16(&mring[((stage * 8 + warp) * 4 + c) * 8 + r], reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(im) & ~uintptr_t(15)));
@@ -764,65 +712,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   };
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) issue(s);
-  // skip_wait 0: release our dependents early (their launch latency hides under our main loop), then wait for x.
-  //           1: every input from the preceding kernel is tagged -> no wait at all.
-  //           2: our dependents skip THEIR wait, so they must not be released before everything older than us has completed,
-  //              i.e. not before our own wait has returned.
-  if constexpr ((MR & 4) != 0) {
-    // MR bit 2: while this CTA waits for the previous kernel (its ring is full), pull the next units of its OWN weight stream
-    // into L2 -- the DRAM pipe is otherwise idle on this SM until the dependency resolves.  The cursor is advanced on a copy.
-    constexpr int kPfUnits = 6;
-    const int s_tile = i_tile, s_k = i_k, s_left = to_issue;
-    const uint8_t *s_a = iw_a, *s_b = iw_b;
-    const T* s_m = im;
-    for (int u = 0; u < kPfUnits && to_issue > 0; ++u) {
-      if (c == 0) {  // one lane per packed row: the unit's 256 bytes = two 128-byte lines
-        HQQ_PREFETCH_L2(iw_a);
-        HQQ_PREFETCH_L2(iw_a + 128);
-        if (F == 1) {
-          HQQ_PREFETCH_L2(iw_b);
-          HQQ_PREFETCH_L2(iw_b + 128);
-        }
-      }
-      --to_issue;
-      if (++i_k == upt) {
-        i_k = 0; ++i_tile;
-        if (to_issue > 0) issue_setup();
-      } else {
-        iw_a += 256; iw_b += 256;
-      }
-    }
-    i_tile = s_tile; i_k = s_k; to_issue = s_left; iw_a = s_a; iw_b = s_b; im = s_m;
-  }
-  if (a.hint_rows) {
-    // warm L2 with what the NEXT kernel will read and nobody in this step writes (KV-cache rows below the current position)
-    const long long per_chunk = *a.hint_rows * a.hint_row_lines, total = per_chunk * a.hint_chunks;
-    for (long long i = (long long)blockIdx.x * 256 + tid; i < total; i += (long long)gridDim.x * 256) {
-      const long long ch = i / per_chunk, off = ch * a.hint_stride + ((i - ch * per_chunk) << 7);
-      HQQ_PREFETCH_L2(a.hint[0] + off);
-      if (a.hint[1]) HQQ_PREFETCH_L2(a.hint[1] + off);
-    }
-  }
-  if (a.pf_lines[0] > 0) {
-    // HBM is idle while this kernel waits for its inputs and the weights of the next launches depend on nothing: pull them into L2
-    if (a.pf_chunk > 0) {
-#pragma unroll 1
-      for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp) {
-        // the bulk prefetch is a warp-level (uniform-datapath) instruction: one chunk per warp and trip, issued by lane 0
-        const long long bytes = a.pf_lines[sp] << 7, nch = (bytes + a.pf_chunk - 1) / a.pf_chunk;
-        for (long long i = (long long)blockIdx.x * 8 + (tid >> 5); i < nch; i += (long long)gridDim.x * 8) {
-          const long long off = i * a.pf_chunk, left = bytes - off;
-          if ((tid & 31) == 0) HQQ_PREFETCH_L2_BULK(a.pf_ptr[sp] + off, (uint32_t)(left < a.pf_chunk ? left : a.pf_chunk));
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int sp = 0; sp < 4 && a.pf_lines[sp] > 0; ++sp)
-        for (long long i = (long long)blockIdx.x * 256 + tid; i < a.pf_lines[sp]; i += (long long)gridDim.x * 256) HQQ_PREFETCH_L2(a.pf_ptr[sp] + (i << 7));
-    }
-  }
-  if (a.skip_wait == 2) { pdl_wait(); pdl_launch_dependents(); }
-  else { pdl_launch_dependents(); if (a.skip_wait == 0) pdl_wait(); }
+  pdl_launch_dependents();  // our dependents' launch latency hides under our main loop
+  pdl_wait();
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
   if (a.step_ctr) {
     const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
@@ -1084,20 +975,29 @@ static int magic_mode() {
   return mode;
 }
 
+// Function attributes (opt-in dynamic shared memory) and SM counts belong to ONE device: every cache below is indexed by the
+// calling thread's current device, so layers living on several GPUs of one process each get their own setup.
+constexpr int kMaxDevices = 64;
+static int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+  static int n[kMaxDevices] = {};
+  const int dev = cur_device();
+  if (!n[dev]) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = kNumSMs;
   }
-  return n;
+  return n[dev];
 }
 
 template <typename T, int NBITS, int GS, int MT, int MAGIC>
 static int grid_for_kernel(int* grid_out) {
   using C = SKCfg<T, NBITS, GS, MT, MAGIC>;
-  static int grid = 0;
+  static int grids[kMaxDevices] = {};
+  int& grid = grids[cur_device()];
   if (!grid) {
     auto k = linear_small_kernel<T, NBITS, GS, MT, MAGIC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -1161,7 +1061,8 @@ static int launch_sk(SKArgs& a, cudaStream_t st) {
 template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC, int MR = 0>
 static int launch_d1(SKArgs& a, cudaStream_t st) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST, MR>;
-  static int max_smem = 0;
+  static int max_smems[kMaxDevices] = {};
+  int& max_smem = max_smems[cur_device()];
   const int smem = C::smem(a.K);
   auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST, MC, MR>;
   if (smem > max_smem) {
@@ -1197,34 +1098,15 @@ template <typename T, int NBITS, int GS, int MAGIC>
 static int sk_mt(SKArgs& a, cudaStream_t st) {
   if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
     if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
-    // HQQ_B200_D1_VARIANT (tuning knob): 42 = 4 stages, 2 CTAs per SM (default; 43/33/23/62/41/61/81 were measured and are not
-    // better); 32 = 3 stages; 1042 = default + scale/zero through the cp.async ring, 2042 = evict-first weight
-    // stream, 3042 = both, 1033 = both with 3 stages and 3 CTAs per SM, 4042 = L2 prefetch under the dependency wait, 7042/7033 = all
-    // (both experimental: written after round 1's GPU budget was spent, see D1Cfg)
-    HQQ_ENV_KNOB(variant, ([] { const char* e = getenv("HQQ_B200_D1_VARIANT"); return e ? atoi(e) : 0; })());
-    if (variant == 32) return launch_d1<T, NBITS, GS, MAGIC, 3, 2>(a, st);
+    // scale/zero ride the cp.async ring at the weights' distance (MR = 1) whenever the ring's aligned 16-byte copies are legal;
+    // measured on the B200 (round 2, profiles/r2_d1_variants.txt): 1.70 ms per token against 1.91 ms with register loads one
+    // unit ahead, bit-identical outputs.  evict-first hints, a third CTA per SM, L2 prefetch under the dependency wait and
+    // cross-launch weight prefetch were measured in the same run, were not faster, and are gone.
     if constexpr (GS == 64 && NBITS != 8) {
-      if (variant == 1042 && a.K % 512 == 0) {
+      if (a.K % 512 == 0) {
         bool ok = true;  // the ring copies aligned 16-byte blocks: every group row must start on one
         for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
         if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(a, st);
-      }
-      if (variant == 2042) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 2>(a, st);  // evict-first weight stream only
-      if (variant == 4042) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 4>(a, st);  // L2 prefetch under the dependency wait only
-      if ((variant == 7042 || variant == 7033) && a.K % 512 == 0 && (variant == 7042 || a.K <= 8192)) {
-        bool ok = true;
-        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
-        if (ok) return variant == 7042 ? launch_d1<T, NBITS, GS, MAGIC, 4, 2, 7>(a, st) : launch_d1<T, NBITS, GS, MAGIC, 3, 3, 7>(a, st);
-      }
-      if (variant == 3042 && a.K % 512 == 0) {
-        bool ok = true;
-        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
-        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 3>(a, st);
-      }
-      if (variant == 1033 && a.K % 512 == 0 && a.K <= 8192) {  // + 3 stages, 3 CTAs per SM (24 warps): fits while K <= 8192
-        bool ok = true;
-        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
-        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 3, 3, 3>(a, st);
       }
     }
     return launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);
@@ -1302,34 +1184,13 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
     }
   }
   a.tp = 1; a.rank = 0; a.red_data = nullptr; a.xtag = nullptr; a.x2tag = nullptr; a.step_ctr = nullptr; a.x_index = 0; a.x_per_step = 1;
-  a.skip_wait = 0;
   for (int i = 0; i < 8; ++i) a.peer_data[i] = nullptr;
-  a.hint[0] = a.hint[1] = nullptr; a.hint_rows = nullptr; a.hint_chunks = 0; a.hint_row_lines = 0; a.hint_stride = 0;
-  if (tpx && tpx->l2_hint_rows) {
-    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
-    a.hint[0] = reinterpret_cast<const char*>(tpx->l2_hint[0]); a.hint[1] = reinterpret_cast<const char*>(tpx->l2_hint[1]);
-    a.hint_rows = reinterpret_cast<const long long*>(tpx->l2_hint_rows); a.hint_chunks = tpx->l2_hint_chunks;
-    a.hint_row_lines = tpx->l2_hint_row_bytes >> 7; a.hint_stride = tpx->l2_hint_chunk_stride;
-  }
-  for (int i = 0; i < 4; ++i) { a.pf_ptr[i] = nullptr; a.pf_lines[i] = 0; }
-  {
-    // HQQ_B200_WPF_BULK=<KiB per bulk prefetch> (tuning knob, 1..1024; 0 / unset = one prefetch.global.L2 per 128-byte line)
-    HQQ_ENV_KNOB(bulk_kib, ([] { const char* e = getenv("HQQ_B200_WPF_BULK"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 1024 ? 1024 : v); })());
-    a.pf_chunk = bulk_kib << 10;
-  }
-  if (tpx && tpx->pf_bytes[0] > 0) {
-    HQQ_REQUIRE(small_xop_ok(M, K), HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
-    for (int i = 0, j = 0; i < 4 && tpx->pf_bytes[i] > 0; ++i) {
-      a.pf_ptr[j] = reinterpret_cast<const char*>(tpx->pf_ptr[i]); a.pf_lines[j] = (long long)(tpx->pf_bytes[i] >> 7); ++j;
-    }
-  }
-  if (tpx && !tpx->step_ctr) tpx = nullptr;  // hints only
+  if (tpx && !tpx->step_ctr) tpx = nullptr;
   if (tpx) {
     HQQ_REQUIRE(small_xop_ok(M, K) && nprob >= 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_fwd_desc: needs the M == 1 kernel");
     HQQ_REQUIRE(tpx->tp >= 1 && tpx->tp <= 8 && tpx->rank >= 0 && tpx->rank < tpx->tp && tpx->step_ctr && tpx->x_per_step > 0, HQQ_E_INVALID,
                 "hqq_b200_decode_linear_fwd_desc: bad tp/rank/step counter");
     a.tp = tpx->tp; a.rank = tpx->rank; a.step_ctr = tpx->step_ctr; a.x_index = tpx->x_index; a.x_per_step = tpx->x_per_step;
-    a.skip_wait = tpx->skip_wait;
     if (tpx->peer_data) {
       HQQ_REQUIRE(nprob == 1, HQQ_E_INVALID, "hqq_b200_decode_linear_fwd_desc: the scatter side takes exactly one matrix");
       for (int i = 0; i < tpx->tp; ++i) a.peer_data[i] = reinterpret_cast<uint32_t*>(tpx->peer_data[i]);

@@ -71,16 +71,11 @@ class DecodeModel:
             fused = False
         self.fused = fused
         import os
-        self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")  # "p2p": tagged-word chaining / fused exchange; "nccl": plain
-        self.chain_all = os.environ.get("HQQ_B200_CHAIN", "0") == "1"
-        self.skip_wait = int(os.environ.get("HQQ_B200_SKIP_WAIT", "1"))
-        self.pair_silu = os.environ.get("HQQ_B200_PAIR_SILU", "1") != "0"
-        # measured neutral at cache_len 256 (the attention kernel already prefetches under the q/k/v tail): opt-in
-        self.kv_hint = os.environ.get("HQQ_B200_KV_HINT", "0") == "1"
-        # cross-launch weight prefetch into L2 (MiB per launch, how many following linear launches it may cover); 0 = off
-        self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
-        self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
-        self.wpf_from = parse_wpf_from(os.environ.get("HQQ_B200_WPF_FROM", ""))
+        # "p2p": the row-parallel partials meet through tagged words over NVLink peer memory inside the kernels (default);
+        # "nccl": NCCL all-reduce between the kernels (the correctness reference for the fused exchange, tools/tp_check.py)
+        self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")
+        if self.tp_mode not in ("p2p", "nccl"):
+            raise ValueError(f"tp_mode must be 'p2p' or 'nccl' (got {self.tp_mode!r})")
         self.nbits, self.group_size = nbits, group_size
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -96,7 +91,15 @@ class DecodeModel:
             return (torch.randn(n, k, device=self.device, generator=gen, dtype=torch.float32) * 0.02).to(dtype)
 
         self.embed = rnd(shape.vocab, shape.hidden, gshared)
-        self.lm_head = rnd(shape.vocab, shape.hidden, gshared)
+        # lm_head stays fp16 like the reference (hqq/models/base.py:43); under tensor parallelism it is sharded by vocabulary:
+        # every rank streams 1/tp of the rows and the argmax candidates meet in one 8-byte all-reduce (round 1 streamed the
+        # full 1.05 GB head on every rank: 68 % of a rank's bytes at tp = 8)
+        if shape.vocab % tp:
+            raise ValueError(f"tp={tp} must divide the vocabulary ({shape.vocab})")
+        self.vocab_shard = shape.vocab // tp
+        head = rnd(shape.vocab, shape.hidden, gshared)
+        self.lm_head = head[rank * self.vocab_shard:(rank + 1) * self.vocab_shard].clone() if tp > 1 else head
+        del head
         self.final_norm = torch.ones(shape.hidden, device=self.device, dtype=dtype)
         self.blocks = []
         self.quantized_weights = 0
@@ -138,9 +141,13 @@ class DecodeModel:
         self.graph = None
 
     # bytes one decode step must read from HBM: packed weights + meta + fp16 lm_head row-major
-    def bytes_per_token(self, nbits=4, group_size=64) -> float:
-        meta = 2 * 2 / group_size
-        return self.quantized_weights * (nbits / 8 + meta) + self.lm_head.numel() * 2
+    def bytes_per_token(self, nbits=None, group_size=None) -> float:
+        nbits = self.nbits if nbits is None else nbits
+        group_size = self.group_size if group_size is None else group_size
+        esize = torch.empty((), dtype=self.dtype).element_size()
+        store = {8: 1.0, 4: 0.5, 3: 0.4, 2: 0.25, 1: 0.125}[int(nbits)]  # bytes per weight as packed (3-bit: 10 fields per int32)
+        meta = 2 * esize / group_size                                       # scale + zero in the compute dtype
+        return self.quantized_weights * (store + meta) + self.lm_head.numel() * esize
 
     @staticmethod
     def _multi(x, layers):
@@ -184,8 +191,33 @@ class DecodeModel:
             h = h + y
         h = F.rms_norm(h, (s.hidden,), self.final_norm, s.rms_eps)
         logits = torch.matmul(h, self.lm_head.t())
-        self.next_tok.copy_(torch.argmax(logits, dim=-1))
+        if self.tp > 1:  # vocabulary shards: (max, first index) per rank, the best one wins
+            val, idx = torch.max(logits.float(), dim=-1)
+            vals = [torch.empty_like(val) for _ in range(self.tp)]
+            idxs = [torch.empty_like(idx) for _ in range(self.tp)]
+            torch.distributed.all_gather(vals, val, group=self.pg)
+            torch.distributed.all_gather(idxs, idx, group=self.pg)
+            vals, idxs = torch.stack(vals), torch.stack(idxs) + torch.arange(self.tp, device=idx.device).view(-1, 1) * self.vocab_shard
+            best = torch.argmax(vals, dim=0, keepdim=True)  # first rank on ties = lowest index
+            self.next_tok.copy_(torch.gather(idxs, 0, best).view(-1))
+        else:
+            self.next_tok.copy_(torch.argmax(logits, dim=-1))
         self.pos.add_(1).remainder_(self.cache_len)
+
+    def _head(self, lib, x, code, st):
+        """Final projection + greedy pick inside the captured step: fp16 lm_head through the library GEMV (it is not an HQQ
+        layer), then our argmax kernel; with tp > 1 each rank covers its vocabulary shard and one 8-byte MAX all-reduce of
+        {value : index} keys picks the winner."""
+        from ._lib import check, ptr
+        b = self._bufs
+        torch.matmul(x, self.lm_head.t(), out=b["logits"])
+        if self.tp == 1:
+            check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), self.vocab_shard, ptr(self.next_tok), code, st))
+            return
+        check(lib.hqq_b200_glue_argmax_key(ptr(b["logits"]), self.vocab_shard, self.rank * self.vocab_shard, ptr(b["key"]), code, st))
+        torch.distributed.all_reduce(b["key"], op=torch.distributed.ReduceOp.MAX, group=self.pg)
+        torch.bitwise_and(b["key"], 0xFFFFFFFF, out=b["key"])
+        self.next_tok.copy_(0xFFFFFFFF - b["key"])
 
     def step_fused(self):
         """Same token step with the package's glue kernels (8 launches per block): add+RMSNorm, fused q/k/v, RoPE+cache+
@@ -216,15 +248,13 @@ class DecodeModel:
                 torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
         check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
-        torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
-        check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
+        self._head(lib, b["x"], code, st)
         self.pos.add_(1).remainder_(self.cache_len)
 
     def _setup_exchange(self):
         """Buffers of tagged 32-bit words {tag16 : value16} through which the one-token kernels hand activations to each other
-        (`hqq_b200_decode_linear_fwd_desc`): o / down partials [2 parities][tp][hidden] -- peer-mapped symmetric memory when tp > 1,
-        so the scatter + reduce IS the tensor-parallel all-reduce -- and gate / up [2][inter/tp] (local).  The step counter the
-        tags derive from lives in local memory."""
+        (`hqq_b200_decode_linear_fwd_desc`): o / down partials [2 parities][tp][hidden] in peer-mapped symmetric memory, so the
+        scatter + reduce IS the tensor-parallel all-reduce.  The step counter the tags derive from lives in local memory."""
         import ctypes
         s, tp, dev = self.shape, self.tp, self.device
         slot_bytes = 2 * tp * s.hidden * 4
@@ -240,7 +270,6 @@ class DecodeModel:
             buf = torch.full((2 * slot_bytes,), 0xFF, dtype=torch.uint8, device=dev)
             ptrs = [buf.data_ptr()]
         self._xbuf = buf
-        self._xact = torch.full((2, 2, s.inter // tp), -1, dtype=torch.int32, device=dev)  # gate, up: [2 parities][inter/tp] words each
         self._xstep = torch.zeros(1, dtype=torch.int32, device=dev)
         VP = ctypes.c_void_p * tp
         self._tp_keep = [VP(*[p + slot * slot_bytes for p in ptrs]) for slot in range(2)]
@@ -255,8 +284,10 @@ class DecodeModel:
         return d
 
     def step_fused5(self):
-        """Five launches per block: [add+RMSNorm -> q/k/v], RoPE+cache+attention, o, [add+RMSNorm -> gate/up],
-        [SiLU*mul -> down]; the bracketed prologues run inside the fused linear's activation staging."""
+        """Five launches per block: [add+RMSNorm -> q/k/v], RoPE+cache+attention, o, [add+RMSNorm -> gate/up -> SiLU*mul], down; the
+        bracketed prologues / epilogue run inside the fused linears.  With tp > 1 and tp_mode "p2p" the o / down partials travel as
+        tagged words over NVLink peer memory from the producing kernel's epilogue into the consuming kernel's prologue (the
+        all-reduce is fused into both); tp_mode "nccl" puts an NCCL all-reduce between the kernels instead."""
         from ._lib import DTYPE_CODE, check, load, ptr, stream_ptr
         lib, s = load(), self.shape
         st = stream_ptr(self.device)
@@ -267,102 +298,45 @@ class DecodeModel:
         torch.index_select(self.embed, 0, self.tok, out=h_cur)
         delta = None
         ok = True
-        # tagged-word exchange: with tp > 1 it is the fused NVLink all-reduce of the o / down partials (default); chaining gate/up
-        # through tagged words with skipped dependency waits is experimental (HQQ_B200_CHAIN=1): on one GPU the polling costs
-        # more than the kernel boundary it removes (measured 414 vs 468 tok/s)
-        chain = self.tp_mode == "p2p" and (self.tp > 1 or self.chain_all)
+        p2p = self.tp > 1 and self.tp_mode == "p2p"
         nb = len(self.blocks)
-        # SiLU(gate) * up in the gate/up launch's epilogue (4/2/1-bit): computed once instead of by each of down's CTAs
-        pair = self.pair_silu and self.nbits < 8
-        if chain:
+        pair = self.nbits < 8  # SiLU(gate) * up in the gate/up launch's epilogue (4/2/1-bit): computed once, not by each of down's CTAs
+        if p2p:
             o_sc, d_sc = self._tp_keep            # scatter targets (every rank's buffer) for o / down
             o_loc, d_loc = self._tp_local         # this rank's buffers
-            g_tag, u_tag = self._xact[0].data_ptr(), self._xact[1].data_ptr()
         for bi, blk in enumerate(self.blocks):
-            if chain:
-                # [residual add + RMSNorm] -> q/k/v; the delta is the sum of the ranks' down-proj partials of block bi-1
-                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None, blk["norm1"], h_nxt, s.rms_eps,
-                                            tpx=(self._tpx(bi - 1, red_data=d_loc) if bi > 0 else None), l2_hint=self._kv_hint(blk), wpf=self._wpf(bi, "qkv"))
-            else:
-                ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, delta, blk["norm1"], h_nxt, s.rms_eps,
-                                            l2_hint=self._kv_hint(blk), wpf=self._wpf(bi, "qkv"))
+            # [residual add + RMSNorm] -> q/k/v; p2p: the delta is the sum of the ranks' down-proj partials of block bi-1
+            ok &= ops.decode_linear_fwd(h_cur, (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]], 1, None if p2p else delta, blk["norm1"], h_nxt,
+                                        s.rms_eps, tpx=(self._tpx(bi - 1, red_data=d_loc) if (p2p and bi > 0) else None))
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            if chain:
-                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc, skip_wait=2 if (self.chain_all and self.skip_wait) else 0), wpf=self._wpf(bi, "o"))
-                # the next two kernels take everything the preceding kernel produces as tagged words: they skip the
-                # programmatic-dependency wait and start streaming their weights under its tail
-                if self.chain_all:
-                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                                tpx=self._tpx(bi, red_data=o_loc, y_tagged=[g_tag, u_tag], skip_wait=self.skip_wait), wpf=self._wpf(bi, "gu"))
-                    h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"],
-                                                tpx=self._tpx(bi, peer_data=d_sc, x_tagged=g_tag, x2_tagged=u_tag, skip_wait=self.skip_wait), wpf=self._wpf(bi, "down"))
-                else:
-                    if pair:  # act = silu(gate) * up leaves the gate/up launch's epilogue; down takes it as is
-                        ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, None, blk["norm2"],
-                                                    h_nxt, s.rms_eps, tpx=self._tpx(bi, red_data=o_loc), wpf=self._wpf(bi, "gu"))
-                        h_cur, h_nxt = h_nxt, h_cur
-                        ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], tpx=self._tpx(bi, peer_data=d_sc), wpf=self._wpf(bi, "down"))
-                    else:
-                        ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, None, blk["norm2"], h_nxt, s.rms_eps,
-                                                    tpx=self._tpx(bi, red_data=o_loc), wpf=self._wpf(bi, "gu"))
-                        h_cur, h_nxt = h_nxt, h_cur
-                        ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc), wpf=self._wpf(bi, "down"))
+            ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc) if p2p else None)
+            if self.tp > 1 and not p2p:
+                torch.distributed.all_reduce(b["o"], group=self.pg)
+            gu_tpx = self._tpx(bi, red_data=o_loc) if p2p else None
+            o_delta = None if p2p else b["o"]
+            if pair:  # act = silu(gate) * up leaves the gate/up launch's epilogue; down takes it as is
+                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, o_delta, blk["norm2"],
+                                            h_nxt, s.rms_eps, tpx=gu_tpx)
+                h_cur, h_nxt = h_nxt, h_cur
+                ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], tpx=self._tpx(bi, peer_data=d_sc) if p2p else None)
             else:
-                ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], wpf=self._wpf(bi, "o"))
-                if self.tp > 1:
-                    torch.distributed.all_reduce(b["o"], group=self.pg)
-                if pair:
-                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, b["o"], blk["norm2"],
-                                                h_nxt, s.rms_eps, wpf=self._wpf(bi, "gu"))
-                    h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["act"], (blk["down"],), [b["down"]], wpf=self._wpf(bi, "down"))
-                else:
-                    ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, b["o"], blk["norm2"], h_nxt, s.rms_eps, wpf=self._wpf(bi, "gu"))
-                    h_cur, h_nxt = h_nxt, h_cur
-                    ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], wpf=self._wpf(bi, "down"))
-                if self.tp > 1:
-                    torch.distributed.all_reduce(b["down"], group=self.pg)
+                ok &= ops.decode_linear_fwd(h_cur, (blk["gate"], blk["up"]), [b["gate"], b["up"]], 1, o_delta, blk["norm2"], h_nxt, s.rms_eps, tpx=gu_tpx)
+                h_cur, h_nxt = h_nxt, h_cur
+                ok &= ops.decode_linear_fwd(b["gate"], (blk["down"],), [b["down"]], 2, b["up"], tpx=self._tpx(bi, peer_data=d_sc) if p2p else None)
+            if self.tp > 1 and not p2p:
+                torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
         if not ok:
             raise RuntimeError("hqq_b200: this model shape is outside the fused M=1 decode kernel; use fused=False or step_fused")
-        if chain:
+        if p2p:
             check(lib.hqq_b200_glue_add_rmsnorm_tp(ptr(h_cur), d_loc, self._xstep.data_ptr(), nb, nb, self.tp, ptr(self.final_norm),
                                                    ptr(b["x"]), s.hidden, s.rms_eps, code, st))
         else:
             check(lib.hqq_b200_glue_add_rmsnorm(ptr(h_cur), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
-        torch.matmul(b["x"], self.lm_head.t(), out=b["logits"])
-        check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), s.vocab, ptr(self.next_tok), code, st))
+        self._head(lib, b["x"], code, st)
         self.pos.add_(1).remainder_(self.cache_len)
-
-    def _wpf(self, bi, stage):
-        """Weight prefetch spans for the launches that FOLLOW launch `stage` of block `bi` (hqq_b200_decode_desc::pf_*): the packed
-        weights of the next `wpf_ahead` linear launches, at most `wpf_mb` MiB and four spans, wrapping into the next block.
-        Off unless HQQ_B200_WPF_MB > 0 (experimental: not yet timed on a GPU).  A launch issues its prefetch in its prologue, i.e.
-        while its PREDECESSOR runs: "o" prefetches under the attention kernel (HBM idle), "gu" under the short o launch, "qkv" and
-        "down" under the big down / gate+up launches (HBM busy) -- HQQ_B200_WPF_FROM=o,gu restricts the issuing launches."""
-        if self.wpf_mb <= 0 or stage not in self.wpf_from:
-            return None
-        order = WPF_STAGES
-        groups = {"qkv": ("q", "k", "v"), "o": ("o",), "gu": ("gate", "up"), "down": ("down",)}
-        i, blk, seq = order.index(stage), bi, []
-        for _ in range(self.wpf_ahead):
-            i += 1
-            if i == len(order):
-                i, blk = 0, (blk + 1) % len(self.blocks)
-            seq += [self.blocks[blk][n] for n in groups[order[i]]]
-        return wpf_spans([(l.W_q.data_ptr(), l.W_q.numel() * l.W_q.element_size()) for l in seq], int(self.wpf_mb * (1 << 20)))
-
-    def _kv_hint(self, blk):
-        """The q/k/v launch warms L2 with the cache rows the attention kernel behind it reads (they are evicted by the ~5 GB
-        of weights streamed between two visits of a layer); `pos` is only written by the non-PDL kernel that ends a step."""
-        if not self.kv_hint:
-            return None
-        kc, vc = blk["k_cache"], blk["v_cache"]
-        return {"ptrs": (kc.data_ptr(), vc.data_ptr()), "rows": self.pos.data_ptr(), "chunks": kc.shape[-3],
-                "row_bytes": kc.shape[-1] * kc.element_size(), "chunk_stride": kc.stride(-3) * kc.element_size()}
 
     def _alloc_bufs(self):
         s, dev, dt = self.shape, self.device, self.dtype
@@ -370,19 +344,16 @@ class DecodeModel:
         tp = self.tp
         self._bufs = {"h": z(s.hidden), "h2": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads // tp * s.head_dim), "k": z(s.n_kv_heads // tp * s.head_dim),
                       "v": z(s.n_kv_heads // tp * s.head_dim), "a": z(s.n_heads // tp * s.head_dim), "o": z(s.hidden),
-                      "gate": z(s.inter // tp), "up": z(s.inter // tp), "act": z(s.inter // tp), "down": z(s.hidden), "logits": z(s.vocab)}
+                      "gate": z(s.inter // tp), "up": z(s.inter // tp), "act": z(s.inter // tp), "down": z(s.hidden), "logits": z(self.vocab_shard),
+                      "key": torch.zeros(1, dtype=torch.long, device=dev)}
 
     def capture(self, warmup: int = 3):
         """Warm up on a side stream, then capture one decode step into a CUDA graph."""
         fused = self.fused
         if fused and not hasattr(self, "_bufs"):
             self._alloc_bufs()
-        if fused and self.fused == 5 and self.tp_mode == "p2p" and (self.tp > 1 or self.chain_all) and not hasattr(self, "_xbuf"):
-            try:
-                self._setup_exchange()
-            except Exception as e:  # symmetric memory unavailable -> plain buffers (+ NCCL all-reduce when tp > 1)
-                print(f"hqq_b200: tagged exchange unavailable ({e}); using plain buffers / NCCL all-reduce")
-                self.tp_mode = "nccl"
+        if fused and self.fused == 5 and self.tp_mode == "p2p" and self.tp > 1 and not hasattr(self, "_xbuf"):
+            self._setup_exchange()  # needs symmetric (peer-mapped) memory; ask for tp_mode="nccl" explicitly where that is not available
         step = (self.step_fused5 if self.fused == 5 else self.step_fused) if fused else self.step
         st = torch.cuda.Stream(device=self.device)
         st.wait_stream(torch.cuda.current_stream(self.device))
@@ -396,42 +367,6 @@ class DecodeModel:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             step()
         return self.graph
-
-    # knobs that only select among bit-identical kernels / pure prefetch hints of the one-token path
-    TUNABLE = ("HQQ_B200_D1_VARIANT", "HQQ_B200_WPF_MB", "HQQ_B200_WPF_AHEAD", "HQQ_B200_WPF_FROM", "HQQ_B200_WPF_BULK")
-
-    def retune(self, knobs: dict | None = None, warmup: int = 2):
-        """Re-capture the decode graph under another choice of the TUNABLE knobs ({} = the default kernels).  The knobs select
-        among kernels that produce identical results (D1 variants) or add prefetch hints (WPF), so the token stream does not
-        change -- bench.py's autotuner checks exactly that before it keeps a choice."""
-        import os
-        from ._lib import load
-        knobs = dict(knobs or {})
-        unknown = set(knobs) - set(self.TUNABLE)
-        if unknown:
-            raise ValueError(f"retune: not a decode tuning knob: {sorted(unknown)}")
-        for k in self.TUNABLE:
-            os.environ.pop(k, None)
-        os.environ.update({k: str(v) for k, v in knobs.items()})
-        load().hqq_b200_reload_env()
-        self.wpf_mb = float(os.environ.get("HQQ_B200_WPF_MB", "0"))
-        self.wpf_ahead = max(1, int(os.environ.get("HQQ_B200_WPF_AHEAD", "2" if self.wpf_mb > 24 else "1")))
-        self.wpf_from = parse_wpf_from(os.environ.get("HQQ_B200_WPF_FROM", ""))
-        self.graph = None
-        return self.capture(warmup=warmup)
-
-    def autotune(self, budget_s: float = 90.0, **kw):
-        """Measure, on this GPU, which of the result-preserving decode knobs pays (hqq_b200/tune.py: child-process guard, then
-        in-process timing on this model) and leave the model captured under the winner.  Returns the tuner's report.  One GPU,
-        one sequence, the five-launch step only: the guard runs an 8-block Llama-3-8B-shaped stand-in with the same kernels."""
-        from . import tune
-        if self.tp != 1 or self.batch != 1 or self.fused != 5:
-            raise ValueError("autotune: single-GPU, batch-1, fused=5 decode only")
-        if self.graph is None:
-            self.capture()
-        import dataclasses
-        margs = {"shape": dataclasses.asdict(self.shape), "nbits": self.nbits, "group_size": self.group_size}
-        return tune.choose_decode(self, tune.guard_decode(budget_s=budget_s, layers=min(8, self.n_layers), model_args=margs), **kw)
 
     def reset_state(self, token: int = 1):
         """Position 0, empty KV caches, `token` as the first input: the state every token-stream comparison starts from."""
@@ -449,32 +384,6 @@ class DecodeModel:
         self.graph.replay()
         if feed_back:
             self.tok.copy_(self.next_tok)
-
-
-WPF_STAGES = ("qkv", "o", "gu", "down")  # the four linear launches of a block, in order
-
-
-def parse_wpf_from(text: str):
-    """HQQ_B200_WPF_FROM: comma-separated subset of WPF_STAGES naming the launches that issue weight prefetches ('' = all)."""
-    names = [t.strip() for t in text.split(",") if t.strip()]
-    bad = [n for n in names if n not in WPF_STAGES]
-    if bad:
-        raise ValueError(f"HQQ_B200_WPF_FROM: unknown launch {bad}; choose from {WPF_STAGES}")
-    return frozenset(names) if names else frozenset(WPF_STAGES)
-
-
-def wpf_spans(tensors, budget_bytes: int, max_spans: int = 4):
-    """(address, bytes) prefetch spans over `tensors` [(address, nbytes), ...] in order: whole 128-byte lines, at most `budget_bytes`
-    in total and `max_spans` spans (the last one is cut to fit).  Pure host logic (unit-tested on CPU)."""
-    spans = []
-    for addr, nbytes in tensors:
-        if budget_bytes < 128 or len(spans) == max_spans:
-            break
-        take = min(int(nbytes), budget_bytes) & ~127
-        if take > 0:
-            spans.append((int(addr), take))
-            budget_bytes -= take
-    return spans or None
 
 
 # ---------------------------------------------------------------------------------------------- quantise-only sharding (SURVEY 8e)

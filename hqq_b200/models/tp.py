@@ -20,6 +20,7 @@ from __future__ import annotations
 import copy
 
 _FIELDS = {8: 1, 4: 2, 2: 4, 1: 8, 3: 10}
+_PACKING_BITS = {"8bit_u8": 8, "4bit_u8": 4, "3bit_32": 3, "2bit_u8": 2, "1bit_u8": 1}
 
 
 def shard_bounds(total: int, tp: int, rank: int, multiple: int = 1):
@@ -35,7 +36,10 @@ def shard_bounds(total: int, tp: int, rank: int, multiple: int = 1):
 def shard_quantized(W_q, meta: dict, tp: int, rank: int, parallel: str, pack, unpack):
     """(W_q, meta) of one tensor-parallel shard.  `meta` needs nbits, group_size, shape, axis, scale, zero (+ anything else, copied);
     `unpack(W_q, nbits)` returns the level matrix (3-bit: padded rows allowed), `pack(levels, nbits)` the packed tensor."""
-    nbits, gs, axis = int(meta["nbits"]), int(meta["group_size"]), int(meta["axis"])
+    # the STORAGE width comes from the packing (nbits = 1.58 is stored as 2bit_u8, 5 / 6 as 8bit_u8: quantize.py:40-73), meta["nbits"]
+    # itself travels on unchanged
+    nbits = _PACKING_BITS[meta["packing"]] if "packing" in meta else int(meta["nbits"])
+    gs, axis = int(meta["group_size"]), int(meta["axis"])
     N, K = (int(v) for v in meta["shape"])
     if axis != 1:
         raise ValueError("shard_quantized: axis=1 layers only (groups along the input dimension)")
@@ -82,6 +86,7 @@ def shard_hqq_linear(layer, tp: int, rank: int, parallel: str):
         W_q = W_q.view(meta["unpack_view_dtype"])
     unpack = lambda t, nbits: ops.unpack(t, nbits, torch.uint8)  # noqa: E731
     Wq_s, meta_s = shard_quantized(W_q, meta, tp, rank, parallel, ops.pack, unpack)
+    meta_s["shape"] = torch.Size(meta_s["shape"])  # the state_dict codec (core/utils.py) encodes torch.Size, like the reference's
     if meta.get("view_as_float"):
         Wq_s = Wq_s.view(layer.compute_dtype)
     cfg = copy.deepcopy(layer.quant_config)

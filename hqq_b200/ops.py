@@ -157,6 +157,15 @@ def _workspace(nbytes: int, device) -> torch.Tensor | None:
     return buf
 
 
+def _on(dev: torch.device):
+    """Make `dev` the current CUDA device around a launch: the C ABI launches on the calling thread's current device (its
+    function-attribute / grid caches are per device), while a layer may live on another GPU of the same process."""
+    if dev.type != "cuda" or dev.index is None or torch.cuda.current_device() == dev.index:
+        import contextlib
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
+
+
 def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, bias, N: int, K: int,
                group_size: int, nbits: int, axis: int, out: torch.Tensor | None = None) -> torch.Tensor | None:
     """y = x2d @ dequantize(W_q).T (+ bias) through the fused kernels; returns None when no fused kernel covers
@@ -171,8 +180,9 @@ def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: 
     y = out if out is not None else torch.empty((M, N), dtype=dtype, device=dev)
     ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, N, K, int(group_size), int(nbits), code)
     ws = _workspace(ws_bytes, dev)
-    rc = lib.hqq_b200_linear_fwd(ptr(x2d), ptr(W_q), ptr(scale), ptr(zero), ptr(bias), ptr(y), M, N, K, int(group_size),
-                                 int(nbits), int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev))
+    with _on(dev):
+        rc = lib.hqq_b200_linear_fwd(ptr(x2d), ptr(W_q), ptr(scale), ptr(zero), ptr(bias), ptr(y), M, N, K, int(group_size),
+                                     int(nbits), int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev))
     if rc == HQQ_E_UNSUPPORTED:
         return None
     check(rc)
@@ -216,24 +226,22 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
     ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, Ns[0], K, int(gs), nbits, code)
     ws = _workspace(ws_bytes, dev)
     Narr = (ctypes.c_int64 * n)(*Ns)
-    check(lib.hqq_b200_linear_fwd_multi(ptr(x2d), n, arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]),
-                                        arr([l.meta["zero"] for l in layers]), arr([l.bias for l in layers]), arr(outs), Narr,
-                                        M, K, int(gs), nbits, int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev)))
+    with _on(dev):
+        check(lib.hqq_b200_linear_fwd_multi(ptr(x2d), n, arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]),
+                                            arr([l.meta["zero"] for l in layers]), arr([l.bias for l in layers]), arr(outs), Narr,
+                                            M, K, int(gs), nbits, int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev)))
     return outs
 
 
 YOP_SILU_MUL_PAIR = 16  # HQQ_YOP_SILU_MUL_PAIR (include/hqq_b200.h): or-ed into x_op
 
 
-def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None, l2_hint=None,
-                      wpf=None) -> bool:
+def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_weight=None, h_out=None, eps: float = 0.0, tpx=None) -> bool:
     """One-token fused linear(s) with the activation prologue folded in (`hqq_b200_decode_linear_fwd`): x_op 1 =
     residual add + RMSNorm, 2 = SiLU(x) * x2.  `tpx` (dict) switches on the peer-memory exchange of
     `hqq_b200_decode_linear_fwd_desc`: keys tp, rank, step_ctr, x_index, x_per_step and any of peer_data (ctypes array of peer
-    pointers), red_data, y_tagged (list of addresses), x_tagged, x2_tagged (addresses), skip_wait.  `l2_hint` (dict: ptrs (a, b),
-    rows = device int64 address, chunks, row_bytes, chunk_stride) asks the grid to warm L2 with the next kernel's read-only rows
-    (the KV cache) before it waits for its own inputs; `wpf` (up to four (address, bytes) pairs) does the same for the packed weights
-    of the FOLLOWING launches (hqq_b200_decode_desc::pf_*).  Returns False when the configuration is outside the fused M = 1 kernel."""
+    pointers), red_data, y_tagged (list of addresses), x_tagged, x2_tagged (addresses).  Returns False when the configuration is
+    outside the fused M = 1 kernel."""
     import ctypes
     lib = load()
     n = len(layers)
@@ -246,15 +254,23 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
     VP = ctypes.c_void_p * n
     arr = lambda ts: VP(*[ptr(t) for t in ts])
     Narr = (ctypes.c_int64 * n)(*[int(l.meta["shape"][0]) for l in layers])
-    if tpx is None and l2_hint is None and not wpf:
+    with _on(x.device):
+        rc = _decode_launch(lib, x, layers, outs, x_op, x2, x_weight, h_out, eps, tpx, n, m0, K, nbits, code, arr, Narr, VP)
+    if rc == HQQ_E_UNSUPPORTED:
+        return False
+    check(rc)
+    return True
+
+
+def _decode_launch(lib, x, layers, outs, x_op, x2, x_weight, h_out, eps, tpx, n, m0, K, nbits, code, arr, Narr, VP):
+    import ctypes
+    if tpx is None:
         rc = lib.hqq_b200_decode_linear_fwd(ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), n, arr([l.W_q for l in layers]),
                                             arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
                                             arr([l.bias for l in layers]), arr(outs), Narr, K, int(m0["group_size"]), nbits, code,
                                             stream_ptr(x.device))
     else:
         cast = lambda a: ctypes.cast(a, ctypes.c_void_p) if a is not None else None
-        if tpx is None:
-            tpx = {"tp": 1, "rank": 0, "step_ctr": None, "x_index": 0, "x_per_step": 1}
         arrays = [arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
                   arr([l.bias for l in layers]), arr(outs)]
         ytag = tpx.get("y_tagged")
@@ -264,21 +280,9 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
                             N=cast(Narr), K=K, group_size=int(m0["group_size"]), nbits=nbits, dtype=code, tp=int(tpx["tp"]), rank=int(tpx["rank"]),
                             peer_data=cast(tpx.get("peer_data")), red_data=tpx.get("red_data"), y_tagged=cast(ytag_arr),
                             x_tagged=tpx.get("x_tagged"), x2_tagged=tpx.get("x2_tagged"), step_ctr=tpx["step_ctr"],
-                            x_index=int(tpx["x_index"]), x_per_step=int(tpx["x_per_step"]), skip_wait=int(tpx.get("skip_wait", 0)))
-        if wpf:
-            spans = [(int(p), int(b)) for p, b in wpf if b > 0][:4]
-            d.pf_ptr = (ctypes.c_void_p * 4)(*([p for p, _ in spans] + [None] * (4 - len(spans))))
-            d.pf_bytes = (ctypes.c_int64 * 4)(*([b for _, b in spans] + [0] * (4 - len(spans))))
-        if l2_hint is not None:
-            d.l2_hint = (ctypes.c_void_p * 2)(*[int(p) if p else None for p in l2_hint["ptrs"]])
-            d.l2_hint_rows = int(l2_hint["rows"])
-            d.l2_hint_chunks, d.l2_hint_row_bytes = int(l2_hint["chunks"]), int(l2_hint["row_bytes"])
-            d.l2_hint_chunk_stride = int(l2_hint["chunk_stride"])
+                            x_index=int(tpx["x_index"]), x_per_step=int(tpx["x_per_step"]))
         rc = lib.hqq_b200_decode_linear_fwd_desc(ctypes.byref(d), stream_ptr(x.device))
-    if rc == HQQ_E_UNSUPPORTED:
-        return False
-    check(rc)
-    return True
+    return rc
 
 
 __all__ = ["pack", "unpack", "dequantize", "quantize", "linear_fwd", "linear_fwd_multi", "linear_route", "packed_shape", "HQQB200Error"]

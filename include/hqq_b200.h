@@ -170,9 +170,7 @@ int hqq_b200_decode_linear_fwd(const void* x, int x_op, const void* x2, const vo
  *     peer_data[dst][parity][rank][n] on all `tp` ranks over NVLink peer memory; the consumer (x_op 1, red_data) sums the `tp`
  *     partials into the residual delta.  This IS the all-reduce, fused into the kernels that produce and consume it.
  *   - on one GPU the same words chain kernels: y_tagged[i] keeps a tagged copy [2][N_i] of output i, x_tagged / x2_tagged feed
- *     the SiLU*mul prologue, red_data with tp == 1 feeds the residual delta.  A consumer whose only inputs from the preceding
- *     kernel are tagged may set skip_wait = 1 and overlap that kernel's tail (no griddepcontrol.wait); the kernel launched
- *     BEFORE such a consumer sets skip_wait = 2 (wait first, release dependents afterwards).
+ *     the SiLU*mul prologue, red_data with tp == 1 feeds the residual delta.
  * tag = low 16 bits of the exchange number (*step_ctr * x_per_step + x_index), parity = its bit 0.  step_ctr is an int in local
  * device memory that hqq_b200_glue_add_rmsnorm_tp bumps once per token, so a captured CUDA graph can be replayed.  Buffers
  * start filled with 0xFF.  All other fields as in hqq_b200_decode_linear_fwd.                                                  */
@@ -186,18 +184,7 @@ typedef struct hqq_b200_decode_desc {
   void* const* y_tagged;    /* `count` local [2][N_i] uint32 buffers, or NULL */
   const void* x_tagged;     /* local [2][K] uint32 (x_op 2), or NULL */
   const void* x2_tagged;
-  const int* step_ctr; int x_index; int x_per_step; int skip_wait;
-  /* optional L2 warm-up for the NEXT kernel's read-only inputs (the decode step's KV cache, which the ~5 GB of weights streamed
-   * per token evict between two visits): rows [0, *l2_hint_rows) of `l2_hint_chunks` chunks (kv heads) of both regions are
-   * prefetched into L2 by the whole grid before it waits for its own inputs.  *l2_hint_rows must not be written by a kernel
-   * launched with programmatic dependent launch in the same step.  All zero / NULL = off. */
-  const void* l2_hint[2]; const int64_t* l2_hint_rows; int l2_hint_chunks; int l2_hint_row_bytes; int64_t l2_hint_chunk_stride;
-  /* optional weight prefetch for the FOLLOWING launches of the step: up to four read-only spans (packed weights of the next
-   * linears) that the whole grid pulls into L2 with prefetch.global.L2 before it waits for its own inputs.  One decoded token is a
-   * chain of dependent, latency-bound launches during which HBM sits idle, while the weights further down the chain depend on
-   * nothing: this keeps HBM busy ahead of the computation (the 126 MB L2 holds about one block's packed weights).  A pure hint --
-   * results never depend on it.  pf_bytes[i] == 0 ends the list. */
-  const void* pf_ptr[4]; int64_t pf_bytes[4];
+  const int* step_ctr; int x_index; int x_per_step;
 } hqq_b200_decode_desc;
 int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* desc, void* stream);
 /* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */
@@ -219,15 +206,19 @@ int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v,
                                    int dtype, void* stream);
 /* out[0] = argmax(logits[0..n)) (first index on ties) */
 int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream);
+/* Vocabulary-sharded lm_head (tensor parallel decode): out_key[0] = a signed 64-bit key {ordered(max) : 0xFFFFFFFF - (index_offset +
+ * argmax)} of this rank's logits slice; the MAX of the keys over the ranks (one 8-byte all-reduce) names the global argmax, first
+ * index on ties: token = 0xFFFFFFFF - (key & 0xFFFFFFFF). */
+int hqq_b200_glue_argmax_key(const void* logits, int n, int64_t index_offset, int64_t* out_key, int dtype, void* stream);
 
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (used by bench.py for its gpu_launches claim).                                        */
 int64_t hqq_b200_launch_count(void);
 void hqq_b200_launch_count_reset(void);
 
-/* The HQQ_B200_* tuning knobs are parsed from the environment once and cached.  After changing them with setenv() call this
- * to have the next launch parse them again (kernel selection only: results are identical across knobs; bench.py's decode
- * autotuner and the tests use it to compare kernel variants inside one process).  Not thread-safe against concurrent launches. */
+/* The few HQQ_B200_* switches the library reads (test hooks: HQQ_B200_GEMM_CTAS, HQQ_B200_DECODE1, HQQ_B200_PDL,
+ * HQQ_B200_PLAIN_SOLVER) are parsed once and cached; after changing one with setenv() call this to have the next launch parse
+ * them again.  Not thread-safe against concurrent launches. */
 void hqq_b200_reload_env(void);
 
 #ifdef __cplusplus

@@ -37,6 +37,18 @@ int hqq_oc_threads(void) {
 #endif
 }
 
+/* Team size of every following parallel region (bench.py pins it: one socket's physical cores, whatever OMP_NUM_THREADS a
+ * launcher such as torchrun exported).  Returns the size now in effect. */
+int hqq_oc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 static int fields_of(int nbits) { return nbits == 3 ? 10 : 8 / nbits; }
 static int valid_bits(int nbits) { return nbits == 8 || nbits == 4 || nbits == 3 || nbits == 2 || nbits == 1; }
 

@@ -22,6 +22,8 @@ def lib():
     if _lib is None:
         L = ctypes.CDLL(build_c.build())
         L.hqq_oc_threads.restype = c_int
+        L.hqq_oc_set_threads.restype = c_int
+        L.hqq_oc_set_threads.argtypes = [c_int]
         L.hqq_oc_packed_rows.restype = c_int64
         L.hqq_oc_packed_rows.argtypes = [c_int, c_int64]
         L.hqq_oc_pack.argtypes = [c_int, c_void_p, c_int64, c_int64, c_void_p]
@@ -37,6 +39,11 @@ def lib():
 
 def threads() -> int:
     return int(lib().hqq_oc_threads())
+
+
+def set_threads(n: int) -> int:
+    """Pin the OpenMP team size (overrides OMP_NUM_THREADS); returns the size in effect."""
+    return int(lib().hqq_oc_set_threads(int(n)))
 
 
 def _p(a):

@@ -118,36 +118,3 @@ def test_batched_decode_step_equals_independent_sequences(monkeypatch):
     assert len({tuple(r.tolist()) for r in together}) > 1  # the sequences really differ
     with pytest.raises(ValueError):
         harness.DecodeModel(shape, dtype=torch.float64, device="cpu", cache_len=16, fused=False, batch=0)
-
-
-def test_weight_prefetch_spans_follow_the_launch_order():
-    """hqq_b200_decode_desc::pf_* (experimental, HQQ_B200_WPF_MB): each linear launch of the decode step names the packed weights of
-    the launches behind it -- next stage, wrapping into the next block -- as whole 128-byte lines within a byte budget and four spans."""
-    assert harness.wpf_spans([(1000, 300), (5000, 1 << 20)], 0) is None
-    assert harness.wpf_spans([(1024, 300), (8192, 1 << 20)], 1 << 10) == [(1024, 256), (8192, 768)]
-    assert harness.wpf_spans([(i * 4096, 4096) for i in range(6)], 1 << 30) == [(i * 4096, 4096) for i in range(4)]  # at most four spans
-
-    class L:
-        def __init__(self, n):
-            self.W_q = torch.zeros(n, dtype=torch.uint8)
-
-    m = harness.DecodeModel.__new__(harness.DecodeModel)
-    m.blocks = [{k: L(s) for k, s in (("q", 1024), ("k", 256), ("v", 256), ("o", 1024), ("gate", 4096), ("up", 4096), ("down", 4096))} for _ in range(2)]
-    m.wpf_mb, m.wpf_ahead, m.wpf_from = 0.0, 1, harness.parse_wpf_from("")
-    assert m._wpf(0, "qkv") is None  # off by default
-    m.wpf_mb = 1.0
-    ptr = lambda b, n: m.blocks[b][n].W_q.data_ptr()  # noqa: E731
-    assert m._wpf(0, "qkv") == [(ptr(0, "o"), 1024)]
-    assert m._wpf(0, "o") == [(ptr(0, "gate"), 4096), (ptr(0, "up"), 4096)]
-    assert m._wpf(0, "down") == [(ptr(1, "q"), 1024), (ptr(1, "k"), 256), (ptr(1, "v"), 256)]
-    assert m._wpf(1, "down") == [(ptr(0, "q"), 1024), (ptr(0, "k"), 256), (ptr(0, "v"), 256)]  # last block -> the next token's first
-    m.wpf_ahead = 2
-    assert m._wpf(0, "qkv") == [(ptr(0, "o"), 1024), (ptr(0, "gate"), 4096), (ptr(0, "up"), 4096)]
-    m.wpf_mb = 5000 / (1 << 20)
-    assert m._wpf(0, "o") == [(ptr(0, "gate"), 4096), (ptr(0, "up"), 896)]  # budget cut to whole lines
-    m.wpf_from = harness.parse_wpf_from("o, gu")  # only the launches whose prologue runs while HBM idles issue prefetches
-    assert m._wpf(0, "qkv") is None and m._wpf(0, "down") is None
-    assert m._wpf(0, "o") is not None and m._wpf(0, "gu") is not None
-    assert harness.parse_wpf_from("") == frozenset(harness.WPF_STAGES)
-    with pytest.raises(ValueError):
-        harness.parse_wpf_from("o,attention")

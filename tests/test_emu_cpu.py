@@ -148,9 +148,17 @@ def test_emulated_register_solver_equals_the_plain_loop(emu, nbits, gs, shape, s
     b = quantize(emu, W, src, nbits, gs, 1, lp)
     # levels, scale, zero-points and the iteration count are bit-identical; the per-iteration error means come from a different
     # (equally fixed) float32 summation order in the plain one-warp-per-group loop, hence the last-bit tolerance on them only
-    for x, y, what in zip(a[:4], b[:4], ("W_q", "scale", "zero", "info")):
-        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
     assert np.allclose(a[4], b[4], rtol=2e-6, atol=0), "errors"
+    assert np.array_equal(a[1], b[1]), "scale"
+    if int(a[3][0]) == int(b[3][0]):
+        for x, y, what in zip(a[:4], b[:4], ("W_q", "scale", "zero", "info")):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
+    else:
+        # two consecutive error means tie to the last float32 bit and the two summation orders break the tie differently: the early
+        # stop fires one iteration apart (the reference's own torch.mean has a third order) -- zero-points then differ by one update
+        assert abs(int(a[3][0]) - int(b[3][0])) == 1
+        k = min(int(a[3][0]), int(b[3][0]))
+        assert abs(float(a[4][k - 1]) - float(a[4][k - 2])) <= 4e-7 * float(a[4][k - 1])
     assert 1 <= a[3][0] <= 20
 
 
@@ -164,9 +172,17 @@ def test_emulated_register_solver_axis0_equals_the_plain_loop(emu, nbits, gs, sh
     b = quantize(emu, W, src, nbits, gs, 1, lp, axis=0)
     # levels, scale, zero-points and the iteration count are bit-identical; the per-iteration error means come from a different
     # (equally fixed) float32 summation order in the plain one-warp-per-group loop, hence the last-bit tolerance on them only
-    for x, y, what in zip(a[:4], b[:4], ("W_q", "scale", "zero", "info")):
-        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
     assert np.allclose(a[4], b[4], rtol=2e-6, atol=0), "errors"
+    assert np.array_equal(a[1], b[1]), "scale"
+    if int(a[3][0]) == int(b[3][0]):
+        for x, y, what in zip(a[:4], b[:4], ("W_q", "scale", "zero", "info")):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
+    else:
+        # two consecutive error means tie to the last float32 bit and the two summation orders break the tie differently: the early
+        # stop fires one iteration apart (the reference's own torch.mean has a third order) -- zero-points then differ by one update
+        assert abs(int(a[3][0]) - int(b[3][0])) == 1
+        k = min(int(a[3][0]), int(b[3][0]))
+        assert abs(float(a[4][k - 1]) - float(a[4][k - 2])) <= 4e-7 * float(a[4][k - 1])
 
 
 @pytest.mark.parametrize("N,K", [(16, 64), (10, 128), (33, 256), (7, 640), (50, 1024), (3, 64), (1, 128)])
@@ -272,16 +288,6 @@ def test_emulated_one_token_prologues_and_paired_epilogue(emu, oracle, tmp_path_
         assert np.array_equal(d[f"dec{ci}_x1pair_h"], t)
 
 
-@pytest.mark.parametrize("variant", [32, 1042, 2042, 3042, 1033, 4042, 7042, 7033])
-def test_emulated_one_token_kernel_variants_are_bit_identical(emu, tmp_path_factory, variant):
-    """The experimental M = 1 kernel variants (scale/zero through the cp.async ring, evict-first hint, 3 CTAs per SM, L2 prefetch
-    under the dependency wait) executed on the emulator: every output equals the default kernel's bit for bit."""
-    ref, got = run_small(tmp_path_factory), run_small(tmp_path_factory, variant)
-    assert ref.keys() == got.keys()
-    for k in ref:
-        assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
-
-
 # ---------------------------------------------------------------------------------------------------------------------------
 # csrc/linear_gemm.cu on the emulator's functional model of mbarrier / TMA (SWIZZLE_128B) / UMMA descriptors / tcgen05.mma /
 # TMEM / tcgen05.ld: addresses, swizzles, barrier phases and who-waits-for-whom are executed; timing, async proxies and memory
@@ -317,33 +323,27 @@ def test_emulated_tcgen05_gemm_matches_the_oracle(emu, tmp_path_factory):
         assert int(d[k[:-4] + "_ws"][0]) == 0  # no default route needs scratch
 
 
-@pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_VARIANT", "ld512"),
-                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_UN", "128")])
-def test_emulated_gemm_variants_are_bit_identical(emu, tmp_path_factory, knob):
-    """un512 (two accumulators per dequantised weight tile), ld (loader warp + cp.async rings), dq16 (sixteen dequant warps) and the UN cap issue the same MMAs in
-    the same k order as the default kernel: identical outputs, and no barrier protocol that stalls."""
+@pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_CTAS", "1"), ("HQQ_B200_GEMM_CTAS", "3"), ("HQQ_B200_GEMM_CTAS", "5")])
+def test_emulated_persistent_gemm_schedules_are_bit_identical(emu, tmp_path_factory, knob):
+    """The persistent kernel with its grid capped to 1 / 3 / 5 CTAs: every CTA then walks several tiles (both TMEM accumulators,
+    epilogue of tile i under the main loop of tile i + 1, rings running across tile boundaries, the half-tile round of the
+    schedule) and issues the same MMAs in the same k order per output element as the one-tile-per-CTA run: identical outputs,
+    and no barrier protocol that stalls."""
     ref, got = run_gemm_emu(tmp_path_factory), run_gemm_emu(tmp_path_factory, knob)
     for k in ref:
         if not k.endswith("_ws"):
             assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
 
 
-def test_emulated_splitk_gemm(emu, tmp_path_factory):
-    """Split-K: k-slices in TMEM, fp32 partials in a (dirty) workspace, last-arriver reduction in slice order -- equal to the
-    one-accumulator kernel up to fp32 summation order, identical run to run, and the tile counters are left clean."""
-    ref, got = run_gemm_emu(tmp_path_factory), run_gemm_emu(tmp_path_factory, ("HQQ_B200_GEMM_SPLITK", "1"))
-    split = [k[:-3] for k in got if k.endswith("_ws") and int(got[k][0]) > 0]
-    assert len(split) >= 5  # the case list holds few-tile / long-K shapes on purpose
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulated_persistent_gemm_under_adversarial_timing(emu, tmp_path_factory, seed):
+    """EMU_ASYNC: TMA copies, tensor-core operations and their commits land a random number of scheduler passes late and threads
+    resume in random order; the capped grid keeps several tiles per CTA in flight.  Same bits as the in-order run."""
+    ref = run_gemm_emu(tmp_path_factory)
+    got = run_gemm_emu(tmp_path_factory, ("HQQ_B200_GEMM_CTAS", "2"), async_seed=seed)
     for k in ref:
-        if k.endswith("_ws"):
-            continue
-        base = k[:-6] if k.endswith("_again") else (k[:-4] if k.endswith("_ref") else k)
-        if base in split and not k.endswith("_ref"):
-            assert rel(got[k], ref[k]) <= 1e-4, k
-        else:
+        if not k.endswith("_ws"):
             assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
-    for b in split:
-        assert np.array_equal(got[b], got[b + "_again"]), b  # second launch on the same workspace: counters were reset
 
 
 @pytest.mark.parametrize("tp", [2, 8])
@@ -388,23 +388,8 @@ def test_emulated_forward_random_shapes(emu, oracle):
     assert routes == {1, 2}
 
 
-@pytest.mark.parametrize("knob", [None, ("HQQ_B200_GEMM_VARIANT", "un512"), ("HQQ_B200_GEMM_VARIANT", "ld"), ("HQQ_B200_GEMM_VARIANT", "ld512"),
-                                  ("HQQ_B200_GEMM_VARIANT", "dq16"), ("HQQ_B200_GEMM_VARIANT", "un512dq"), ("HQQ_B200_GEMM_SPLITK", "1")])
-def test_emulated_gemm_pipelines_under_adversarial_timing(emu, tmp_path_factory, knob):
-    """The emulator as a protocol checker: TMA copies, tensor-core operations (operands read when they EXECUTE, commits after them)
-    and mbarrier-tied cp.async land a random number of scheduler passes after issue, and threads are resumed in random order.  A
-    pipeline that reads a stage before its full barrier, or refills one before its empty barrier, computes garbage or deadlocks
-    here (checked by removing a wait while developing this); a correct one reproduces the in-order result bit for bit."""
-    ref = run_gemm_emu(tmp_path_factory, knob)
-    for seed in (1, 2):
-        got = run_gemm_emu(tmp_path_factory, knob, async_seed=seed)
-        for k in ref:
-            assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), (k, seed)
-
-
 def test_emulated_reload_env_switches_cached_knobs_in_one_process(emu):
-    """`hqq_b200_reload_env()` (what DecodeModel.retune and bench.py's autotuner rely on): a changed HQQ_B200_* knob is ignored until
-    the reload, honoured after it, and the one-token kernel variants it selects stay bit-identical inside ONE process."""
+    """`hqq_b200_reload_env()`: a changed HQQ_B200_* switch is ignored until the reload and honoured after it."""
     import json
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_reload.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -413,8 +398,6 @@ def test_emulated_reload_env_switches_cached_knobs_in_one_process(emu):
     assert out["cached_rc"] == 0 and out["cached_same"]          # no reload: the cached choice stands
     assert out["reloaded_rc"] == -2                              # HQQ_E_UNSUPPORTED once HQQ_B200_DECODE1=0 is seen
     assert out["restored_rc"] == 0 and out["restored_same"]
-    for v in ("1042", "2042", "4042", "7042"):
-        assert out[f"variant_{v}"] == [0, True], v
 
 
 @pytest.mark.parametrize("variant,cases", [(0, [(4, 0), (4, 1), (2, 0), (2, 1), (1, 0), (1, 1)]), (1, [(4, 1), (2, 0)])])

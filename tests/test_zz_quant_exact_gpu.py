@@ -12,7 +12,6 @@ pytestmark = pytest.mark.gpu
 COMBOS = [(nbits, axis, gs) for nbits in (8, 4, 3, 2, 1) for axis in (0, 1) for gs in ((64,) if nbits != 4 else (64, 32, 128))]
 
 
-@pytest.mark.xfail(strict=False, reason="stricter than the validated bound; written after round 1's GPU budget was spent")
 @pytest.mark.parametrize("nbits,axis,gs", COMBOS)
 def test_solver_levels_equal_the_reference_fixtures(golden, oracle, nbits, axis, gs):
     q = golden.quant
@@ -25,7 +24,6 @@ def test_solver_levels_equal_the_reference_fixtures(golden, oracle, nbits, axis,
     assert np.array_equal(oracle.UNPACK[pk](W_q.cpu().numpy())[:rows], oracle.UNPACK[pk](q[key + "/W_q"])[:rows])
 
 
-@pytest.mark.xfail(strict=False, reason="fixture and test added after round 1's GPU budget was spent")
 @pytest.mark.parametrize("nbits,axis", [(nbits, axis) for nbits in (4, 2, 1) for axis in (0, 1)])
 def test_solver_on_heavy_tailed_weights(golden, oracle, nbits, axis):
     """quantize_heavy: the shrinkage's |x|^(p-1) branch is active, i.e. the SFU's ex2 / lg2 take part.  Bound: the validated suite's

@@ -10,7 +10,6 @@ from hqq_b200.models.tp import shard_bounds, shard_hqq_linear
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; not yet seen on a GPU")
 @pytest.mark.parametrize("nbits", (4, 3, 2))
 def test_shards_dequantise_to_slices_and_recombine(nbits):
     dev = "cuda:0"
@@ -38,7 +37,6 @@ def test_shards_dequantise_to_slices_and_recombine(nbits):
     assert tuple(int(v) for v in sd["shape"]) == (N // tp, K)
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; not yet seen on a GPU")
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_tensor_parallel_model_equals_the_one_gpu_model_on_the_same_quantised_weights():
     """tools/tp_vs_single.py: shards cut out of the unsharded quantisation -> TP = 2 decodes the one-GPU model's tokens."""
