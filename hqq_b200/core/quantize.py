@@ -18,7 +18,7 @@ from enum import Enum
 from typing import Union
 
 import torch
-from torch import Tensor, float16, int32, nn, uint8
+from torch import Tensor, bfloat16, float16, int32, nn, uint8
 
 from .. import ops
 from .bitpack import BitPack
@@ -219,7 +219,7 @@ class HQQMatmulNoCacheMul(torch.autograd.Function):
         x, bias = ctx.saved_tensors
         grad_input = grad_bias = None
         if ctx.needs_input_grad[0]:
-            grad_input = torch.matmul(grad_output, ctx.layer.dequantize())
+            grad_input = ctx.layer.matmul(grad_output, transpose=False)  # grad @ W_r on the dense tcgen05 kernel (W_r^T as the weight)
         if bias is not None and ctx.needs_input_grad[2]:
             grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(0)
         return grad_input, None, grad_bias
@@ -488,7 +488,13 @@ class HQQLinear(nn.Module):
     def matmul(self, x: Tensor, transpose: bool = True) -> Tensor:
         if transpose:
             return self._fused_forward(x, with_bias=False)
-        return torch.matmul(x, self.dequantize())
+        # x @ W_r (the backward of the forward, quantize.py:322-352): the dense tcgen05 GEMM on W_r^T -- K and N swap roles
+        W_r = self.dequantize()
+        if x.is_cuda and x.dtype in (float16, bfloat16) and W_r.dtype == x.dtype:
+            out = ops.dense_gemm(x.reshape(-1, W_r.shape[0]), W_r.t().contiguous())
+            if out is not None:
+                return out.reshape(*x.shape[:-1], W_r.shape[1])
+        return torch.matmul(x, W_r)
 
     # ------------------------------------------------------------------ the one forward path
     def _fused_forward(self, x: Tensor, with_bias: bool = True) -> Tensor:
@@ -506,8 +512,14 @@ class HQQLinear(nn.Module):
             y = ops.linear_fwd(x2d, self.W_q, meta["scale"], meta["zero"], bias, N, K, gs, int(nbits), meta["axis"])
             if y is not None:
                 return y.reshape(*x.shape[:-1], N)
-        # configuration outside the fused kernels: CUDA dequantize kernel + library GEMM (still no CPU arithmetic)
-        out = torch.matmul(x, self.dequantize().t())
+        # what no route of hqq_b200_linear_fwd covers (float32 compute, quantised meta): our dequantize kernel, then the dense
+        # tcgen05 GEMM when the compute dtype allows it; float32 has no tensor-core path here and goes to the library GEMM
+        W_r = self.dequantize()
+        x2d = x.reshape(-1, K)
+        out = ops.dense_gemm(x2d, W_r.to(x.dtype), bias) if (x.is_cuda and x.dtype in (float16, bfloat16)) else None
+        if out is not None:
+            return out.reshape(*x.shape[:-1], N)
+        out = torch.matmul(x, W_r.t())
         if bias is not None:
             out += bias
         return out

@@ -13,25 +13,34 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int gs, int nbits, int dtype);
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int gs, int nbits, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
-bool fused3_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
-size_t fused3_workspace_bytes(int64_t N);
-int linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N, int64_t K,
-                  int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+bool dense_route_ok(int64_t M, int64_t N, int64_t K, int dtype);
+int linear_dense(const void* x, const void* W, const void* bias, void* y, int64_t M, int64_t N, int64_t K, int dtype, cudaStream_t st);
 }  // namespace hqq
 
 using namespace hqq;
 
+// what hqq_b200_dequantize accepts (bitpack.cu): every width, both axes, any group size that divides the tensor
+static bool dequant_ok(int64_t N, int64_t K, int gs, int nbits, int axis) {
+  if (!valid_nbits(nbits) || !(axis == 0 || axis == 1) || gs <= 0 || N <= 0 || K <= 0 || (N * K) % gs != 0) return false;
+  const int64_t R = axis == 1 ? N * K / gs : gs;
+  return nbits == 3 || R % fields_of(nbits) == 0;
+}
+
+static size_t dense_ws_bytes(int64_t N, int64_t K, int dtype) { return (size_t)((N * K * (int64_t)dtype_size(dtype) + 255) & ~(int64_t)255); }
+
 extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {
   if (small_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 1;
   if (gemm_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 2;
-  if (fused3_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 3;  // opt-in (HQQ_B200_FUSED_3BIT=1), one token, 3-bit
+  if (dequant_ok(N, K, group_size, nbits, axis) && dense_route_ok(M, N, K, dtype)) return 3;  // dequantize kernel -> dense tcgen05 GEMM
   return 0;
 }
 
-extern "C" size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int dtype) {
-  if (small_route_ok(M, N, K, group_size, nbits, 1, dtype)) return small_workspace_bytes(M);
-  if (gemm_route_ok(M, N, K, group_size, nbits, 1, dtype)) return gemm_workspace_bytes(M, N, K, group_size, nbits, dtype);
-  if (fused3_route_ok(M, N, K, group_size, nbits, 1, dtype)) return fused3_workspace_bytes(N);
+extern "C" size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {
+  switch (hqq_b200_linear_fwd_route(M, N, K, group_size, nbits, axis, dtype)) {
+    case 1: return small_workspace_bytes(M);
+    case 2: return gemm_workspace_bytes(M, N, K, group_size, nbits, dtype);
+    case 3: return dense_ws_bytes(N, K, dtype);  // W_r, written by the dequantize kernel and read back (mostly from L2) by the GEMM
+  }
   return 0;
 }
 
@@ -53,10 +62,22 @@ extern "C" int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* s
   const int route = hqq_b200_linear_fwd_route(M, N, K, group_size, nbits, axis, dtype);
   if (route == 1) return linear_small_multi(x, 1, &W_q, &scale, &zero, &bias, &y, &N, M, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
   if (route == 2) return linear_gemm(x, W_q, scale, zero, bias, y, M, N, K, group_size, nbits, dtype, workspace, workspace_bytes, st);
-  if (route == 3) return linear_fused3(x, W_q, scale, zero, bias, y, N, K, dtype, workspace, workspace_bytes, st);
+  if (route == 3) {
+    HQQ_REQUIRE(workspace != nullptr && workspace_bytes >= dense_ws_bytes(N, K, dtype) && aligned(workspace, 256), HQQ_E_WORKSPACE,
+                "hqq_b200_linear_fwd: this configuration runs dequantize + dense GEMM and needs a 256-byte aligned workspace of %zu bytes (got %zu)",
+                dense_ws_bytes(N, K, dtype), workspace_bytes);
+    rc = hqq_b200_dequantize(W_q, scale, zero, workspace, N, K, group_size, nbits, axis, dtype, stream);
+    if (rc) return rc;
+    return linear_dense(x, workspace, bias, y, M, N, K, dtype, st);
+  }
   set_error("hqq_b200_linear_fwd: no fused kernel for M=%lld N=%lld K=%lld gs=%d nbits=%d axis=%d dtype=%d", (long long)M, (long long)N,
             (long long)K, group_size, nbits, axis, dtype);
   return HQQ_E_UNSUPPORTED;
+}
+
+extern "C" int hqq_b200_dense_gemm(const void* x, const void* W, const void* bias, void* y, int64_t M, int64_t N, int64_t K, int dtype,
+                                   void* stream) {
+  return linear_dense(x, W, bias, y, M, N, K, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, const void* const* scale,

@@ -95,6 +95,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) { :
 #define HQQ_STS_V4(addr, a, b, c, d) ::emu::sts(addr, a, b, c, d)
 #define HQQ_STS_V2(addr, a, b) ::emu::sts(addr, a, b)
 #define HQQ_PREFETCH_TENSORMAP(p) ((void)(p))
+#define HQQ_PREFETCH_L2(p) ((void)(p))
 #define HQQ_NAMED_BAR_SYNC(id, n) ::emu::named_barrier(id, n)
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,6 +169,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 #define HQQ_STS_V4(addr, a, b, c, d) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
 #define HQQ_STS_V2(addr, a, b) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory")
 #define HQQ_PREFETCH_TENSORMAP(p) asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory")
+#define HQQ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define HQQ_NAMED_BAR_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(n) : "memory")
 #endif  // HQQ_EMU
 
@@ -251,12 +253,17 @@ struct Smem {
   static constexpr int BYTES = kStages * (A_STAGE + B_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// NBITS = 16 ("dense"): the A operand is an ordinary [N, K] fp16/bf16 matrix fetched by TMA like B -- the dequant warps idle.  It is
+// the second half of the routes no fused expansion exists for (3-bit's 10-field int32 slabs, axis = 0 groups, other group sizes,
+// the backward pass): our dequantize kernel writes W_r once, this kernel multiplies (hqq_b200_linear_fwd route 4).
 template <typename T, int NBITS, int GS>
 __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_constant__ CUtensorMap xmap256,
-                                                                  const __grid_constant__ CUtensorMap xmap128, const Args a) {
-  constexpr int F = 8 / NBITS;             // slabs per byte
+                                                                  const __grid_constant__ CUtensorMap xmap128,
+                                                                  const __grid_constant__ CUtensorMap amap, const Args a) {
+  constexpr bool DENSE = NBITS == 16;
+  constexpr int F = DENSE ? 1 : 8 / NBITS;  // slabs per byte
   constexpr int PR = kTileRows / F;        // packed rows per tile
-  constexpr int BPT = 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
+  constexpr int BPT = DENSE ? 32 : 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
   static_assert(BPT >= 4, "a dequant thread expands at least four packed bytes per k-block");
   constexpr int TPR = 64 / BPT;            // dequant threads per packed row
   constexpr uint32_t MASK = (1u << NBITS) - 1u;
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = a.K / kBlockK;
+  const int num_kb = (a.K + kBlockK - 1) / kBlockK;  // quantised routes: K % 256 == 0; dense: the TMA zero-fills a ragged last block
   const int n_items = a.sched.n_items;
 
   if (warp == 0) {
@@ -286,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       fence_barrier_init();
       HQQ_PREFETCH_TENSORMAP(&xmap256);
       HQQ_PREFETCH_TENSORMAP(&xmap128);
+      if constexpr (DENSE) HQQ_PREFETCH_TENSORMAP(&amap);
     }
     __syncwarp();
     tmem_alloc<kTmemCols>(tmem_slot);
@@ -305,13 +313,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          constexpr uint32_t A_TX = DENSE ? S::A_STAGE : 0;  // dense: the weight tile rides the same barrier
           if (im.un == kUN) {
-            mbar_expect_tx(&full_b[s], S::B_STAGE);
+            mbar_expect_tx(&full_b[s], S::B_STAGE + A_TX);
             tma_load_2d(sB + s * S::B_STAGE, &xmap256, &full_b[s], kb * kBlockK, im.m0);
           } else {
-            mbar_expect_tx(&full_b[s], S::B_STAGE / 2);
+            mbar_expect_tx(&full_b[s], S::B_STAGE / 2 + A_TX);
             tma_load_2d(sB + s * S::B_STAGE, &xmap128, &full_b[s], kb * kBlockK, im.m0);
           }
+          if constexpr (DENSE) tma_load_2d(sA + s * S::A_STAGE, &amap, &full_b[s], kb * kBlockK, im.tile_n * kTileRows);
         }
       }
     }
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full_a[s], ph);
+        if constexpr (!DENSE) mbar_wait(&full_a[s], ph);
         mbar_wait(&full_b[s], ph);
         tc_fence_after();
         if (lane == 0) {
@@ -346,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       ++q;
     }
   } else if (warp < 2 + kDequantThreads / 32) {
+    if constexpr (!DENSE) {
     // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
     static_assert(kStages == 4, "the dequant loop is unrolled over the 4 ring stages");
     const int td = threadIdx.x - 64;
@@ -414,6 +425,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           wptr += 4 * kBlockK;
 #pragma unroll
           for (int f = 0; f < F; ++f) { sptr[f] += GPQ; zptr[f] += GPQ; }
+          // the register prefetch reaches one quad ahead, about 1 us of main loop at small M -- less than a DRAM round trip under
+          // load when a weight tile is read for the first time (M <= 512: every tile is); pull the line this thread will load
+          // three quads from now into L2 (a packed row has 256 bytes = two lines per quad: even / odd threads of the row take one each)
+          if (q + 4 < num_quads) HQQ_PREFETCH_L2(wptr + 3 * 4 * kBlockK + (c & 1) * 128);
           load_quad();
         } else if (jn < n_items) {
           tile_ptrs(decode_item(a, jn).tile_n);
@@ -451,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       }
       j = jn;
     }
+    }  // !DENSE
   } else {
     // ================= epilogue warps: TMEM -> registers -> y, one tile behind the main loop =================
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
@@ -518,12 +534,13 @@ static EncodeTiledFn get_encode() {
 }
 
 
-static int encode_xmap(CUtensorMap* xmap, const void* x, const Args& a, CUtensorMapDataType dt, size_t esize, int box_tokens) {
+// [rows, K] row-major 16-bit matrix, boxes of 64 k x `box_rows` rows, 128B swizzle, out-of-range elements read as zero
+static int encode_map(CUtensorMap* xmap, const void* x, int64_t rows, int64_t K, CUtensorMapDataType dt, size_t esize, int box_rows) {
   EncodeTiledFn enc = get_encode();
   HQQ_REQUIRE(enc != nullptr, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
-  const cuuint64_t strides[1] = {(cuuint64_t)a.K * esize};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_tokens};
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * esize};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(xmap, dt, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -550,14 +567,20 @@ Sched make_sched(int64_t M, int64_t row_tiles, int P) {
 }
 
 template <typename T, int NBITS, int GS>
-static int launch(const void* x, Args& a, cudaStream_t st) {
-  CUtensorMap xmap256, xmap128;
+static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W = nullptr) {
+  CUtensorMap xmap256, xmap128, amap;
   const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  int rc = encode_xmap(&xmap256, x, a, dt, sizeof(T), kUN);
+  int rc = encode_map(&xmap256, x, a.M, a.K, dt, sizeof(T), kUN);
   if (rc) return rc;
-  rc = encode_xmap(&xmap128, x, a, dt, sizeof(T), kUN / 2);
+  rc = encode_map(&xmap128, x, a.M, a.K, dt, sizeof(T), kUN / 2);
   if (rc) return rc;
-  constexpr int PR = kTileRows / (8 / NBITS);
+  if (NBITS == 16) {
+    rc = encode_map(&amap, dense_W, a.N, a.K, dt, sizeof(T), kTileRows);
+    if (rc) return rc;
+  } else {
+    amap = xmap128;  // unused
+  }
+  constexpr int PR = NBITS == 16 ? kTileRows : kTileRows / (NBITS == 16 ? 1 : 8 / NBITS);
   // HQQ_B200_GEMM_CTAS=<n> (test hook): cap the persistent grid, so that small problems exercise tile-after-tile execution, both
   // accumulators and the half-tile round (the emulator tests and tests/test_linear_gpu.py set it; results never depend on it)
   HQQ_ENV_KNOB(cta_cap, ([] { const char* e = getenv("HQQ_B200_GEMM_CTAS"); return e ? atoi(e) : 0; })());
@@ -574,7 +597,7 @@ static int launch(const void* x, Args& a, cudaStream_t st) {
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem::BYTES, cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  k<<<grid, kThreads, Smem::BYTES, st>>>(xmap256, xmap128, a);
+  k<<<grid, kThreads, Smem::BYTES, st>>>(xmap256, xmap128, amap, a);
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   return HQQ_OK;
 }
@@ -610,6 +633,26 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
 }
 
 size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+
+// y[M, N] = x[M, K] @ W[N, K]^T (+ bias), W an ordinary fp16/bf16 matrix: the same persistent tcgen05 kernel with both operands on TMA
+bool dense_route_ok(int64_t M, int64_t N, int64_t K, int dtype) {
+  if (dtype != HQQ_F16 && dtype != HQQ_BF16) return false;
+  return M >= 1 && N >= 1 && K >= 8 && K % 8 == 0 && N <= (1 << 28) && K <= (1 << 28) && M <= (1 << 28);  // 16-byte row pitch for the TMA
+}
+
+int linear_dense(const void* x, const void* W, const void* bias, void* y, int64_t M, int64_t N, int64_t K, int dtype, cudaStream_t st) {
+  HQQ_REQUIRE(x && W && y, HQQ_E_INVALID, "hqq_b200_dense_gemm: null pointer");
+  HQQ_REQUIRE(dense_route_ok(M, N, K, dtype), HQQ_E_UNSUPPORTED, "hqq_b200_dense_gemm: needs fp16/bf16 and K a multiple of 8 (M=%lld N=%lld K=%lld)",
+              (long long)M, (long long)N, (long long)K);
+  HQQ_REQUIRE(aligned(x, 16) && aligned(W, 16), HQQ_E_INVALID, "hqq_b200_dense_gemm: x and W must be 16-byte aligned");
+  gemm::Args a;
+  a.Wq = nullptr; a.scale = nullptr; a.zero = nullptr; a.bias = bias; a.y = y;
+  a.M = (int)M; a.N = (int)N; a.K = (int)K;
+  a.step = (int)N;  // one "slab": tile row t is weight row tile_n * 128 + t
+  a.Gk = 0;
+  if (dtype == HQQ_F16) return gemm::launch<__half, 16, 64>(x, a, st, W);
+  return gemm::launch<__nv_bfloat16, 16, 64>(x, a, st, W);
+}
 
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M, int64_t N,
                 int64_t K, int gs, int nbits, int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {

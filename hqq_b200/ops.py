@@ -178,11 +178,30 @@ def linear_fwd(x2d: torch.Tensor, W_q: torch.Tensor, scale: torch.Tensor, zero: 
         return None
     dev = x2d.device
     y = out if out is not None else torch.empty((M, N), dtype=dtype, device=dev)
-    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, N, K, int(group_size), int(nbits), code)
+    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, N, K, int(group_size), int(nbits), int(axis), code)
     ws = _workspace(ws_bytes, dev)
     with _on(dev):
         rc = lib.hqq_b200_linear_fwd(ptr(x2d), ptr(W_q), ptr(scale), ptr(zero), ptr(bias), ptr(y), M, N, K, int(group_size),
                                      int(nbits), int(axis), code, ptr(ws), ws_bytes, stream_ptr(dev))
+    if rc == HQQ_E_UNSUPPORTED:
+        return None
+    check(rc)
+    return y
+
+
+def dense_gemm(x2d: torch.Tensor, W: torch.Tensor, bias=None, out: torch.Tensor | None = None) -> torch.Tensor | None:
+    """y = x2d @ W.T (+ bias) for an ordinary fp16/bf16 [N, K] matrix through the dense tcgen05 kernel (`hqq_b200_dense_gemm`);
+    None when the shape / dtype is outside it (fp32, K not a multiple of 8)."""
+    _lib.require_cuda(x2d, "the activation passed to dense_gemm")
+    code = DTYPE_CODE.get(x2d.dtype, -1)
+    M, K = x2d.shape
+    N = W.shape[0]
+    if code not in (DTYPE_CODE[torch.float16], DTYPE_CODE[torch.bfloat16]) or W.dtype != x2d.dtype or W.shape[1] != K or K % 8:
+        return None
+    x2d, W = x2d.contiguous(), W.contiguous()
+    y = out if out is not None else torch.empty((M, N), dtype=x2d.dtype, device=x2d.device)
+    with _on(x2d.device):
+        rc = load().hqq_b200_dense_gemm(ptr(x2d), ptr(W), ptr(bias), ptr(y), M, N, K, code, stream_ptr(x2d.device))
     if rc == HQQ_E_UNSUPPORTED:
         return None
     check(rc)
@@ -223,7 +242,7 @@ def linear_fwd_multi(x2d: torch.Tensor, layers, outs=None):
         outs = [torch.empty((M, N), dtype=dtype, device=dev) for N in Ns]
     VP = ctypes.c_void_p * n
     arr = lambda ts: VP(*[ptr(t) for t in ts])
-    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, Ns[0], K, int(gs), nbits, code)
+    ws_bytes = lib.hqq_b200_linear_fwd_workspace_bytes(M, Ns[0], K, int(gs), nbits, int(axis), code)
     ws = _workspace(ws_bytes, dev)
     Narr = (ctypes.c_int64 * n)(*Ns)
     with _on(dev):

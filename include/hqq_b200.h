@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HQQ_B200_ABI_VERSION 1
+#define HQQ_B200_ABI_VERSION 2
 
 /* element types */
 enum {
@@ -116,18 +116,25 @@ int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int64_t K,
  * i.e. y = x @ dequantize(W_q).T + bias, as ONE fused unpack->dequant->MMA kernel.
  *   hqq/core/quantize.py:880-898 ; semantic template hqq/kernels/hqq_aten_torch.cpp:79-107
  *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
- *   axis must be 1.  Returns HQQ_E_UNSUPPORTED for configurations the fused kernels do
- *   not cover (the Python layer then runs hqq_b200_dequantize + a library GEMM).
- *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, 256-byte aligned scratch owned by the caller.  0 for every
- *   default route (split-K partials of the small-M kernel meet in shared memory); non-zero only for the opt-in
- *   kernels that need global scratch (HQQ_B200_GEMM_SPLITK=1: fp32 k-slice partials + tile counters;
- *   HQQ_B200_FUSED_3BIT=1: three fp32 slots per output row).  Contents on entry are irrelevant.                    */
+ *   Routes (hqq_b200_linear_fwd_route): 1 = small-M weight-streaming kernel (M <= 32), 2 = fused tcgen05 GEMM -- both axis 1,
+ *   nbits 8/4/2/1, group_size 64/128, K % 256 == 0 -- and 3 = everything else hqq_b200_dequantize accepts (3-bit, axis 0, other
+ *   group sizes, ragged K): the dequantize kernel writes W_r into `workspace`, the dense tcgen05 GEMM multiplies.  Returns
+ *   HQQ_E_UNSUPPORTED where none applies (fp32 compute).
+ *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, 256-byte aligned scratch owned by the caller: 0 for routes 1 and 2
+ *   (split-K partials of the small-M kernel meet in shared memory), N*K*sizeof(dtype) for route 3.  Contents on entry are
+ *   irrelevant.                                                                                                        */
 size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size,
-                                           int nbits, int dtype);
+                                           int nbits, int axis, int dtype);
 int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero,
                         const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                         int group_size, int nbits, int axis, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* y[M,N] = x[M,K] @ W[N,K]^T (+ bias) for an ordinary fp16/bf16 matrix W: the persistent tcgen05 kernel of route 2 with both
+ * operands on TMA.  Used by route 3 and by the backward pass of HQQMatmulNoCacheMul (grad_out @ W_r, hqq/core/quantize.py:322-352:
+ * W = W_r^T).  K % 8 == 0 (16-byte row pitch), x / W 16-byte aligned.                                                        */
+int hqq_b200_dense_gemm(const void* x, const void* W, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                        int dtype, void* stream);
 
 /* Several HQQLinear layers that consume the SAME activation (q/k/v, gate/up) in one launch of the small-M kernel:
  * the 16-row tiles of all `count` (<= 4) matrices form one stream-K work list, so small matrices no longer pay a
@@ -139,9 +146,8 @@ int hqq_b200_linear_fwd_multi(const void* x, int count, const void* const* W_q, 
                               int64_t M, int64_t K, int group_size, int nbits, int axis, int dtype,
                               void* workspace, size_t workspace_bytes, void* stream);
 
-/* Which fused kernel hqq_b200_linear_fwd would use: 0 none (unsupported), 1 small-M
- * mma.sync weight-streaming kernel, 2 tcgen05/TMA GEMM, 3 the 3-bit one-token kernel
- * (only with HQQ_B200_FUSED_3BIT=1; 3-bit is route 0 otherwise).                         */
+/* Which kernels hqq_b200_linear_fwd would use: 0 none (unsupported), 1 small-M mma.sync weight-streaming kernel,
+ * 2 fused tcgen05/TMA GEMM, 3 dequantize kernel + dense tcgen05 GEMM.                                         */
 int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits,
                               int axis, int dtype);
 

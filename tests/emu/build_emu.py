@@ -15,23 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "hqq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libhqq_b200_emu.so")
-SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear3.cu", "linear_small.cu", "linear_gemm.cu", "linear.cu"]
+SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear_small.cu", "linear_gemm.cu", "linear.cu"]
 CUDA_INC = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
-EXTRA = r'''
-// C entry points for internals that the real library reaches through hqq_b200_linear_fwd's router
-#include "common.cuh"
-namespace hqq {
-size_t fused3_workspace_bytes(int64_t N);
-int linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N, int64_t K,
-                  int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
-}
-extern "C" size_t emu_fused3_workspace_bytes(int64_t N) { return hqq::fused3_workspace_bytes(N); }
-extern "C" int emu_linear_fused3(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t N,
-                                 int64_t K, int dtype, void* ws, size_t ws_bytes) {
-  return hqq::linear_fused3(x, Wq, scale, zero, bias, y, N, K, dtype, ws, ws_bytes, nullptr);
-}
-'''
+EXTRA = ''
 
 
 def rewrite(src: str) -> str:

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version(lib):
-    assert lib.hqq_b200_abi_version() == 1
+    assert lib.hqq_b200_abi_version() == 2
 
 
 def test_argument_validation_uses_reference_wording(lib):

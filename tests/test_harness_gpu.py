@@ -90,25 +90,29 @@ def test_paired_silu_mul_epilogue_is_bit_identical(dt, nbits, N):
     assert torch.equal(act, ref)
 
 
-def test_l2_hint_is_a_pure_hint():
-    """The KV-cache L2 warm-up of the q/k/v launch changes no result; a malformed hint is rejected."""
+def test_ring_and_register_meta_paths_of_the_one_token_kernel_agree():
+    """K % 512 == 0 with 16-byte aligned scale/zero rows takes the shipped kernel (scale/zero on the cp.async ring); a view whose meta
+    rows start 8 bytes off takes the register-load instantiation of the same kernel.  Same bits."""
     from hqq_b200 import ops
     from hqq_b200.core.quantize import BaseQuantizeConfig, HQQLinear
-    torch.manual_seed(5)
-    lin = HQQLinear.from_weights((torch.randn(512, 1024, device=DEV) * 0.05).half(), None, BaseQuantizeConfig(nbits=4, group_size=64, axis=1),
-                                 compute_dtype=torch.float16, device=DEV)
-    x = torch.randn(1, 1024, device=DEV).half()
-    kc, vc = (torch.randn(1, 2, 64, 128, device=DEV).half() for _ in range(2))
-    pos = torch.tensor([37], device=DEV)
-    y0, y1 = torch.empty(1, 512, device=DEV, dtype=torch.float16), torch.empty(1, 512, device=DEV, dtype=torch.float16)
-    assert ops.decode_linear_fwd(x, (lin,), [y0])
-    hint = {"ptrs": (kc.data_ptr(), vc.data_ptr()), "rows": pos.data_ptr(), "chunks": 2, "row_bytes": 256, "chunk_stride": 64 * 256}
-    kc0, vc0 = kc.clone(), vc.clone()
-    assert ops.decode_linear_fwd(x, (lin,), [y1], l2_hint=hint)
-    torch.cuda.synchronize()
-    assert torch.equal(y0, y1) and torch.equal(kc, kc0) and torch.equal(vc, vc0)
-    with pytest.raises(Exception):
-        ops.decode_linear_fwd(x, (lin,), [y1], l2_hint=dict(hint, row_bytes=100))
+    for dt in (torch.float16, torch.bfloat16):
+        for nbits in (4, 2, 1):
+            torch.manual_seed(5 + nbits)
+            lin = HQQLinear.from_weights((torch.randn(512, 1024, device=DEV) * 0.05).to(dt), None, BaseQuantizeConfig(nbits=nbits, group_size=64, axis=1),
+                                         compute_dtype=dt, device=DEV)
+            x = torch.randn(1, 1024, device=DEV).to(dt)
+            y0, y1 = (torch.empty(1, 512, device=DEV, dtype=dt) for _ in range(2))
+            assert ops.decode_linear_fwd(x, (lin,), [y0])
+            # same values, scale / zero shifted by 4 elements (8 bytes): the ring's aligned 16-byte copies are not legal there
+            s, z = lin.meta["scale"], lin.meta["zero"]
+            for name, t in (("scale", s), ("zero", z)):
+                buf = torch.empty(t.numel() + 4, device=DEV, dtype=t.dtype)
+                buf[4:].copy_(t.view(-1))
+                lin.meta[name] = buf[4:].view(t.shape)
+            assert lin.meta["scale"].data_ptr() % 16 == 8
+            assert ops.decode_linear_fwd(x, (lin,), [y1])
+            torch.cuda.synchronize()
+            assert torch.equal(y0, y1), (dt, nbits)
 
 
 def test_paired_epilogue_rejects_what_it_cannot_pair():
