@@ -58,6 +58,9 @@ SIGNATURES = {
 }
 
 
+ABI_VERSION = 2  # HQQ_B200_ABI_VERSION of include/hqq_b200.h this binding was written against
+
+
 class DecodeDesc(ctypes.Structure):
     """Mirror of `hqq_b200_decode_desc` (include/hqq_b200.h)."""
     _fields_ = [("x", c_void_p), ("x_op", c_int), ("x2", c_void_p), ("x_weight", c_void_p), ("h_out", c_void_p), ("eps", c_float),
@@ -91,7 +94,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here means the .so is stale -> fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.hqq_b200_abi_version() != 1:
+    if lib.hqq_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("hqq_b200: ABI version mismatch between libhqq_b200.so and the Python layer; rebuild")
     if path is None:
         _lib = lib

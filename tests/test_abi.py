@@ -58,12 +58,16 @@ def test_forward_routing_table(lib):
     r = lib.hqq_b200_linear_fwd_route
     assert r(1, 4096, 4096, 64, 4, 1, HQQ_F16) == 1      # decode: weight-streaming kernel
     assert r(32, 14336, 4096, 64, 4, 1, HQQ_BF16) == 1
-    assert r(1, 4096, 4096, 64, 4, 0, HQQ_F16) == 0      # axis 0: dequantize + GEMM
-    assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0
-    assert r(1, 4096, 4096, 64, 3, 1, HQQ_F16) == 0      # 3-bit: not fused (yet)
-    assert r(1, 4096, 4000, 64, 4, 1, HQQ_F16) == 0      # K must be a multiple of 256
+    assert r(1, 4096, 4096, 64, 4, 0, HQQ_F16) == 3      # axis 0: dequantize kernel + dense tcgen05 GEMM
+    assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0      # float32 compute: no tensor-core route
+    assert r(1, 4096, 4096, 64, 3, 1, HQQ_F16) == 3      # 3-bit (ten fields per int32, slabs cut rows): route 3
+    assert r(1, 4096, 4000, 64, 4, 1, HQQ_F16) == 3      # the fused kernels need K % 256 == 0; the dense GEMM's TMA zero-fills ragged K
     assert r(1, 4096, 4096, 128, 2, 1, HQQ_BF16) == 1
-    assert r(1, 4096, 4096, 32, 4, 1, HQQ_F16) == 0      # group sizes other than 64/128: dequantize + GEMM
+    assert r(1, 4096, 4096, 32, 4, 1, HQQ_F16) == 3      # group sizes other than 64/128
+    assert r(4096, 4096, 4096, 64, 4, 1, HQQ_F16) == 2   # fused tcgen05 GEMM
+    wsb = lib.hqq_b200_linear_fwd_workspace_bytes
+    assert wsb(1, 4096, 4096, 64, 4, 1, HQQ_F16) == 0 and wsb(4096, 4096, 4096, 64, 4, 1, HQQ_F16) == 0
+    assert wsb(64, 4096, 4096, 64, 3, 1, HQQ_F16) == 4096 * 4096 * 2 and wsb(64, 4096, 4096, 64, 4, 0, HQQ_BF16) == 4096 * 4096 * 2
     assert r(64, 4096, 4096, 64, 4, 1, HQQ_F16) != 1     # beyond the small-M kernel
 
 

@@ -173,8 +173,9 @@ def test_forward_is_deterministic_and_batch_invariant():
                                  dict(nbits=4, group_size=16, axis=1), dict(nbits=2, group_size=64, axis=1)])
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
 def test_every_config_has_a_forward(cfg, dt):
-    """Configurations outside the fused kernels (axis=0, 3-bit, fp32, odd group sizes, M > 32) run the CUDA dequantize
-    kernel + a library GEMM; results agree with the explicit dequantise-then-matmul definition (quantize.py:880-898)."""
+    """Configurations outside the fused kernels (axis=0, 3-bit, other group sizes) run route 3: our dequantize kernel + the dense
+    tcgen05 GEMM (float32 compute: dequantize kernel + library GEMM); results agree with the explicit dequantise-then-matmul
+    definition (quantize.py:880-898)."""
     torch.manual_seed(9)
     lin = torch.nn.Linear(256, 128, bias=True)
     layer = HQQLinear(lin, BaseQuantizeConfig(**cfg), compute_dtype=dt, device=DEV)
@@ -210,3 +211,52 @@ def test_backward_matches_dequant_matmul():
     y.backward(g)
     ref = g.float() @ layer.dequantize().float()
     assert (x.grad.float() - ref).norm() / ref.norm() <= 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 512), (40, 384, 1000), (300, 130, 72), (1024, 4096, 4096), (257, 11008, 4096)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_dense_tcgen05_gemm_vs_fp32_matmul(M, N, K, dt):
+    """hqq_b200_dense_gemm (the persistent tcgen05 kernel with both operands on TMA): ragged rows / tokens / K (K % 8 == 0 only),
+    bias, against an fp32 matmul of the same 16-bit operands."""
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV).to(dt)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    b = torch.randn(N, device=DEV).to(dt)
+    y = ops.dense_gemm(x, W, b)
+    assert y is not None and y.shape == (M, N)
+    ref = x.float() @ W.float().t()
+    assert ((y.float() - b.float()) - ref).norm() / ref.norm() <= (1e-3 if dt == torch.float16 else 6e-3)
+    assert torch.equal(ops.dense_gemm(x, W, b), y)
+
+
+@pytest.mark.parametrize("cfg", [dict(nbits=3, group_size=64, axis=1), dict(nbits=4, group_size=64, axis=0), dict(nbits=2, group_size=32, axis=1)])
+def test_route3_full_size(cfg):
+    """3-bit / axis 0 / other group sizes at a BASELINE sweep size: route 3 (dequantize kernel -> dense tcgen05 GEMM) against an fp32
+    GEMM over the (bit-exactly tested) dequantised matrix; the A operand IS that matrix, so only the accumulation order differs."""
+    torch.manual_seed(11)
+    N, K = 4096, 4096
+    layer = HQQLinear.from_weights((torch.randn(N, K, device=DEV) * 0.02).half(), None, BaseQuantizeConfig(**cfg), compute_dtype=torch.float16, device=DEV)
+    nb = Quantizer._packing_bits[layer.meta["packing"]]
+    for M in (1, 48, 600):
+        assert ops.linear_route(M, N, K, layer.meta["group_size"], nb, cfg["axis"], torch.float16) == 3
+        x = torch.randn(M, K, device=DEV).half()
+        y = layer(x).float()
+        ref = x.float() @ layer.dequantize().float().t()
+        assert (y - ref).norm() / ref.norm() <= 5e-4
+
+
+def test_persistent_gemm_schedule_is_result_invariant(monkeypatch):
+    """HQQ_B200_GEMM_CTAS caps the persistent grid: 7 CTAs walk 32 x 5 tiles one after another (both TMEM accumulators, epilogue under
+    the next main loop, the half-tile round) and must reproduce the full-grid result bit for bit."""
+    from hqq_b200 import _lib
+    torch.manual_seed(12)
+    layer = HQQLinear.from_weights((torch.randn(4096, 1024, device=DEV) * 0.02).half(), torch.randn(4096, device=DEV).half(),
+                                   BaseQuantizeConfig(nbits=4, group_size=64, axis=1), compute_dtype=torch.float16, device=DEV)
+    x = torch.randn(1100, 1024, device=DEV).half()
+    ref = layer(x)
+    for cap in ("7", "1", "40"):
+        monkeypatch.setenv("HQQ_B200_GEMM_CTAS", cap)
+        _lib.load().hqq_b200_reload_env()
+        assert torch.equal(layer(x), ref), cap
+    monkeypatch.delenv("HQQ_B200_GEMM_CTAS")
+    _lib.load().hqq_b200_reload_env()
