@@ -1,6 +1,6 @@
 """GPU: hqq_b200.models.tp.shard_hqq_linear -- tensor-parallel shards cut out of an already quantised HQQLinear with this package's
 unpack / pack kernels.  Written after round 1's GPU budget was spent (the index arithmetic is covered on the CPU through the oracle,
-tests/test_tp_shards_cpu.py): non-strict xfail until seen green."""
+tests/test_tp_shards_cpu.py)."""
 import pytest
 import torch
 
@@ -30,7 +30,10 @@ def test_shards_dequantise_to_slices_and_recombine(nbits):
         k0, k1 = (v * 64 for v in shard_bounds(K // 64, tp, rank))
         assert torch.equal(r.dequantize(), full[:, k0:k1]) and (r.bias is not None) == (rank == 0)
         rows.append(r(x[:, k0:k1].contiguous()).float())
-    assert torch.equal(torch.cat(cols, dim=1), y_full)                      # same kernel, same rows
+    # same rows, same kernel -- but a row's level sits in another bit field of the shard's bytes (the slab step changes), and the one-token
+    # kernel plants the fields into fp16 lanes at different scales (1024 + q vs 1024 + 16 q): equal up to fp32 accumulation order
+    y_col = torch.cat(cols, dim=1)
+    assert (y_col.float() - y_full.float()).norm() / y_full.float().norm() <= 1e-3
     y_row = (rows[0] + rows[1]).half()
     assert (y_row.float() - y_full.float()).norm() / y_full.float().norm() <= 2e-3
     sd = shard_hqq_linear(layer, tp, 1, "column").state_dict()             # a shard serialises like any HQQLinear
