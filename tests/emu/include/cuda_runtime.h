@@ -203,13 +203,18 @@ inline void mbar_arrive(uint64_t* bar) {
 inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { mb(bar)->tx += (int32_t)bytes; mbar_arrive(bar); }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) { mb(bar)->tx -= (int32_t)bytes; ++g_progress; mbar_check(bar); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (mbar_phase(bar) == (parity & 1u)) yield(); }  // spinning is not progress
-struct TMap { const char* base; uint64_t dims[2]; uint64_t stride_bytes; uint32_t box[2]; uint32_t esize; };
+struct TMap { const char* base; uint64_t dims[2]; uint64_t stride_bytes; uint32_t box[2]; uint32_t esize; uint32_t swz; };
 static_assert(sizeof(TMap) <= sizeof(CUtensorMap), "fake tensor map must fit the opaque CUtensorMap");
-inline CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32_t rank, void* gaddr, const cuuint64_t* dims, const cuuint64_t* strides,
+inline CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* gaddr, const cuuint64_t* dims, const cuuint64_t* strides,
                              const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
                              CUtensorMapFloatOOBfill) {
-  if (rank != 2 || sw != CU_TENSOR_MAP_SWIZZLE_128B || box[0] * 2 != 128) return CUDA_ERROR_INVALID_VALUE;  // what the model covers
-  TMap t{reinterpret_cast<const char*>(gaddr), {dims[0], dims[1]}, strides[0], {box[0], box[1]}, 2};
+  // what the model covers: 16-bit tiles of 64 elements with SWIZZLE_128B (the MMA operands), and plain byte tiles (the packed weights)
+  const bool bytes = dt == CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  if (rank != 2) return CUDA_ERROR_INVALID_VALUE;
+  if (!bytes && (sw != CU_TENSOR_MAP_SWIZZLE_128B || box[0] * 2 != 128)) return CUDA_ERROR_INVALID_VALUE;
+  if (bytes && (sw != CU_TENSOR_MAP_SWIZZLE_NONE || box[0] % 16 != 0)) return CUDA_ERROR_INVALID_VALUE;
+  if (strides[0] % 16 != 0 || (reinterpret_cast<uintptr_t>(gaddr) % 16) != 0) return CUDA_ERROR_INVALID_VALUE;  // the hardware's constraints
+  TMap t{reinterpret_cast<const char*>(gaddr), {dims[0], dims[1]}, strides[0], {box[0], box[1]}, bytes ? 1u : 2u, bytes ? 0u : 1u};
   memset(out, 0, sizeof(*out));
   memcpy(out, &t, sizeof(t));
   return CUDA_SUCCESS;
@@ -218,15 +223,30 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, i
   TMap t;
   memcpy(&t, map, sizeof(t));
   char* dst = reinterpret_cast<char*>(smem_dst);
-  if (smem_offset(dst) % 1024) { fprintf(stderr, "emu: TMA destination not 1024-byte aligned\n"); abort(); }
+  if (smem_offset(dst) % (t.swz ? 1024 : 128)) { fprintf(stderr, "emu: TMA destination misaligned\n"); abort(); }
   defer_unordered([=]() {
-    for (uint32_t j = 0; j < t.box[1]; ++j) {
-      const long long row = (long long)c1 + j;
-      for (uint32_t ch = 0; ch < 8; ++ch) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
-        char* d = dst + j * 128 + ((ch ^ (j & 7)) << 4);
-        const long long k = (long long)c0 + ch * 8;
-        if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k + 8 <= (long long)t.dims[0]) memcpy(d, t.base + row * t.stride_bytes + k * 2, 16);
-        else memset(d, 0, 16);  // out-of-range elements are zero-filled and still count as transferred bytes
+    if (t.swz) {
+      for (uint32_t j = 0; j < t.box[1]; ++j) {
+        const long long row = (long long)c1 + j;
+        for (uint32_t ch = 0; ch < 8; ++ch) {  // 128-byte rows, SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+          char* d = dst + j * 128 + ((ch ^ (j & 7)) << 4);
+          const long long k = (long long)c0 + ch * 8;
+          if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k + 8 <= (long long)t.dims[0]) memcpy(d, t.base + row * t.stride_bytes + k * 2, 16);
+          else if (row >= 0 && row < (long long)t.dims[1] && k >= 0 && k < (long long)t.dims[0]) {  // ragged inside a chunk: element-wise
+            for (int e = 0; e < 8; ++e) {
+              if (k + e < (long long)t.dims[0]) memcpy(d + 2 * e, t.base + row * t.stride_bytes + (k + e) * 2, 2);
+              else memset(d + 2 * e, 0, 2);
+            }
+          } else memset(d, 0, 16);  // out-of-range elements are zero-filled and still count as transferred bytes
+        }
+      }
+    } else {
+      for (uint32_t j = 0; j < t.box[1]; ++j) {
+        const long long row = (long long)c1 + j;
+        for (uint32_t b = 0; b < t.box[0]; ++b) {
+          const long long col = (long long)c0 + b;
+          dst[j * t.box[0] + b] = (row >= 0 && row < (long long)t.dims[1] && col >= 0 && col < (long long)t.dims[0]) ? t.base[row * t.stride_bytes + col] : 0;
+        }
       }
     }
     mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esize);
