@@ -2,13 +2,14 @@
 //
 //   y[M,N] = x[M,K] @ dequantize(W_q)^T (+bias)          reference: hqq/core/quantize.py:184-199, 880-898
 //
-// ONE persistent kernel, one CTA per SM, 15 warps with fixed roles; a CTA walks a static list of output tiles
+// ONE persistent kernel, one CTA per SM, 16 warps with fixed roles; a CTA walks a static list of output tiles
 // [128 weight rows] x [UN tokens] (UN = 256, or 128 for the ragged part of the schedule, see `Sched`):
 //   warp 0       TMA producer: the activation tile [UN tokens x 64 k] of every k-block (cp.async.bulk.tensor.2d, 128B swizzle,
 //                out-of-range tokens zero-filled by the hardware) into a 3-stage shared-memory ring = B operand (N = UN)
-//   warp 14      loader: the PACKED weight tile of every k-block by TMA (the reference's slab layout, bitpack.py: 128/F packed
-//                rows x 64 bytes, F slabs per byte = 128 output rows) into an 8-stage ring, and the tile's scale / zero for four
-//                k-blocks at a time into a second ring -- both run k-blocks ahead of their consumers
+//   warp 14      the PACKED weight tile of every k-block by TMA (the reference's slab layout, bitpack.py: 128/F packed rows x 64
+//                bytes, F slabs per byte = 128 output rows) into a 12-stage ring
+//   warp 15      the tile's scale / zero for four k-blocks at a time by cp.async into a 4-slot ring -- both producers run
+//                k-blocks ahead of their consumers and never wait for data themselves
 //   warps 2..9   dequant: read packed bytes + scale/zero from shared memory, expand them in registers with the reference's two
 //                roundings W_r = fl(fl(q - z) * s) (bit-identical to Quantizer.dequantize) and store K-major SWIZZLE_128B
 //                fp16/bf16 rows into a 4-stage ring = A operand (M = 128).  The dequantised matrix never exists in HBM.
@@ -37,7 +38,7 @@ constexpr int kBlockK = 64;          // k elements per stage = one 128-byte swiz
 constexpr int kTileRows = 128;       // weight rows per CTA = UMMA M
 constexpr int kDequantThreads = 256;
 constexpr int kEpilogueThreads = 128;
-constexpr int kThreads = 64 + kDequantThreads + kEpilogueThreads + 32;  // warp 0: TMA + TMEM alloc, 1: MMA issue, 2..9: dequant, 10..13: epilogue, 14: loader
+constexpr int kThreads = 64 + kDequantThreads + kEpilogueThreads + 64;  // warp 0: TMA + TMEM alloc, 1: MMA issue, 2..9: dequant, 10..13: epilogue, 14: packed-weight TMA, 15: scale/zero loader
 constexpr int kStagesB = 3;          // activation ring
 constexpr int kUN = 256;             // tokens per full tile = UMMA N; half tiles use 128
 constexpr int kTmemCols = 512;       // two accumulators of kUN fp32 columns
@@ -97,6 +98,9 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) { ::emu::tmem_alloc(dst_in_smem, NCOLS); }
 template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t) {}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) { ::emu::tmem_ld32(taddr, v); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* g) { ::emu::cp_async(smem_dst, g, 8); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* g) { ::emu::cp_async(smem_dst, g, 4); }
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) { ::emu::cp_async_mbar_arrive(bar); }
 #define HQQ_STS_V4(addr, a, b, c, d) ::emu::sts(addr, a, b, c, d)
 #define HQQ_STS_V2(addr, a, b) ::emu::sts(addr, a, b)
 #define HQQ_PREFETCH_TENSORMAP(p) ((void)(p))
@@ -171,6 +175,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all of this thread's earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 #define HQQ_STS_V4(addr, a, b, c, d) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
 #define HQQ_STS_V2(addr, a, b) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory")
 #define HQQ_PREFETCH_TENSORMAP(p) asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory")
@@ -266,7 +280,7 @@ struct Smem {
   static constexpr int A_STAGE = kTileRows * 128;      // 128 rows x 128 B
   static constexpr int B_STAGE = kUN * 128;
   static constexpr int W_STAGE = DENSE ? 0 : PR * 64;  // PR packed rows x 64 bytes
-  static constexpr int WS = DENSE ? 0 : (NBITS == 8 ? 4 : 8);
+  static constexpr int WS = DENSE ? 0 : (NBITS == 8 ? 6 : 12);  // 48 KB of packed bytes in flight (24 KB at 2-bit, 12 KB at 1-bit)
   static constexpr int M_SLOT = DENSE ? 0 : 2 * kTileRows * GPQ * 2;  // scale + zero, 16-bit
   static constexpr int MS = 4;
   static constexpr int OFF_B = kStages * A_STAGE;
@@ -306,13 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   uint64_t* empty_a = bars + 4;              // [4]  MMA (tcgen05.commit) -> dequant warps
   uint64_t* full_b = bars + 8;               // [3]  TMA -> MMA (1 arrival + tx bytes)
   uint64_t* empty_b = bars + 11;             // [3]  MMA (tcgen05.commit) -> TMA producer
-  uint64_t* w_full = bars + 14;              // [8]  TMA -> dequant warps (1 arrival + tx bytes)
-  uint64_t* w_empty = bars + 22;             // [8]  dequant warps (one arrival per warp) -> loader warp
-  uint64_t* m_full = bars + 30;              // [4]  loader warp -> dequant warps
-  uint64_t* m_empty = bars + 34;             // [4]  dequant warps -> loader warp
-  uint64_t* acc_full = bars + 38;            // [2]  MMA (tcgen05.commit) -> epilogue
-  uint64_t* acc_empty = bars + 40;           // [2]  epilogue (one arrival per warp) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  uint64_t* w_full = bars + 14;              // [12] TMA -> dequant warps (1 arrival + tx bytes)
+  uint64_t* w_empty = bars + 26;             // [12] dequant warps (one arrival per warp) -> warp 14
+  uint64_t* m_full = bars + 38;              // [4]  warp 15 (one cp.async-completion arrival per lane) -> dequant warps
+  uint64_t* m_empty = bars + 42;             // [4]  dequant warps -> warp 15
+  uint64_t* acc_full = bars + 46;            // [2]  MMA (tcgen05.commit) -> epilogue
+  uint64_t* acc_empty = bars + 48;           // [2]  epilogue (one arrival per warp) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (a.K + kBlockK - 1) / kBlockK;  // quantised routes: K % 256 == 0; dense: the TMA zero-fills a ragged last block
@@ -320,9 +334,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < 4; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty_a[s], 1); mbar_init(&m_full[s], 1); mbar_init(&m_empty[s], kDequantThreads / 32); }
+      for (int s = 0; s < 4; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty_a[s], 1); mbar_init(&m_full[s], 32); mbar_init(&m_empty[s], kDequantThreads / 32); }
       for (int s = 0; s < kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-      for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kDequantThreads / 32); }
+      for (int s = 0; s < 12; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kDequantThreads / 32); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpilogueThreads / 32); }
       fence_barrier_init();
       HQQ_PREFETCH_TENSORMAP(&xmap256);
@@ -512,15 +526,33 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&acc_empty[buf]);  // every lane's tcgen05.ld has completed (wait::ld) before the syncwarp
       ++q;
     }
+  } else if (warp == 14) {
+    if constexpr (!DENSE) {
+    // ================= packed weight tiles by TMA: [PR packed rows x 64 bytes] per k-block, rows past `step` read as zero =================
+    if (lane == 0) {
+      uint32_t wb = 0;
+      for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
+        const Item im = decode_item(a, j);
+        if (!im.valid) continue;
+        const int prow0 = im.tile_n * PR;
+        for (int kb = 0; kb < num_kb; ++kb, ++wb) {
+          const uint32_t ws = wb % WS;
+          mbar_wait(&w_empty[ws], ((wb / WS) & 1) ^ 1);
+          mbar_expect_tx(&w_full[ws], S::W_STAGE);
+          tma_load_2d(sW + ws * S::W_STAGE, &amap, &w_full[ws], kb * kBlockK, prow0);
+        }
+      }
+    }
+    }  // !DENSE
   } else {
     if constexpr (!DENSE) {
-    // ================= loader warp: packed weight tiles by TMA (W ring), scale / zero by plain loads (M ring) =================
-    // One in-order producer for both rings: the dequant warps consume them in the same order (scale/zero of a quad, then its four
-    // k-blocks), so it never waits for a slot whose release needs something it has not produced yet.
+    // ================= scale / zero of the tile's 128 rows, four k-blocks per slot, by cp.async straight into shared memory =================
+    // The copies of a slot signal its mbarrier when they land (one pre-counted arrival per lane), so this warp never waits for
+    // data: it runs up to four quads ahead of the dequant warps and the L2 / HBM latency of these small scattered reads stays hidden.
     const T* scale = reinterpret_cast<const T*>(a.scale);
     const T* zero = reinterpret_cast<const T*>(a.zero);
     const int num_quads = num_kb >> 2;
-    uint32_t gq = 0, wb = 0;
+    uint32_t gq = 0;
     for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
       const Item im = decode_item(a, j);
       if (!im.valid) continue;
@@ -532,29 +564,21 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
         mrow[i] = (prow0 + r) < a.step ? (long long)(f * a.step + prow0 + r) * a.Gk : 0;  // rows past the ragged edge: row 0, never stored
       }
       for (int q = 0; q < num_quads; ++q, ++gq) {
-        if (lane == 0) {
-#pragma unroll 1
-          for (int d = 0; d < 4; ++d, ++wb) {
-            const uint32_t ws = wb % WS;
-            mbar_wait(&w_empty[ws], ((wb / WS) & 1) ^ 1);
-            mbar_expect_tx(&w_full[ws], S::W_STAGE);
-            tma_load_2d(sW + ws * S::W_STAGE, &amap, &w_full[ws], (q * 4 + d) * kBlockK, prow0);  // [PR packed rows x 64 bytes], rows past `step` read as zero
-          }
-        }
-        Vec<T, GPQ> sv[kTileRows / 32], zv[kTileRows / 32];
-#pragma unroll
-        for (int i = 0; i < kTileRows / 32; ++i) {
-          sv[i] = *reinterpret_cast<const Vec<T, GPQ>*>(scale + mrow[i] + q * GPQ);
-          zv[i] = *reinterpret_cast<const Vec<T, GPQ>*>(zero + mrow[i] + q * GPQ);
-        }
         const uint32_t slot = gq % MS;
         mbar_wait(&m_empty[slot], ((gq / MS) & 1) ^ 1);
         Vec<T, GPQ>* ms = reinterpret_cast<Vec<T, GPQ>*>(sM + slot * S::M_SLOT);
         Vec<T, GPQ>* mz = ms + kTileRows;
 #pragma unroll
-        for (int i = 0; i < kTileRows / 32; ++i) { ms[lane + 32 * i] = sv[i]; mz[lane + 32 * i] = zv[i]; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&m_full[slot]);
+        for (int i = 0; i < kTileRows / 32; ++i) {
+          if constexpr (sizeof(Vec<T, GPQ>) == 8) {
+            cp_async8(&ms[lane + 32 * i], scale + mrow[i] + q * GPQ);
+            cp_async8(&mz[lane + 32 * i], zero + mrow[i] + q * GPQ);
+          } else {
+            cp_async4(&ms[lane + 32 * i], scale + mrow[i] + q * GPQ);
+            cp_async4(&mz[lane + 32 * i], zero + mrow[i] + q * GPQ);
+          }
+        }
+        cp_async_mbar_arrive(&m_full[slot]);
       }
     }
     }  // !DENSE
