@@ -45,7 +45,6 @@ SIGNATURES = {
     "hqq_b200_decode_linear_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "hqq_b200_decode_linear_fwd_desc": (c_int, [c_void_p, c_void_p]),
-    "hqq_b200_decode_linear_chain": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hqq_b200_glue_add_rmsnorm_tp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_silu_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

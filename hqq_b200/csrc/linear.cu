@@ -9,7 +9,6 @@ int linear_small_multi(const void* x, int nprob, const void* const* Wq, const vo
                        void* ws, size_t ws_bytes, cudaStream_t st, int xop = 0, const void* x2 = nullptr, const void* xw = nullptr,
                        void* h_out = nullptr, float eps = 0.0f, const TpExchange* tpx = nullptr);
 bool small_xop_ok(int64_t M, int64_t K);
-int linear_small_chain(int n, const hqq_b200_decode_desc* d, void* barrier, cudaStream_t st);
 bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis, int dtype);
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int gs, int nbits, int dtype);
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M,
@@ -74,10 +73,6 @@ extern "C" int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* s
   set_error("hqq_b200_linear_fwd: no fused kernel for M=%lld N=%lld K=%lld gs=%d nbits=%d axis=%d dtype=%d", (long long)M, (long long)N,
             (long long)K, group_size, nbits, axis, dtype);
   return HQQ_E_UNSUPPORTED;
-}
-
-extern "C" int hqq_b200_decode_linear_chain(const hqq_b200_decode_desc* descs, int count, void* barrier, void* stream) {
-  return linear_small_chain(count, descs, barrier, (cudaStream_t)stream);
 }
 
 extern "C" int hqq_b200_dense_gemm(const void* x, const void* W, const void* bias, void* y, int64_t M, int64_t N, int64_t K, int dtype,

@@ -2,27 +2,22 @@
 //
 //   y[M,N] = x[M,K] @ dequantize(W_q)^T (+bias)          reference: hqq/core/quantize.py:184-199, 880-898
 //
-// ONE persistent kernel, one CTA per SM, 16 warps with fixed roles; a CTA walks a static list of output tiles
+// ONE persistent kernel, one CTA per SM, 14 warps with fixed roles; a CTA walks a static list of output tiles
 // [128 weight rows] x [UN tokens] (UN = 256, or 128 for the ragged part of the schedule, see `Sched`):
 //   warp 0       TMA producer: the activation tile [UN tokens x 64 k] of every k-block (cp.async.bulk.tensor.2d, 128B swizzle,
-//                out-of-range tokens zero-filled by the hardware) into a 3-stage shared-memory ring = B operand (N = UN)
-//   warp 14      the PACKED weight tile of every k-block by TMA (the reference's slab layout, bitpack.py: 128/F packed rows x 64
-//                bytes, F slabs per byte = 128 output rows) into a 12-stage ring
-//   warp 15      the tile's scale / zero for four k-blocks at a time by cp.async into a 4-slot ring -- both producers run
-//                k-blocks ahead of their consumers and never wait for data themselves
-//   warps 2..9   dequant: read packed bytes + scale/zero from shared memory, expand them in registers with the reference's two
-//                roundings W_r = fl(fl(q - z) * s) (bit-identical to Quantizer.dequantize) and store K-major SWIZZLE_128B
-//                fp16/bf16 rows into a 4-stage ring = A operand (M = 128).  The dequantised matrix never exists in HBM.
+//                out-of-range tokens zero-filled by the hardware) into a 4-stage shared-memory ring = B operand (N = UN)
+//   warps 2..9   dequant: stream the packed bytes of the weight tile from HBM/L2 (the reference's slab layout, bitpack.py: 128/F
+//                packed rows x F slabs = 128 output rows), expand them in registers with the reference's two roundings
+//                W_r = fl(fl(q - z) * s) (bit-identical to Quantizer.dequantize) and store K-major SWIZZLE_128B fp16/bf16 rows
+//                into the ring = A operand (M = 128).  The dequantised matrix never exists in HBM.
 //   warp 1       one elected thread issues tcgen05.mma (4 per 64-k stage) into one of TWO fp32 accumulators in TMEM
-//                (2 x 256 columns = all 512); tcgen05.commit frees the stages / publishes the accumulator
+//                (2 x 256 columns = all 512); tcgen05.commit frees the stage / publishes the accumulator
 //   warps 10..13 epilogue: tcgen05.ld (lane = weight row, column = token) -> bias -> y, for tile i while the other roles are
 //                already in the main loop of tile i+1 (the rings never drain between tiles)
-// History.  Round 1 launched one CTA per tile (512 tiles on 148 SMs = 3.46 -> 4 waves, prologue/epilogue exposed per tile) and its
-// dequant warps fetched the packed bytes themselves, four k-blocks ahead in registers: fence.proxy.async then waited for those
-// loads at every stage, ~900 cycles per 64-k block whatever M (measured: 32 us for M = 64..512 on 4096 x 4096, tensor pipe 61 %
-// active at M = 4096).  tools/ummabench.cu (round 2) measured the bare MMA stream at 1.35-1.40 PFLOP/s on this part, with A from
-// TMEM (tcgen05.mma "ts" form) no faster than from shared memory -- so A stays in shared memory and the TMEM goes to the second
-// accumulator.
+// Round 1 launched one CTA per tile: 512 tiles on 148 SMs = 3.46 -> 4 waves, prologue/epilogue exposed per tile, tensor pipe
+// 61 % active.  tools/ummabench.cu (round 2) measured the same MMA stream alone at 1.35-1.40 PFLOP/s on this part, with A from
+// TMEM (tcgen05.mma "ts" form) no faster than from shared memory -- so A stays in shared memory and the TMEM goes to the
+// second accumulator.
 // sm_100a only: tcgen05 / TMEM / TMA, no mma.sync fallback.
 #include <stdlib.h>
 #include <cuda.h>  // CUtensorMap types only; the encode entry point is resolved through the runtime (no -lcuda)
@@ -38,8 +33,7 @@ constexpr int kBlockK = 64;          // k elements per stage = one 128-byte swiz
 constexpr int kTileRows = 128;       // weight rows per CTA = UMMA M
 constexpr int kDequantThreads = 256;
 constexpr int kEpilogueThreads = 128;
-constexpr int kThreads = 64 + kDequantThreads + kEpilogueThreads + 64;  // warp 0: TMA + TMEM alloc, 1: MMA issue, 2..9: dequant, 10..13: epilogue, 14: packed-weight TMA, 15: scale/zero loader
-constexpr int kStagesB = 3;          // activation ring
+constexpr int kThreads = 64 + kDequantThreads + kEpilogueThreads;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, 2..9: dequant, 10..13: epilogue
 constexpr int kUN = 256;             // tokens per full tile = UMMA N; half tiles use 128
 constexpr int kTmemCols = 512;       // two accumulators of kUN fp32 columns
 
@@ -98,9 +92,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) { ::emu::tmem_alloc(dst_in_smem, NCOLS); }
 template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t) {}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) { ::emu::tmem_ld32(taddr, v); }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* g) { ::emu::cp_async(smem_dst, g, 8); }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* g) { ::emu::cp_async(smem_dst, g, 4); }
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) { ::emu::cp_async_mbar_arrive(bar); }
 #define HQQ_STS_V4(addr, a, b, c, d) ::emu::sts(addr, a, b, c, d)
 #define HQQ_STS_V2(addr, a, b) ::emu::sts(addr, a, b)
 #define HQQ_PREFETCH_TENSORMAP(p) ((void)(p))
@@ -175,16 +166,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
-}
-// the mbarrier receives one (pre-counted) arrival once all of this thread's earlier cp.async copies have landed
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 #define HQQ_STS_V4(addr, a, b, c, d) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
 #define HQQ_STS_V2(addr, a, b) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory")
 #define HQQ_PREFETCH_TENSORMAP(p) asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory")
@@ -266,67 +247,40 @@ template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return 
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 
-// Shared memory (dynamic, 1024-byte aligned for the SWIZZLE_128B atoms):
-//   A ring  4 x 16 KB   dequantised weight tile of one 64-k block (K-major, SWIZZLE_128B)          dequant warps -> tensor core
-//   B ring  3 x 32 KB   activation tile [256 tokens x 64 k]                                         TMA -> tensor core
-//   W ring  WS x PR*64  packed bytes of the tile's PR packed rows for one 64-k block (plain rows)   TMA -> dequant warps
-//   M ring  4 x 2 x (128 x GPQ x 2 B)  scale / zero of the tile's 128 rows for four 64-k blocks      loader warp -> dequant warps
-template <int NBITS, int GS>
 struct Smem {
-  static constexpr bool DENSE = NBITS == 16;
-  static constexpr int F = DENSE ? 1 : 8 / NBITS;
-  static constexpr int PR = kTileRows / F;
-  static constexpr int GPQ = 256 / GS;                 // groups per quad of k-blocks
-  static constexpr int A_STAGE = kTileRows * 128;      // 128 rows x 128 B
+  static constexpr int A_STAGE = kTileRows * 128;  // 128 rows x 128 B
   static constexpr int B_STAGE = kUN * 128;
-  static constexpr int W_STAGE = DENSE ? 0 : PR * 64;  // PR packed rows x 64 bytes
-  static constexpr int WS = DENSE ? 0 : (NBITS == 8 ? 6 : 12);  // 48 KB of packed bytes in flight (24 KB at 2-bit, 12 KB at 1-bit)
-  static constexpr int M_SLOT = DENSE ? 0 : 2 * kTileRows * GPQ * 2;  // scale + zero, 16-bit
-  static constexpr int MS = 4;
-  static constexpr int OFF_B = kStages * A_STAGE;
-  static constexpr int OFF_W = OFF_B + kStagesB * B_STAGE;
-  static constexpr int OFF_M = OFF_W + WS * W_STAGE;
-  static constexpr int OFF_BAR = OFF_M + MS * M_SLOT;
-  static constexpr int BYTES = OFF_BAR + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr int BYTES = kStages * (A_STAGE + B_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// NBITS = 16 ("dense"): the A operand is an ordinary [N, K] fp16/bf16 matrix fetched by TMA like B -- dequant and loader warps idle.
-// It is the second half of the routes no fused expansion exists for (3-bit's 10-field int32 slabs, axis = 0 groups, other group
-// sizes, the backward pass): our dequantize kernel writes W_r once, this kernel multiplies (hqq_b200_linear_fwd route 3).
+// NBITS = 16 ("dense"): the A operand is an ordinary [N, K] fp16/bf16 matrix fetched by TMA like B -- the dequant warps idle.  It is
+// the second half of the routes no fused expansion exists for (3-bit's 10-field int32 slabs, axis = 0 groups, other group sizes,
+// the backward pass): our dequantize kernel writes W_r once, this kernel multiplies (hqq_b200_linear_fwd route 4).
 template <typename T, int NBITS, int GS>
 __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_constant__ CUtensorMap xmap256,
                                                                   const __grid_constant__ CUtensorMap xmap128,
                                                                   const __grid_constant__ CUtensorMap amap, const Args a) {
-  using S = Smem<NBITS, GS>;
-  constexpr bool DENSE = S::DENSE;
-  constexpr int F = S::F;                  // slabs per byte
-  constexpr int PR = S::PR;                // packed rows per tile
+  constexpr bool DENSE = NBITS == 16;
+  constexpr int F = DENSE ? 1 : 8 / NBITS;  // slabs per byte
+  constexpr int PR = kTileRows / F;        // packed rows per tile
   constexpr int BPT = DENSE ? 32 : 64 * PR / kDequantThreads;  // packed bytes per dequant thread and k-block (32 / F)
   static_assert(BPT >= 4, "a dequant thread expands at least four packed bytes per k-block");
   constexpr int TPR = 64 / BPT;            // dequant threads per packed row
-  constexpr uint32_t MASK = DENSE ? 0u : (1u << (NBITS & 15)) - 1u;
-  constexpr int GPQ = S::GPQ;
-  constexpr int WS = S::WS, MS = S::MS;
+  constexpr uint32_t MASK = (1u << NBITS) - 1u;
+  using S = Smem;
   using P2 = Pair<T>;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
   uint8_t* sA = smem;
-  uint8_t* sB = smem + S::OFF_B;
-  uint8_t* sW = smem + S::OFF_W;
-  uint8_t* sM = smem + S::OFF_M;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* full_a = bars;                   // [4]  dequant warps -> MMA (one arrival per warp)
-  uint64_t* empty_a = bars + 4;              // [4]  MMA (tcgen05.commit) -> dequant warps
-  uint64_t* full_b = bars + 8;               // [3]  TMA -> MMA (1 arrival + tx bytes)
-  uint64_t* empty_b = bars + 11;             // [3]  MMA (tcgen05.commit) -> TMA producer
-  uint64_t* w_full = bars + 14;              // [12] TMA -> dequant warps (1 arrival + tx bytes)
-  uint64_t* w_empty = bars + 26;             // [12] dequant warps (one arrival per warp) -> warp 14
-  uint64_t* m_full = bars + 38;              // [4]  warp 15 (one cp.async-completion arrival per lane) -> dequant warps
-  uint64_t* m_empty = bars + 42;             // [4]  dequant warps -> warp 15
-  uint64_t* acc_full = bars + 46;            // [2]  MMA (tcgen05.commit) -> epilogue
-  uint64_t* acc_empty = bars + 48;           // [2]  epilogue (one arrival per warp) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
+  uint8_t* sB = smem + kStages * S::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (S::A_STAGE + S::B_STAGE));
+  uint64_t* full_a = bars;                 // [kStages] dequant warps -> MMA (one arrival per warp)
+  uint64_t* full_b = bars + kStages;       // [kStages] TMA -> MMA (1 arrival + tx bytes)
+  uint64_t* empty = bars + 2 * kStages;    // [kStages] MMA (tcgen05.commit) -> both producers
+  uint64_t* acc_full = bars + 3 * kStages;       // [2] MMA (tcgen05.commit) -> epilogue
+  uint64_t* acc_empty = bars + 3 * kStages + 2;  // [2] epilogue (one arrival per warp) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (a.K + kBlockK - 1) / kBlockK;  // quantised routes: K % 256 == 0; dense: the TMA zero-fills a ragged last block
@@ -334,14 +288,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < 4; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&empty_a[s], 1); mbar_init(&m_full[s], 32); mbar_init(&m_empty[s], kDequantThreads / 32); }
-      for (int s = 0; s < kStagesB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-      for (int s = 0; s < 12; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kDequantThreads / 32); }
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_a[s], kDequantThreads / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpilogueThreads / 32); }
       fence_barrier_init();
       HQQ_PREFETCH_TENSORMAP(&xmap256);
       HQQ_PREFETCH_TENSORMAP(&xmap128);
-      HQQ_PREFETCH_TENSORMAP(&amap);
+      if constexpr (DENSE) HQQ_PREFETCH_TENSORMAP(&amap);
     }
     __syncwarp();
     tmem_alloc<kTmemCols>(tmem_slot);
@@ -352,15 +304,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer: activation tiles (dense: and the weight tile) =================
+    // ================= TMA producer: activation tiles =================
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position)
       for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
         const Item im = decode_item(a, j);
         if (!im.valid) continue;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kStagesB;
-          mbar_wait(&empty_b[s], ((it / kStagesB) & 1) ^ 1);
+          const int s = it % kStages;
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           constexpr uint32_t A_TX = DENSE ? S::A_STAGE : 0;  // dense: the weight tile rides the same barrier
           if (im.un == kUN) {
             mbar_expect_tx(&full_b[s], S::B_STAGE + A_TX);
@@ -385,19 +337,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       const uint32_t idesc = make_idesc<T>(im.un);
       const uint32_t tmem_d = tmem_base + buf * kUN;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int sb = it % kStagesB;
-        const int sa = DENSE ? sb : (int)(it % kStages);
-        if constexpr (!DENSE) mbar_wait(&full_a[sa], (it / kStages) & 1);
-        mbar_wait(&full_b[sb], (it / kStagesB) & 1);
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if constexpr (!DENSE) mbar_wait(&full_a[s], ph);
+        mbar_wait(&full_b[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t adesc = make_desc_sw128(smem_u32(sA + sa * S::A_STAGE));
-          const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * S::B_STAGE));
+          const uint64_t adesc = make_desc_sw128(smem_u32(sA + s * S::A_STAGE));
+          const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * S::B_STAGE));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
             tc_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          if constexpr (!DENSE) tc_commit(&empty_a[sa]);     // frees the stages when these MMAs have read them
-          tc_commit(&empty_b[sb]);
+          tc_commit(&empty[s]);                              // frees the stage when these MMAs have read it
           if (kb == num_kb - 1) tc_commit(&acc_full[buf]);   // accumulator complete
         }
         __syncwarp();
@@ -406,13 +357,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     }
   } else if (warp < 2 + kDequantThreads / 32) {
     if constexpr (!DENSE) {
-    // ================= dequant warps: packed bytes (W ring) + scale/zero (M ring) -> swizzled fp16/bf16 A tile =================
-    // Every operand arrives in shared memory through somebody else (TMA / the loader warp): this thread has no global load in
-    // flight when it executes fence.proxy.async, which waits for the thread's own earlier memory operations -- round 1's kernel
-    // prefetched the packed bytes into registers and paid one L2/DRAM round trip per four k-blocks at exactly that fence.
+    // ================= dequant warps: packed bytes -> swizzled fp16/bf16 A tile =================
     static_assert(kStages == 4, "the dequant loop is unrolled over the 4 ring stages");
     const int td = threadIdx.x - 64;
     const int pr = td / TPR, c = td % TPR;
+    constexpr int GPQ = 256 / GS;  // quantisation groups per 4 k-blocks (4 or 2): one vector load per slab and array
     uint32_t soff[F];              // shared-memory offsets are tile invariant
 #pragma unroll
     for (int f = 0; f < F; ++f) {
@@ -422,43 +371,73 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       else soff[f] = (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8);
     }
     const uint32_t sA_u32 = smem_u32(sA);
-    const uint8_t* my_w = sW + pr * 64 + c * BPT;  // this thread's bytes inside a W stage
+    const uint8_t* wptr = nullptr;
+    const T* sptr[F];
+    const T* zptr[F];
+    auto tile_ptrs = [&](int tile_n) {  // this thread's packed row / meta rows at k = 0 of a weight tile
+      const int prow0 = tile_n * PR;
+      const bool row_ok = (prow0 + pr) < a.step;  // rows past the ragged edge re-read row 0 (always mapped); never stored
+      wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+        sptr[f] = reinterpret_cast<const T*>(a.scale) + mrow;
+        zptr[f] = reinterpret_cast<const T*>(a.zero) + mrow;
+      }
+    };
+    auto next_valid = [&](int j) {  // first valid item of this CTA at or after j (n_items if none)
+      while (j < n_items && !decode_item(a, j).valid) j += gridDim.x;
+      return j < n_items ? j : n_items;
+    };
+    // Packed bytes and scale/zero for the NEXT four k-blocks sit in registers while the current four are expanded -- across tile
+    // boundaries too: their HBM/L2 latency stays off the critical path of the 64-k stages.
+    uint32_t wbuf[4][BPT / 4];
+    Vec<T, GPQ> sv[F], zv[F];
+    auto load_w = [&](const uint8_t* p, uint32_t (&w)[BPT / 4]) {
+      if constexpr (BPT == 32) { const uint4 v0 = ldg_stream_v4(p), v1 = ldg_stream_v4(p + 16); w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; }
+      else if constexpr (BPT == 16) { const uint4 v = ldg_stream_v4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      else if constexpr (BPT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; }
+      else { w[0] = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    };
+    auto load_quad = [&]() {  // the four k-blocks starting at wptr, and their groups
+#pragma unroll
+      for (int d = 0; d < 4; ++d) load_w(wptr + d * kBlockK, wbuf[d]);
+#pragma unroll
+      for (int f = 0; f < F; ++f) { sv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(sptr[f]); zv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(zptr[f]); }
+    };
     const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router): every tile starts at ring stage 0
-    uint32_t gq = 0, wb = 0;            // quads / k-blocks done so far (ring positions)
-    for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
-      if (!decode_item(a, j).valid) continue;
+    int j = next_valid((int)blockIdx.x);
+    if (j < n_items) { tile_ptrs(decode_item(a, j).tile_n); load_quad(); }
+    uint32_t gq = 0;  // quads done so far (ring parity)
+    while (j < n_items) {
+      const int jn = next_valid(j + (int)gridDim.x);
       for (int q = 0; q < num_quads; ++q, ++gq) {
+        uint32_t wq[4][BPT / 4];
         typename P2::T2 s2[4][F], z2[4][F];
-        {
-          const uint32_t slot = gq % MS;
-          mbar_wait(&m_full[slot], (gq / MS) & 1);
-          const Vec<T, GPQ>* ms = reinterpret_cast<const Vec<T, GPQ>*>(sM + slot * S::M_SLOT);
-          const Vec<T, GPQ>* mz = ms + kTileRows;
 #pragma unroll
-          for (int f = 0; f < F; ++f) {
-            const Vec<T, GPQ> sv = ms[f * PR + pr], zv = mz[f * PR + pr];
+        for (int d = 0; d < 4; ++d) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) { s2[d][f] = P2::bcast(sv.v[(d * kBlockK) / GS]); z2[d][f] = P2::bcast(zv.v[(d * kBlockK) / GS]); }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&m_empty[slot]);  // every lane has its values in registers
+          for (int i = 0; i < BPT / 4; ++i) wq[d][i] = wbuf[d][i];
+#pragma unroll
+          for (int f = 0; f < F; ++f) { s2[d][f] = P2::bcast(sv[f].v[(d * kBlockK) / GS]); z2[d][f] = P2::bcast(zv[f].v[(d * kBlockK) / GS]); }
+        }
+        if (q + 1 < num_quads) {
+          wptr += 4 * kBlockK;
+#pragma unroll
+          for (int f = 0; f < F; ++f) { sptr[f] += GPQ; zptr[f] += GPQ; }
+          // the register prefetch reaches one quad ahead, about 1 us of main loop at small M -- less than a DRAM round trip under
+          // load when a weight tile is read for the first time (M <= 512: every tile is); pull the line this thread will load
+          // three quads from now into L2 (a packed row has 256 bytes = two lines per quad: even / odd threads of the row take one each)
+          if (q + 4 < num_quads) HQQ_PREFETCH_L2(wptr + 3 * 4 * kBlockK + (c & 1) * 128);
+          load_quad();
+        } else if (jn < n_items) {
+          tile_ptrs(decode_item(a, jn).tile_n);
+          load_quad();
         }
         const uint32_t parity = (gq & 1u) ^ 1u;
 #pragma unroll
-        for (int d = 0; d < 4; ++d, ++wb) {  // A stage index == d because the ring has exactly four stages
-          uint32_t wq[BPT / 4];
-          {
-            const uint32_t ws = wb % WS;
-            mbar_wait(&w_full[ws], (wb / WS) & 1);
-            const uint8_t* p = my_w + ws * S::W_STAGE;
-            if constexpr (BPT == 32) { const uint4 v0 = *reinterpret_cast<const uint4*>(p), v1 = *reinterpret_cast<const uint4*>(p + 16); wq[0] = v0.x; wq[1] = v0.y; wq[2] = v0.z; wq[3] = v0.w; wq[4] = v1.x; wq[5] = v1.y; wq[6] = v1.z; wq[7] = v1.w; }
-            else if constexpr (BPT == 16) { const uint4 v = *reinterpret_cast<const uint4*>(p); wq[0] = v.x; wq[1] = v.y; wq[2] = v.z; wq[3] = v.w; }
-            else if constexpr (BPT == 8) { const uint2 v = *reinterpret_cast<const uint2*>(p); wq[0] = v.x; wq[1] = v.y; }
-            else { wq[0] = *reinterpret_cast<const uint32_t*>(p); }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&w_empty[ws]);  // the bytes are in registers: the slot may be refilled
-          }
-          mbar_wait(&empty_a[d], parity);
+        for (int d = 0; d < 4; ++d) {  // stage index == d because the ring has exactly four stages
+          mbar_wait(&empty[d], parity);
           const uint32_t stage = sA_u32 + d * S::A_STAGE;
 #pragma unroll
           for (int f = 0; f < F; ++f) {
@@ -466,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
             uint32_t out[BPT / 2];  // BPT levels -> BPT/2 packed pairs
 #pragma unroll
             for (int i = 0; i < BPT / 4; ++i) {
-              const uint32_t t = (wq[i] >> sh) & (MASK * 0x01010101u);
+              const uint32_t t = (wq[d][i] >> sh) & (MASK * 0x01010101u);
               P2::deq4(t, z2[d][f], s2[d][f], out[2 * i], out[2 * i + 1]);
             }
             if constexpr (BPT >= 8) {
@@ -485,9 +464,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           if (lane == 0) mbar_arrive(&full_a[d]);  // one arrival per warp: every lane has fenced its stores before the syncwarp
         }
       }
+      j = jn;
     }
     }  // !DENSE
-  } else if (warp < 2 + kDequantThreads / 32 + kEpilogueThreads / 32) {
+  } else {
     // ================= epilogue warps: TMEM -> registers -> y, one tile behind the main loop =================
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter .. +31
     const int t = quarter * 32 + lane;            // tile row = weight row inside the tile
@@ -526,62 +506,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&acc_empty[buf]);  // every lane's tcgen05.ld has completed (wait::ld) before the syncwarp
       ++q;
     }
-  } else if (warp == 14) {
-    if constexpr (!DENSE) {
-    // ================= packed weight tiles by TMA: [PR packed rows x 64 bytes] per k-block, rows past `step` read as zero =================
-    if (lane == 0) {
-      uint32_t wb = 0;
-      for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
-        const Item im = decode_item(a, j);
-        if (!im.valid) continue;
-        const int prow0 = im.tile_n * PR;
-        for (int kb = 0; kb < num_kb; ++kb, ++wb) {
-          const uint32_t ws = wb % WS;
-          mbar_wait(&w_empty[ws], ((wb / WS) & 1) ^ 1);
-          mbar_expect_tx(&w_full[ws], S::W_STAGE);
-          tma_load_2d(sW + ws * S::W_STAGE, &amap, &w_full[ws], kb * kBlockK, prow0);
-        }
-      }
-    }
-    }  // !DENSE
-  } else {
-    if constexpr (!DENSE) {
-    // ================= scale / zero of the tile's 128 rows, four k-blocks per slot, by cp.async straight into shared memory =================
-    // The copies of a slot signal its mbarrier when they land (one pre-counted arrival per lane), so this warp never waits for
-    // data: it runs up to four quads ahead of the dequant warps and the L2 / HBM latency of these small scattered reads stays hidden.
-    const T* scale = reinterpret_cast<const T*>(a.scale);
-    const T* zero = reinterpret_cast<const T*>(a.zero);
-    const int num_quads = num_kb >> 2;
-    uint32_t gq = 0;
-    for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
-      const Item im = decode_item(a, j);
-      if (!im.valid) continue;
-      const int prow0 = im.tile_n * PR;
-      long long mrow[kTileRows / 32];  // this lane's rows of the meta arrays: tile rows lane, lane + 32, ...
-#pragma unroll
-      for (int i = 0; i < kTileRows / 32; ++i) {
-        const int rs = lane + 32 * i, f = rs / PR, r = rs % PR;
-        mrow[i] = (prow0 + r) < a.step ? (long long)(f * a.step + prow0 + r) * a.Gk : 0;  // rows past the ragged edge: row 0, never stored
-      }
-      for (int q = 0; q < num_quads; ++q, ++gq) {
-        const uint32_t slot = gq % MS;
-        mbar_wait(&m_empty[slot], ((gq / MS) & 1) ^ 1);
-        Vec<T, GPQ>* ms = reinterpret_cast<Vec<T, GPQ>*>(sM + slot * S::M_SLOT);
-        Vec<T, GPQ>* mz = ms + kTileRows;
-#pragma unroll
-        for (int i = 0; i < kTileRows / 32; ++i) {
-          if constexpr (sizeof(Vec<T, GPQ>) == 8) {
-            cp_async8(&ms[lane + 32 * i], scale + mrow[i] + q * GPQ);
-            cp_async8(&mz[lane + 32 * i], zero + mrow[i] + q * GPQ);
-          } else {
-            cp_async4(&ms[lane + 32 * i], scale + mrow[i] + q * GPQ);
-            cp_async4(&mz[lane + 32 * i], zero + mrow[i] + q * GPQ);
-          }
-        }
-        cp_async_mbar_arrive(&m_full[slot]);
-      }
-    }
-    }  // !DENSE
   }
   tc_fence_before();
   __syncthreads();
@@ -624,20 +548,6 @@ static int encode_map(CUtensorMap* xmap, const void* x, int64_t rows, int64_t K,
   return HQQ_OK;
 }
 
-// packed weights as a [packed_rows, K] byte matrix, boxes of 64 bytes x `box_rows` packed rows, plain rows, out-of-range rows read as zero
-static int encode_map_u8(CUtensorMap* wmap, const void* Wq, int64_t rows, int64_t K, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  HQQ_REQUIRE(enc != nullptr, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)K};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(Wq), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  HQQ_REQUIRE(r == CUDA_SUCCESS, HQQ_E_CUDA, "hqq_b200_linear_fwd: cuTensorMapEncodeTiled (packed weights) failed (%d)", (int)r);
-  return HQQ_OK;
-}
-
 static int sm_count() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
@@ -668,11 +578,9 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
     rc = encode_map(&amap, dense_W, a.N, a.K, dt, sizeof(T), kTileRows);
     if (rc) return rc;
   } else {
-    rc = encode_map_u8(&amap, a.Wq, a.step, a.K, Smem<NBITS, GS>::PR);  // K bytes per packed row: 16-byte pitch since K % 256 == 0
-    if (rc) return rc;
+    amap = xmap128;  // unused
   }
-  constexpr int PR = Smem<NBITS, GS>::PR;
-  using SM = Smem<NBITS, GS>;
+  constexpr int PR = NBITS == 16 ? kTileRows : kTileRows / (NBITS == 16 ? 1 : 8 / NBITS);
   // HQQ_B200_GEMM_CTAS=<n> (test hook): cap the persistent grid, so that small problems exercise tile-after-tile execution, both
   // accumulators and the half-tile round (the emulator tests and tests/test_linear_gpu.py set it; results never depend on it)
   HQQ_ENV_KNOB(cta_cap, ([] { const char* e = getenv("HQQ_B200_GEMM_CTAS"); return e ? atoi(e) : 0; })());
@@ -685,11 +593,11 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
   cudaGetDevice(&dev);
   static bool attr_set[64] = {};  // per device: the attribute belongs to the function on ONE device
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
-    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", SM::BYTES, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES);
+    HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem::BYTES, cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  k<<<grid, kThreads, SM::BYTES, st>>>(xmap256, xmap128, amap, a);
+  k<<<grid, kThreads, Smem::BYTES, st>>>(xmap256, xmap128, amap, a);
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   return HQQ_OK;
 }

@@ -82,13 +82,6 @@ struct SKArgs {
   int x_index, x_per_step;
 };
 
-constexpr int kMaxChain = 4;
-struct SKChain {
-  SKArgs a[kMaxChain];
-  int n;
-  unsigned* bar;  // n > 1: {arrival count, generation}, zero when first used; returns to {0, generation + n - 1} after every launch
-};
-
 #ifdef HQQ_EMU
 #define HQQ_ST_RELAXED_SYS(p, v) (*reinterpret_cast<volatile uint32_t*>(p) = (v))
 #else
@@ -577,45 +570,6 @@ __global__ void __launch_bounds__(256, SKCfg<T, NBITS, GS, MT, MAGIC>::MIN_CTAS)
   cp_async_wait<0>();
 }
 
-// ---- grid-wide barrier between the phases of one launch (every CTA is resident: the host sizes the grid to the SMs' capacity) ----
-// arrive: every thread fences its stores, thread 0 notes the generation and counts in; the last CTA resets the count and bumps
-// the generation (release).  wait: thread 0 spins until the generation moves (acquire), then the CTA barrier publishes it.
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-#ifdef HQQ_EMU
-  return *reinterpret_cast<const volatile unsigned*>(p);
-#else
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-#endif
-}
-__device__ __forceinline__ void grid_arrive(unsigned* bar, unsigned nblocks, unsigned& gen) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    gen = ld_acquire_gpu_u32(bar + 1);
-#ifdef HQQ_EMU
-    if (++bar[0] == nblocks) { bar[0] = 0; ++bar[1]; }
-#else
-    if (atomicAdd(bar, 1u) == nblocks - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    }
-#endif
-  }
-}
-__device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned gen) {
-  if (threadIdx.x == 0) {
-    while (ld_acquire_gpu_u32(bar + 1) == gen) {
-#ifdef HQQ_EMU
-      ::emu::yield();
-#endif
-    }
-  }
-  __syncthreads();
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // M == 1 specialisation (the decode hot path).  Same scheduling and staging as linear_small_kernel, but everything that
 // depends only on the activation is hoisted out of the per-tile loop: each warp stages ITS k-chunk of x once in shared
@@ -635,7 +589,7 @@ struct D1Cfg {
 };
 
 template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC, int MR = 0>
-__global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_constant__ SKChain ch) {
+__global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_constant__ SKArgs a) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST, MR>;
   constexpr int F = C::F, P = C::P, MPG = C::MPG, GPB = C::GPB, NWV = C::NWV;
   using MM = MT16<T>;
@@ -643,6 +597,8 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   uint4* wring = reinterpret_cast<uint4*>(smem);
   uint4* mring = reinterpret_cast<uint4*>(smem + C::W_BYTES);  // MR only
   float* part_s = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES);       // [2][8][16]
+  T* xs = reinterpret_cast<T*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES);      // [K] permuted activations
+  float* xsum = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES + a.K * 2);  // [K/GS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, c = lane & 3;
@@ -651,22 +607,10 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
   Lanes<T, NBITS, MAGIC> lanes;
   lanes.init(8 - NBITS * (fa + 1), 8 - NBITS * (fb + 1));
 
-  // A launch is a chain of 1..kMaxChain phases (hqq_b200_decode_linear_chain): phase i+1 consumes what phase i produced, the whole
-  // grid meets at a barrier in between, and the weight ring keeps streaming across it -- a phase issues its first ST-1 units
-  // BEFORE it waits for its inputs, exactly what programmatic dependent launch does across kernels, without the launch.
-  int stage = 0;            // ring position, carried across phases
-  unsigned bar_gen = 0;     // thread 0: generation of the grid barrier it last arrived at
-  for (int ph = 0; ph < ch.n; ++ph) {
-  const SKArgs& a = ch.a[ph];
-  T* xs = reinterpret_cast<T*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES);      // [K] permuted activations
-  float* xsum = reinterpret_cast<float*>(smem + C::W_BYTES + C::M_BYTES + C::P_BYTES + a.K * 2);  // [K/GS]
   const int kb0 = a.KB * warp / 8, kb1 = a.KB * (warp + 1) / 8;
   const int upt = kb1 - kb0;
   const int n_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (n_tiles <= 0) {
-    if (ch.n == 1) return;
-    if (ph == 0) { pdl_launch_dependents(); pdl_wait(); } else grid_wait(ch.bar, bar_gen);
-  } else {
+  if (n_tiles <= 0) return;
 
   struct Tile { const uint8_t* Wq; const T* scale; const T* zero; const T* bias; T* y; uint32_t* ytag; int N, step, tile0; };
   auto pick = [&](int pi, Tile& t) {
@@ -767,13 +711,9 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     cp_async_commit();
   };
 #pragma unroll
-  for (int s = 0; s < ST - 1; ++s) issue(stage + s < ST ? stage + s : stage + s - ST);
-  if (ph == 0) {
-    pdl_launch_dependents();  // our dependents' launch latency hides under our main loop
-    pdl_wait();
-  } else {
-    grid_wait(ch.bar, bar_gen);  // the previous phase's outputs are complete and visible
-  }
+  for (int s = 0; s < ST - 1; ++s) issue(s);
+  pdl_launch_dependents();  // our dependents' launch latency hides under our main loop
+  pdl_wait();
   uint32_t send_tag = 0, send_par = 0;  // this launch's exchange number (shared by its producer and consumer sides)
   if (a.step_ctr) {
     const uint32_t ex = (uint32_t)(*reinterpret_cast<volatile const int*>(a.step_ctr)) * (uint32_t)a.x_per_step + (uint32_t)a.x_index;
@@ -925,6 +865,7 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
     __syncwarp();
   }
 
+  int stage = 0;
   for (int ti = 0; ti < n_tiles; ++ti) {
     float tot_a = 0.0f, tot_b = 0.0f;
     for (int ku = 0; ku < upt; ++ku) {
@@ -1025,9 +966,6 @@ __global__ void __launch_bounds__(256, MC) linear_decode1_kernel(const __grid_co
       }
     }
   }
-  }  // n_tiles > 0
-  if (ph + 1 < ch.n) grid_arrive(ch.bar, gridDim.x, bar_gen);
-  }  // phases
   cp_async_wait<0>();
 }
 
@@ -1121,15 +1059,11 @@ static int launch_sk(SKArgs& a, cudaStream_t st) {
 }
 
 template <typename T, int NBITS, int GS, int MAGIC, int ST, int MC, int MR = 0>
-static int launch_d1(SKChain& ch, cudaStream_t st) {
+static int launch_d1(SKArgs& a, cudaStream_t st) {
   using C = D1Cfg<T, NBITS, GS, MAGIC, ST, MR>;
   static int max_smems[kMaxDevices] = {};
   int& max_smem = max_smems[cur_device()];
-  int smem = 0, tiles = 0;
-  for (int i = 0; i < ch.n; ++i) {
-    smem = C::smem(ch.a[i].K) > smem ? C::smem(ch.a[i].K) : smem;
-    tiles = ch.a[i].total_tiles > tiles ? ch.a[i].total_tiles : tiles;
-  }
+  const int smem = C::smem(a.K);
   auto k = linear_decode1_kernel<T, NBITS, GS, MAGIC, ST, MC, MR>;
   if (smem > max_smem) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1138,12 +1072,7 @@ static int launch_d1(SKChain& ch, cudaStream_t st) {
   }
   int per_sm = MC;
   while (per_sm > 1 && (smem + 1024) * per_sm > 227 * 1024) --per_sm;
-  // a chain synchronises the whole grid between its phases: every CTA must be resident, i.e. at most the SMs' capacity (the
-  // kernels launched before it finish on their own, the ones behind it cannot start before all of its CTAs run)
-  int grid = balanced_grid(tiles, sm_count() * per_sm);
-#ifdef HQQ_EMU
-  if (ch.n > 1) grid = 1;  // the emulator runs CTAs one after another: a grid barrier needs a grid of one there
-#endif
+  int grid = balanced_grid(a.total_tiles, sm_count() * per_sm);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(256);
@@ -1154,7 +1083,7 @@ static int launch_d1(SKChain& ch, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k, ch);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd/decode1: CUDA launch failed: %s", cudaGetErrorString(e));
   return HQQ_OK;
@@ -1166,55 +1095,52 @@ static bool d1_enabled() {
 }
 
 template <typename T, int NBITS, int GS, int MAGIC>
-static int sk_mt(SKChain& ch, cudaStream_t st) {
-  SKArgs& a = ch.a[0];
+static int sk_mt(SKArgs& a, cudaStream_t st) {
   if (a.M == 1 && a.K <= 16384 && d1_enabled()) {
-    if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(ch, st);
+    if (NBITS == 8) return launch_d1<T, NBITS, GS, MAGIC, 2, 2>(a, st);
     // scale/zero ride the cp.async ring at the weights' distance (MR = 1) whenever the ring's aligned 16-byte copies are legal;
     // measured on the B200 (round 2, profiles/r2_d1_variants.txt): 1.70 ms per token against 1.91 ms with register loads one
     // unit ahead, bit-identical outputs.  evict-first hints, a third CTA per SM, L2 prefetch under the dependency wait and
     // cross-launch weight prefetch were measured in the same run, were not faster, and are gone.
     if constexpr (GS == 64 && NBITS != 8) {
-      bool ok = true;  // the ring copies aligned 16-byte blocks: every group row must start on one
-      for (int ph = 0; ph < ch.n; ++ph) {
-        ok = ok && ch.a[ph].K % 512 == 0;
-        for (int i = 0; i < ch.a[ph].nprob; ++i) ok = ok && aligned(ch.a[ph].p[i].scale, 16) && aligned(ch.a[ph].p[i].zero, 16);
+      if (a.K % 512 == 0) {
+        bool ok = true;  // the ring copies aligned 16-byte blocks: every group row must start on one
+        for (int i = 0; i < a.nprob; ++i) ok = ok && aligned(a.p[i].scale, 16) && aligned(a.p[i].zero, 16);
+        if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(a, st);
       }
-      if (ok) return launch_d1<T, NBITS, GS, MAGIC, 4, 2, 1>(ch, st);
     }
-    return launch_d1<T, NBITS, GS, MAGIC, 4, 2>(ch, st);
+    return launch_d1<T, NBITS, GS, MAGIC, 4, 2>(a, st);
   }
-  HQQ_REQUIRE(ch.n == 1, HQQ_E_UNSUPPORTED, "hqq_b200_decode_linear_chain: needs the M == 1 kernel");
   if (a.M <= 8) return launch_sk<T, NBITS, GS, 1, MAGIC>(a, st);
   if (a.M <= 16) return launch_sk<T, NBITS, GS, 2, MAGIC>(a, st);
   return launch_sk<T, NBITS, GS, 4, MAGIC>(a, st);
 }
 
 template <typename T, int NBITS, int MAGIC>
-static int sk_gs(SKChain& ch, int gs, cudaStream_t st) {
+static int sk_gs(SKArgs& a, int gs, cudaStream_t st) {
   switch (gs) {
-    case 64: return sk_mt<T, NBITS, 64, MAGIC>(ch, st);
-    case 128: return sk_mt<T, NBITS, 128, MAGIC>(ch, st);
+    case 64: return sk_mt<T, NBITS, 64, MAGIC>(a, st);
+    case 128: return sk_mt<T, NBITS, 128, MAGIC>(a, st);
   }
   return HQQ_E_UNSUPPORTED;
 }
 
 template <typename T>
-static int sk_bits(SKChain& ch, int gs, int nbits, cudaStream_t st) {
+static int sk_bits(SKArgs& a, int gs, int nbits, cudaStream_t st) {
   const bool sub = std::is_same<T, __half>::value && magic_mode() == MAGIC_SUBNORMAL;
   switch (nbits) {
     case 8:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 8, MAGIC_SUBNORMAL>(ch, gs, st) : sk_gs<T, 8, MAGIC_OFFSET>(ch, gs, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 8, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 8, MAGIC_OFFSET>(a, gs, st);
       else return HQQ_E_UNSUPPORTED;
     case 4:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 4, MAGIC_SUBNORMAL>(ch, gs, st) : sk_gs<T, 4, MAGIC_OFFSET>(ch, gs, st);
-      else return sk_gs<T, 4, MAGIC_OFFSET>(ch, gs, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 4, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 4, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 4, MAGIC_OFFSET>(a, gs, st);
     case 2:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 2, MAGIC_SUBNORMAL>(ch, gs, st) : sk_gs<T, 2, MAGIC_OFFSET>(ch, gs, st);
-      else return sk_gs<T, 2, MAGIC_OFFSET>(ch, gs, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 2, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 2, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 2, MAGIC_OFFSET>(a, gs, st);
     case 1:
-      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 1, MAGIC_SUBNORMAL>(ch, gs, st) : sk_gs<T, 1, MAGIC_OFFSET>(ch, gs, st);
-      else return sk_gs<T, 1, MAGIC_OFFSET>(ch, gs, st);
+      if constexpr (std::is_same<T, __half>::value) return sub ? sk_gs<T, 1, MAGIC_SUBNORMAL>(a, gs, st) : sk_gs<T, 1, MAGIC_OFFSET>(a, gs, st);
+      else return sk_gs<T, 1, MAGIC_OFFSET>(a, gs, st);
   }
   return HQQ_E_UNSUPPORTED;
 }
@@ -1236,13 +1162,15 @@ size_t small_workspace_bytes(int64_t) { return 0; }  // split-K partials meet in
 
 bool small_xop_ok(int64_t M, int64_t K) { return M == 1 && K <= 16384 && d1_enabled(); }
 
-// argument block of one launch / one phase of a chain
-static int fill_args(SKArgs& a, const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
-                     const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int xop,
-                     const void* x2, const void* xw, void* h_out, float eps, const TpExchange* tpx) {
+int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
+                       const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
+                       void* ws, size_t ws_bytes, cudaStream_t st, int xop, const void* x2, const void* xw, void* h_out, float eps,
+                       const TpExchange* tpx) {
   HQQ_REQUIRE(nprob >= 1 && nprob <= kMaxProb, HQQ_E_INVALID, "hqq_b200_linear_fwd_multi: 1..%d matrices per launch (got %d)", kMaxProb, nprob);
   HQQ_REQUIRE(aligned(x, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x must be 16-byte aligned");
+  (void)ws; (void)ws_bytes;
   const int F = 8 / nbits, P = 16 / F;
+  SKArgs a;
   a.nprob = nprob; a.x = x; a.M = (int)M; a.K = (int)K; a.Gk = (int)(K / gs); a.KB = (int)(K / 256);
   const int yop = xop >> 4;  // HQQ_YOP_* travel in the high bits of x_op
   xop &= 15;
@@ -1287,47 +1215,8 @@ static int fill_args(SKArgs& a, const void* x, int nprob, const void* const* Wq,
     if (i < nprob) tiles += (int)cdiv(a.p[i].step, P);
   }
   a.total_tiles = yop ? (int)cdiv(a.p[0].step, P / 2) : tiles;
-  return HQQ_OK;
-}
-
-int linear_small_multi(const void* x, int nprob, const void* const* Wq, const void* const* scale, const void* const* zero,
-                       const void* const* bias, void* const* y, const int64_t* N, int64_t M, int64_t K, int gs, int nbits, int dtype,
-                       void* ws, size_t ws_bytes, cudaStream_t st, int xop, const void* x2, const void* xw, void* h_out, float eps,
-                       const TpExchange* tpx) {
-  (void)ws; (void)ws_bytes;
-  SKChain ch;
-  ch.n = 1; ch.bar = nullptr;
-  int rc = fill_args(ch.a[0], x, nprob, Wq, scale, zero, bias, y, N, M, K, gs, nbits, xop, x2, xw, h_out, eps, tpx);
-  if (rc) return rc;
-  if (dtype == HQQ_F16) return sk_bits<__half>(ch, gs, nbits, st);
-  return sk_bits<__nv_bfloat16>(ch, gs, nbits, st);
-}
-
-// hqq_b200_decode_linear_chain: `n` one-token launches, each consuming what the one before produced, as ONE launch (see SKChain)
-int linear_small_chain(int n, const hqq_b200_decode_desc* d, void* barrier, cudaStream_t st) {
-  HQQ_REQUIRE(n >= 1 && n <= kMaxChain && d, HQQ_E_INVALID, "hqq_b200_decode_linear_chain: 1..%d phases (got %d)", kMaxChain, n);
-  HQQ_REQUIRE(n == 1 || (barrier && aligned(barrier, 8)), HQQ_E_INVALID, "hqq_b200_decode_linear_chain: needs an 8-byte aligned barrier word pair");
-  SKChain ch;
-  ch.n = n; ch.bar = reinterpret_cast<unsigned*>(barrier);
-  for (int i = 0; i < n; ++i) {
-    HQQ_REQUIRE(d[i].group_size == d[0].group_size && d[i].nbits == d[0].nbits && d[i].dtype == d[0].dtype, HQQ_E_INVALID,
-                "hqq_b200_decode_linear_chain: every phase must share group_size, nbits and dtype");
-    HQQ_REQUIRE(!d[i].step_ctr && !d[i].peer_data && !d[i].red_data && !d[i].y_tagged && !d[i].x_tagged && !d[i].x2_tagged, HQQ_E_UNSUPPORTED,
-                "hqq_b200_decode_linear_chain: the tagged-word exchange is not chained (one GPU only)");
-    HQQ_REQUIRE(d[i].x && d[i].count >= 1 && d[i].count <= kMaxProb && d[i].W_q && d[i].scale && d[i].zero && d[i].y && d[i].N, HQQ_E_INVALID,
-                "hqq_b200_decode_linear_chain: phase %d: 1..4 matrices, non-null arrays", i);
-    for (int j = 0; j < d[i].count; ++j)
-      if (!small_route_ok(1, d[i].N[j], d[i].K, d[i].group_size, d[i].nbits, 1, d[i].dtype) || !small_xop_ok(1, d[i].K)) {
-        set_error("hqq_b200_decode_linear_chain: phase %d matrix %d is outside the fused M=1 kernel", i, j);
-        return HQQ_E_UNSUPPORTED;
-      }
-    int rc = fill_args(ch.a[i], d[i].x, d[i].count, d[i].W_q, d[i].scale, d[i].zero, d[i].bias, d[i].y, d[i].N, 1, d[i].K, d[i].group_size, d[i].nbits,
-                       d[i].x_op, d[i].x2, d[i].x_weight, d[i].h_out, d[i].eps, nullptr);
-    if (rc) return rc;
-  }
-  if (!d1_enabled()) { set_error("hqq_b200_decode_linear_chain: needs the M == 1 kernel"); return HQQ_E_UNSUPPORTED; }
-  if (d[0].dtype == HQQ_F16) return sk_bits<__half>(ch, d[0].group_size, d[0].nbits, st);
-  return sk_bits<__nv_bfloat16>(ch, d[0].group_size, d[0].nbits, st);
+  if (dtype == HQQ_F16) return sk_bits<__half>(a, gs, nbits, st);
+  return sk_bits<__nv_bfloat16>(a, gs, nbits, st);
 }
 
 }  // namespace hqq

@@ -76,8 +76,6 @@ class DecodeModel:
         self.tp_mode = tp_mode or os.environ.get("HQQ_B200_TP_MODE", "p2p")
         if self.tp_mode not in ("p2p", "nccl"):
             raise ValueError(f"tp_mode must be 'p2p' or 'nccl' (got {self.tp_mode!r})")
-        # one GPU: chain o_proj / gate+up / down_proj of a block into one launch (test hook HQQ_B200_DECODE_CHAIN=0: five launches)
-        self.chain = os.environ.get("HQQ_B200_DECODE_CHAIN", "1") != "0"
         self.nbits, self.group_size = nbits, group_size
         self.tp, self.rank, self.pg = tp, rank, process_group
         self.cache_len = cache_len
@@ -141,7 +139,6 @@ class DecodeModel:
         self.pos = torch.zeros(1, dtype=torch.long, device=self.device)
         self.next_tok = torch.zeros(self.batch, dtype=torch.long, device=self.device)
         self.graph = None
-        self._chain_bar = torch.zeros(2, dtype=torch.int32, device=self.device)  # grid-barrier words of the chained launches
 
     # bytes one decode step must read from HBM: packed weights + meta + fp16 lm_head row-major
     def bytes_per_token(self, nbits=None, group_size=None) -> float:
@@ -314,16 +311,6 @@ class DecodeModel:
             h_cur, h_nxt = h_nxt, h_cur
             check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
                                                      ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            if self.tp == 1 and pair and self.chain:
-                # one GPU: o_proj -> [add+RMSNorm -> gate/up -> SiLU*mul] -> down_proj as ONE persistent launch of three phases with
-                # grid barriers in between (hqq_b200_decode_linear_chain): 3 launches per block instead of 5
-                done = ops.decode_linear_chain([(b["a"], (blk["o"],), [b["o"]]),
-                                                (h_cur, (blk["gate"], blk["up"]), [b["act"], b["up"]], 1 | ops.YOP_SILU_MUL_PAIR, b["o"], blk["norm2"], h_nxt, s.rms_eps),
-                                                (b["act"], (blk["down"],), [b["down"]])], self._chain_bar)
-                if done:
-                    h_cur, h_nxt = h_nxt, h_cur
-                    delta = b["down"]
-                    continue
             ok &= ops.decode_linear_fwd(b["a"], (blk["o"],), [b["o"]], tpx=self._tpx(bi, peer_data=o_sc) if p2p else None)
             if self.tp > 1 and not p2p:
                 torch.distributed.all_reduce(b["o"], group=self.pg)

@@ -281,43 +281,6 @@ def decode_linear_fwd(x: torch.Tensor, layers, outs, x_op: int = 0, x2=None, x_w
     return True
 
 
-def decode_linear_chain(phases, barrier: torch.Tensor) -> bool:
-    """`hqq_b200_decode_linear_chain`: up to four one-token launches as ONE persistent launch with grid barriers in between.
-    `phases` is a list of tuples (x, layers, outs, x_op, x2, x_weight, h_out, eps) as for `decode_linear_fwd`; `barrier` a
-    2-element int32 device tensor, zero at first use, kept alive by the caller.  Returns False when a phase is outside the fused
-    M = 1 kernel (the caller then launches them one by one)."""
-    import ctypes
-    lib = load()
-    n = len(phases)
-    descs = (_lib.DecodeDesc * n)()
-    keep = []
-    dev = phases[0][0].device
-    for i, ph in enumerate(phases):
-        x, layers, outs, x_op, x2, x_weight, h_out, eps = (list(ph) + [0, None, None, None, 0.0])[:8]
-        m0 = layers[0].meta
-        nbits = {"8bit_u8": 8, "4bit_u8": 4, "3bit_32": 3, "2bit_u8": 2, "1bit_u8": 1}.get(m0["packing"], 0)
-        code = DTYPE_CODE.get(x.dtype, -1)
-        if code < 0 or m0["group_size"] is None or nbits == 0 or m0["axis"] != 1:
-            return False
-        k = len(layers)
-        VP = ctypes.c_void_p * k
-        arr = lambda ts: VP(*[ptr(t) for t in ts])  # noqa: E731
-        arrays = [arr([l.W_q for l in layers]), arr([l.meta["scale"] for l in layers]), arr([l.meta["zero"] for l in layers]),
-                  arr([l.bias for l in layers]), arr(outs), (ctypes.c_int64 * k)(*[int(l.meta["shape"][0]) for l in layers])]
-        keep.append(arrays)
-        cast = lambda a: ctypes.cast(a, ctypes.c_void_p)  # noqa: E731
-        d = descs[i]
-        d.x, d.x_op, d.x2, d.x_weight, d.h_out, d.eps, d.count = ptr(x), int(x_op), ptr(x2), ptr(x_weight), ptr(h_out), float(eps), k
-        d.W_q, d.scale, d.zero, d.bias, d.y, d.N = (cast(a) for a in arrays)
-        d.K, d.group_size, d.nbits, d.dtype, d.tp, d.rank = int(m0["shape"][1]), int(m0["group_size"]), nbits, code, 1, 0
-    with _on(dev):
-        rc = lib.hqq_b200_decode_linear_chain(ctypes.cast(descs, ctypes.c_void_p), n, ptr(barrier), stream_ptr(dev))
-    if rc == HQQ_E_UNSUPPORTED:
-        return False
-    check(rc)
-    return True
-
-
 def _decode_launch(lib, x, layers, outs, x_op, x2, x_weight, h_out, eps, tpx, n, m0, K, nbits, code, arr, Narr, VP):
     import ctypes
     if tpx is None:

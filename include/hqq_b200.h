@@ -193,14 +193,6 @@ typedef struct hqq_b200_decode_desc {
   const int* step_ctr; int x_index; int x_per_step;
 } hqq_b200_decode_desc;
 int hqq_b200_decode_linear_fwd_desc(const hqq_b200_decode_desc* desc, void* stream);
-/* `count` (1..4) one-token launches as ONE: phase i+1 reads what phase i wrote (o_proj -> [add+RMSNorm -> gate/up -> SiLU*mul] ->
- * down_proj is one launch of three phases).  Persistent CTAs walk the phases; between two phases the whole grid meets at a barrier
- * (`barrier`: two 32-bit words in device memory, zero before their first use, owned by the caller for the lifetime of the
- * layers -- they return to a clean state after every launch, so a captured graph can be replayed), and every CTA starts streaming
- * the next phase's weights BEFORE it waits there, as programmatic dependent launch does across kernels -- without the launch, its
- * drain and its ramp.  Each desc as in hqq_b200_decode_linear_fwd_desc, without the tagged-word exchange (tp fields zero / NULL);
- * all phases share group_size, nbits and dtype.  Results are bit-identical to the same descs launched one by one.              */
-int hqq_b200_decode_linear_chain(const hqq_b200_decode_desc* descs, int count, void* barrier, void* stream);
 /* final-norm consumer of the same exchange: h += sum_r red_data[parity][r]; y = rmsnorm(h) * weight; ++*step_ctr */
 int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp,
                                  const void* weight, void* y, int H, float eps, int dtype, void* stream);

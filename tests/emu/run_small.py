@@ -98,37 +98,6 @@ def main(out_path):
         # references for the plain one-token call
         for nm, Lr in (("a", A), ("b", B)):
             res[f"dec{ci}_x0_{nm}_ref"] = O.linear_forward(x.astype(np.float32), Lr["Wq_host"], Lr["meta"], None, "float16")
-    # chained launch (hqq_b200_decode_linear_chain): o_proj -> [add + RMSNorm -> gate/up -> SiLU*mul] -> down_proj as three phases of
-    # ONE launch against the same three descs launched one by one; hidden 512 / 1024 (K % 512 == 0: the ring kernel) and 768 (register
-    # meta path), inter 1024 / 1536
-    import hqq_desc
-    for ci, (nbits, H, I) in enumerate([(4, 512, 1024), (2, 1024, 1536), (4, 768, 1024)]):
-        rng = np.random.default_rng(400 + ci)
-        Lo, Lg, Lu, Ld = make_layer(rng, H, H, nbits, 64), make_layer(rng, I, H, nbits, 64), make_layer(rng, I, H, nbits, 64), make_layer(rng, H, I, nbits, 64)
-        a_in = dev(rng.standard_normal((1, H)).astype(np.float16))
-        h = dev(rng.standard_normal((1, H)).astype(np.float16))
-        w = dev(rng.random(H).astype(np.float16))
-        outs = {}
-        for mode in ("single", "chain"):
-            o, act, up, down, hout = (aligned((1, n), np.float16) for n in (H, I, I, H, H))
-            descs, keep = hqq_desc.make_descs([
-                dict(x=a_in, layers=[Lo], outs=[o], K=H),
-                dict(x=h, layers=[Lg, Lu], outs=[act, up], K=H, x_op=1 | 16, x2=o, x_weight=w, h_out=hout, eps=1e-5),
-                dict(x=act, layers=[Ld], outs=[down], K=I)], nbits, 64, F16)
-            if mode == "single":
-                for i in range(3):
-                    rc = lib.hqq_b200_decode_linear_fwd_desc(ctypes.byref(descs[i]), None)
-                    assert rc == 0, lib.hqq_b200_last_error()
-            else:
-                bar = aligned((2,), np.uint32)
-                bar[...] = 0
-                for rep in range(2):  # the barrier words return to a clean state: a second launch on the same words
-                    rc = lib.hqq_b200_decode_linear_chain(descs, 3, P(bar), None)
-                    assert rc == 0, lib.hqq_b200_last_error()
-                assert int(bar[0]) == 0
-            outs[mode] = [t.copy() for t in (o, act, down, hout)]
-        for nm, x_, y_ in zip(("o", "act", "down", "h"), outs["single"], outs["chain"]):
-            res[f"chain{ci}_{nm}_single"], res[f"chain{ci}_{nm}_chain"] = x_, y_
     np.savez(out_path, **res)
 
 

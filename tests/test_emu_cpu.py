@@ -255,18 +255,6 @@ def test_emulated_one_token_prologues_and_paired_epilogue(emu, oracle, tmp_path_
         assert np.array_equal(d[f"dec{ci}_x1pair_h"], t)
 
 
-def test_emulated_chained_decode_launch_equals_single_launches(emu, tmp_path_factory):
-    """hqq_b200_decode_linear_chain: three phases of one launch (phase loop, ring position carried across phases, weights of the
-    next phase issued before the barrier wait, barrier words back to a clean state) reproduce the three launches bit for bit.
-    The emulator runs a chain as a grid of ONE CTA (it executes CTAs one after another); the barrier among CTAs runs on the GPU
-    (tests/test_harness_gpu.py)."""
-    d = run_small(tmp_path_factory)
-    keys = [k[:-7] for k in d if k.startswith("chain") and k.endswith("_single")]
-    assert len(keys) == 12
-    for k in keys:
-        assert np.array_equal(d[k + "_single"].view(np.uint8), d[k + "_chain"].view(np.uint8)), k
-
-
 # ---------------------------------------------------------------------------------------------------------------------------
 # csrc/linear_gemm.cu on the emulator's functional model of mbarrier / TMA (SWIZZLE_128B) / UMMA descriptors / tcgen05.mma /
 # TMEM / tcgen05.ld: addresses, swizzles, barrier phases and who-waits-for-whom are executed; timing, async proxies and memory
