@@ -119,3 +119,24 @@ def test_module_plumbing(lin):
     x = torch.randn(2, 16, device=DEV).half()
     assert torch.equal(m(x), m2(x))
     assert "in_features=16, out_features=128" in repr(m2[0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_layers_on_a_device_that_is_not_current():
+    """BaseHQQModel.quantize_model(device=[...]) spreads layers over GPUs of one process: a layer on cuda:1 must launch on cuda:1 while
+    cuda:0 is current (the C ABI launches on the calling thread's current device: ops.py guards it, the function-attribute and grid
+    caches of the kernels are per device) -- every route: one-token kernel, small-M kernel, tcgen05 GEMM, dequantize + dense GEMM."""
+    torch.manual_seed(21)
+    assert torch.cuda.current_device() == 0
+    for cfg in (dict(nbits=4, group_size=64, axis=1), dict(nbits=3, group_size=64, axis=1)):
+        lin = torch.nn.Linear(2048, 1024, bias=True)
+        W, b = lin.weight.data.clone(), lin.bias.data.clone()
+        layers = [HQQLinear.from_weights(W.clone().half(), torch.nn.Parameter(b.clone().half()), BaseQuantizeConfig(**cfg), compute_dtype=torch.float16,
+                                         device=d) for d in ("cuda:0", "cuda:1")]
+        for M in (1, 8, 300):
+            x = torch.randn(M, 2048).half()
+            y0 = layers[0](x.to("cuda:0"))
+            y1 = layers[1](x.to("cuda:1"))
+            assert y1.device.index == 1
+            assert torch.equal(y0.cpu(), y1.cpu()), (cfg, M)
+    assert torch.cuda.current_device() == 0
