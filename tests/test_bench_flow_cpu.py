@@ -133,6 +133,9 @@ def test_host_topology_and_the_reference_step(monkeypatch):
         def step(self):
             self.n += 1
 
+        def lm_share_s(self, reps=5):
+            return 1e-6
+
     r = Tiny()
     v, info = r.run(steps=25, warmup=2, budget_s=10.0)
     assert r.n == 27 and info["steps_timed"] == 25 and v > 0 and len(info["tokens_per_s_min_median_max"]) == 3
