@@ -30,6 +30,10 @@ SIGNATURES = {
     "hqq_b200_unpack": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "hqq_b200_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "hqq_b200_quantize_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
+    "hqq_b200_quantize_shard_begin": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+                                              c_void_p, c_size_t, c_void_p]),
+    "hqq_b200_quantize_shard_finish": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+                                               c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hqq_b200_quantize": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hqq_b200_quantize_ex": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,

@@ -404,18 +404,30 @@ __global__ void __launch_bounds__(kSolverThreads) solver_generic_kernel(SolverAr
 }
 
 // ---- K2: fixed-order reduction of the error partials + the reference's early-stop rule -----------------
+// Sharded quantisation (optimize.py:239-247 compares a WHOLE-tensor mean): with `sums_out` the kernel stops after the
+// reduction and hands the `iters` float64 error sums of this shard to the caller, who adds the shards' sums (one all-reduce of
+// iters x 8 bytes) and comes back with `sums_in` (global sums) and the global element count in `total`.
 __global__ void __launch_bounds__(1024) stop_kernel(const double* __restrict__ partial, int nblocks, int iters, long long total,
-                                                    int32_t* __restrict__ info, float* __restrict__ err_out) {
+                                                    int32_t* __restrict__ info, float* __restrict__ err_out,
+                                                    const double* __restrict__ sums_in, double* __restrict__ sums_out) {
   __shared__ double e[kMaxIters];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int it = warp; it < iters; it += 32) {
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += partial[(long long)b * iters + it];
+  if (sums_in) {
+    if ((int)threadIdx.x < iters) e[threadIdx.x] = sums_in[threadIdx.x];
+  } else {
+    for (int it = warp; it < iters; it += 32) {
+      double s = 0.0;
+      for (int b = lane; b < nblocks; b += 32) s += partial[(long long)b * iters + it];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) e[it] = s;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) e[it] = s;
+    }
   }
   __syncthreads();
+  if (sums_out) {
+    if ((int)threadIdx.x < iters) sums_out[threadIdx.x] = e[threadIdx.x];
+    return;
+  }
   if (threadIdx.x == 0) {
     // optimize.py:236-247: best = inf; for i: err = mean|W - W_r| (float32); if err < best: best = err else break
     float best = INFINITY;
@@ -592,10 +604,13 @@ static int launch_quant_pack(const void* W, const float* s_inv, const float* his
   return HQQ_OK;
 }
 
+// phase 0: everything; 1: solver + this shard's error sums -> err_sums (trajectories stay in the workspace); 2: early stop from the
+// caller's global err_sums / total_override, then round + pack on the same workspace
 template <typename TIn>
 static int quantize_typed(const void* W, long long N, long long K, int gs, int nbits, int maxv, int axis, int round_zero, int optimize,
                           float lp_norm, float beta, int iters, const float* s_init, const float* z_init, void* Wq, float* scale_out,
-                          float* zero_out, int32_t* info_out, float* err_out, char* ws, const Layout& L, cudaStream_t st) {
+                          float* zero_out, int32_t* info_out, float* err_out, char* ws, const Layout& L, cudaStream_t st, int phase = 0,
+                          double* err_sums = nullptr, long long total_override = 0) {
   SolverArgs a;
   a.W = W; a.total = L.total; a.G = L.G; a.gs = gs;
   a.s_init = s_init; a.z_init = z_init;
@@ -607,12 +622,18 @@ static int quantize_typed(const void* W, long long N, long long K, int gs, int n
   a.hist = reinterpret_cast<float*>(ws + L.off_hist);
   a.partial = reinterpret_cast<double*>(ws + L.off_partial);
   int32_t* info = reinterpret_cast<int32_t*>(ws + L.off_info);
-  int rc = launch_solver<TIn>(a, axis, L.nblocks, st);
-  if (rc) return rc;
+  int rc = HQQ_OK;
+  if (phase != 2) {
+    rc = launch_solver<TIn>(a, axis, L.nblocks, st);
+    if (rc) return rc;
+  }
   if (a.iters > 0) {
-    stop_kernel<<<1, 1024, 0, st>>>(a.partial, L.nblocks, a.iters, L.total, info, err_out);
+    if (phase == 1) stop_kernel<<<1, 1024, 0, st>>>(a.partial, L.nblocks, a.iters, L.total, info, nullptr, nullptr, err_sums);
+    else if (phase == 2) stop_kernel<<<1, 1024, 0, st>>>(a.partial, L.nblocks, a.iters, total_override, info, err_out, err_sums, nullptr);
+    else stop_kernel<<<1, 1024, 0, st>>>(a.partial, L.nblocks, a.iters, L.total, info, err_out, nullptr, nullptr);
     HQQ_LAUNCH_CHECK("hqq_b200_quantize/stop");
   }
+  if (phase == 1) return HQQ_OK;
   const int32_t* sel = a.iters > 0 ? info : nullptr;
   switch (nbits) {
     case 8: rc = launch_quant_pack<8, TIn>(W, a.s_inv, a.hist, sel, Wq, L, gs, axis, a.maxv, scale_out, zero_out, st); break;
@@ -682,6 +703,44 @@ extern "C" int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int
   }
   set_error("hqq_b200_quantize: unsupported source dtype %d (need f32/f16/bf16)", src_dtype);
   return HQQ_E_INVALID;
+}
+
+static int quantize_phase(int phase, const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis, int round_zero,
+                          float lp_norm, float beta, int iters, void* W_q_out, float* scale_out, float* zero_out, int32_t* info_out,
+                          float* err_out, double* err_sums, int64_t total, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_quant_args(N, K, group_size, nbits, axis, iters);
+  if (rc) return rc;
+  HQQ_REQUIRE(W && workspace && err_sums && iters >= 1, HQQ_E_INVALID, "hqq_b200_quantize_shard: null pointer or no iterations");
+  HQQ_REQUIRE(phase == 1 || (W_q_out && scale_out && zero_out && total >= N * K), HQQ_E_INVALID, "hqq_b200_quantize_shard_finish: null output or bad global element count");
+  HQQ_REQUIRE(beta > 0.0f, HQQ_E_INVALID, "hqq_b200_quantize: beta must be positive");
+  Layout L = make_layout(N, K, group_size, nbits, axis, iters);
+  HQQ_REQUIRE(workspace_bytes >= L.bytes, HQQ_E_WORKSPACE, "hqq_b200_quantize: workspace %zu < required %zu bytes", workspace_bytes, L.bytes);
+  HQQ_REQUIRE(aligned(workspace, 256) && aligned(W, 16) && aligned(err_sums, 8), HQQ_E_INVALID, "hqq_b200_quantize_shard: misaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const int maxv = (1 << nbits) - 1;
+  switch (src_dtype) {
+    case HQQ_F32: return quantize_typed<float>(W, N, K, group_size, nbits, maxv, axis, round_zero, 1, lp_norm, beta, iters, nullptr, nullptr, W_q_out, scale_out, zero_out, info_out, err_out, ws, L, st, phase, err_sums, total);
+    case HQQ_F16: return quantize_typed<__half>(W, N, K, group_size, nbits, maxv, axis, round_zero, 1, lp_norm, beta, iters, nullptr, nullptr, W_q_out, scale_out, zero_out, info_out, err_out, ws, L, st, phase, err_sums, total);
+    case HQQ_BF16: return quantize_typed<__nv_bfloat16>(W, N, K, group_size, nbits, maxv, axis, round_zero, 1, lp_norm, beta, iters, nullptr, nullptr, W_q_out, scale_out, zero_out, info_out, err_out, ws, L, st, phase, err_sums, total);
+  }
+  set_error("hqq_b200_quantize: unsupported source dtype %d (need f32/f16/bf16)", src_dtype);
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_quantize_shard_begin(const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis,
+                                             int round_zero, float lp_norm, float beta, int iters, double* err_sums_out, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  return quantize_phase(1, W, src_dtype, N, K, group_size, nbits, axis, round_zero, lp_norm, beta, iters, nullptr, nullptr, nullptr, nullptr, nullptr,
+                        err_sums_out, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int hqq_b200_quantize_shard_finish(const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis,
+                                              int round_zero, float lp_norm, float beta, int iters, const double* err_sums,
+                                              int64_t total_elements, void* W_q_out, float* scale_out, float* zero_out, int32_t* info_out,
+                                              float* err_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return quantize_phase(2, W, src_dtype, N, K, group_size, nbits, axis, round_zero, lp_norm, beta, iters, W_q_out, scale_out, zero_out, info_out,
+                        err_out, const_cast<double*>(err_sums), total_elements, workspace, workspace_bytes, stream);
 }
 
 extern "C" int hqq_b200_quantize(const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis,

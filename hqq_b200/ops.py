@@ -130,6 +130,44 @@ def quantize(W: torch.Tensor, nbits: int, group_size: int, axis: int, round_zero
     return W_q, scale, zero, trace
 
 
+def quantize_sharded(W_shard: torch.Tensor, nbits: int, group_size: int, axis: int, round_zero: bool, process_group=None,
+                     lp_norm: float = 0.7, beta: float = 10.0, iters: int = 20, want_trace: bool = False):
+    """`quantize` for ONE shard of a layer whose rows / groups live on several ranks (tensor parallelism), with the unsharded result:
+    every rank solves its groups (`hqq_b200_quantize_shard_begin`), the per-iteration error sums and the element count are
+    all-reduced over `process_group` (iters x 8 + 8 bytes -- the reference's early stop looks at the WHOLE tensor,
+    optimize.py:239-247), then every rank stops at the global iteration, rounds and packs its shard
+    (`hqq_b200_quantize_shard_finish`).  Same return value as `quantize`."""
+    import torch.distributed as dist
+    _lib.require_cuda(W_shard, "the weight passed to quantize_sharded")
+    W = W_shard if W_shard.dtype in (torch.float32, torch.float16, torch.bfloat16) else W_shard.float()
+    W = W.contiguous()
+    N, K = W.shape
+    lib = load()
+    dev = W.device
+    pshape, _, G = packed_shape(N, K, group_size, nbits, axis)
+    ws_bytes = lib.hqq_b200_quantize_workspace_bytes(N, K, group_size, nbits, axis, iters)
+    if ws_bytes == 0:
+        check(lib.hqq_b200_quantize(None, 0, N, K, group_size, nbits, axis, 0, 0, lp_norm, beta, iters, None, None, None, None, None, None, 0, None))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sums = torch.zeros(iters + 1, dtype=torch.float64, device=dev)  # [iters] error sums + the element count
+    args = (ptr(W), DTYPE_CODE[W.dtype], N, K, int(group_size), int(nbits), int(axis), int(bool(round_zero)), float(lp_norm), float(beta), int(iters))
+    with torch.cuda.device(dev):
+        check(lib.hqq_b200_quantize_shard_begin(*args, ptr(sums), ptr(ws), ws_bytes, stream_ptr(dev)))
+    sums[iters] = float(N * K)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
+    total = int(sums[iters].item())
+    W_q = torch.empty(pshape, dtype=torch.int32 if nbits == 3 else torch.uint8, device=dev)
+    scale = torch.empty(G, dtype=torch.float32, device=dev)
+    zero = torch.empty(G, dtype=torch.float32, device=dev)
+    info = torch.zeros(4, dtype=torch.int32, device=dev) if want_trace else None
+    errs = torch.zeros(iters, dtype=torch.float32, device=dev) if want_trace else None
+    with torch.cuda.device(dev):
+        check(lib.hqq_b200_quantize_shard_finish(*args, ptr(sums), total, ptr(W_q), ptr(scale), ptr(zero), ptr(info), ptr(errs), ptr(ws), ws_bytes,
+                                                 stream_ptr(dev)))
+    return W_q, scale, zero, ({"info": info, "errors": errs} if want_trace else None)
+
+
 # ----------------------------------------------------------------------------- fused forward
 def linear_route(M: int, N: int, K: int, group_size: int, nbits: int, axis: int, dtype: torch.dtype) -> int:
     code = DTYPE_CODE.get(dtype, -1)

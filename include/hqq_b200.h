@@ -112,6 +112,21 @@ int hqq_b200_quantize_ex(const void* W, int src_dtype, int64_t N, int64_t K,
                          int32_t* info_out, float* err_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Quantising a layer whose rows / groups are spread over several GPUs (tensor-parallel shards) with the reference's result:
+ * the groups are independent except for the early stop, which compares the mean |W - W_r| of the WHOLE tensor per iteration
+ * (hqq/core/optimize.py:239-247).  _begin runs init + solver on this shard and writes its `iters` float64 error sums to
+ * err_sums_out (device memory; the zero-point trajectories stay in `workspace`); the caller adds the shards' sums (one all-reduce of
+ * iters x 8 bytes) and calls _finish with the global sums and the global element count: early stop, round, pack -- every shard
+ * then holds exactly the levels / scale / zero of the unsharded quantisation.  Same workspace (hqq_b200_quantize_workspace_bytes)
+ * for both calls, untouched in between.                                                                                        */
+int hqq_b200_quantize_shard_begin(const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis,
+                                  int round_zero, float lp_norm, float beta, int iters, double* err_sums_out,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+int hqq_b200_quantize_shard_finish(const void* W, int src_dtype, int64_t N, int64_t K, int group_size, int nbits, int axis,
+                                   int round_zero, float lp_norm, float beta, int iters, const double* err_sums,
+                                   int64_t total_elements, void* W_q_out, float* scale_out, float* zero_out,
+                                   int32_t* info_out, float* err_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* HQQLinear.forward under HQQBackend.PYTORCH (forward_pytorch / forward_pytorch_backprop),
  * i.e. y = x @ dequantize(W_q).T + bias, as ONE fused unpack->dequant->MMA kernel.
  *   hqq/core/quantize.py:880-898 ; semantic template hqq/kernels/hqq_aten_torch.cpp:79-107

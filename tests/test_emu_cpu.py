@@ -440,3 +440,51 @@ def test_emulated_solver_equals_the_c_oracle_on_random_layers(emu, oracle):
             assert np.array_equal(a, b), case
             exact += 1
     assert exact >= 8
+
+
+@pytest.mark.parametrize("nbits,gs,shape,axis", [(4, 64, (32, 256), 1), (2, 32, (16, 128), 1), (4, 64, (64, 48), 0), (3, 64, (25, 128), 1)])
+def test_emulated_sharded_quantise_hooks_reproduce_the_one_call_path(emu, nbits, gs, shape, axis):
+    """hqq_b200_quantize_shard_begin / _finish (the early stop taken from error sums the caller may all-reduce): with the shard's own
+    sums and element count they must reproduce hqq_b200_quantize bit for bit; two 'ranks' that each hold half the rows and add their
+    sums get the unsharded iteration count."""
+    rng = np.random.default_rng(nbits * 7 + gs)
+    W = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    ref = quantize(emu, W, F32, nbits, gs, 1, axis=axis)
+    emu.hqq_b200_quantize_shard_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_int] * 4 + \
+        [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    emu.hqq_b200_quantize_shard_finish.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_int] * 4 + \
+        [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.c_size_t, ctypes.c_void_p]
+
+    def shard(Wp):
+        N, K = Wp.shape
+        Wd = aligned(Wp.shape, np.float32); Wd[...] = Wp
+        nb = emu.hqq_b200_quantize_workspace_bytes(N, K, gs, nbits, axis, 20)
+        ws = aligned((nb,), np.uint8)
+        sums = aligned((20,), np.float64)
+        rc = emu.hqq_b200_quantize_shard_begin(P(Wd), F32, N, K, gs, nbits, axis, int(nbits == 4), 0.7, 10.0, 20, P(sums), P(ws), nb, None)
+        assert rc == 0, emu.hqq_b200_last_error()
+        return Wd, ws, nb, sums
+
+    def finish(Wd, ws, nb, sums, total):
+        N, K = Wd.shape
+        G = N * K // gs
+        R, C = (G, gs) if axis == 1 else (gs, G)
+        prow = -(-R // 10) if nbits == 3 else R // (8 // nbits)
+        Wq = aligned((prow, C), np.int32 if nbits == 3 else np.uint8)
+        s, z, info, err = aligned((G,), np.float32), aligned((G,), np.float32), aligned((4,), np.int32), aligned((20,), np.float32)
+        rc = emu.hqq_b200_quantize_shard_finish(P(Wd), F32, N, K, gs, nbits, axis, int(nbits == 4), 0.7, 10.0, 20, P(sums), total, P(Wq), P(s), P(z),
+                                                P(info), P(err), P(ws), nb, None)
+        assert rc == 0, emu.hqq_b200_last_error()
+        return Wq, s, z, info, err
+
+    Wd, ws, nb, sums = shard(W)
+    got = finish(Wd, ws, nb, sums, W.size)
+    for x, y, what in zip(ref[:5], got, ("W_q", "scale", "zero", "info", "errors")):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
+    if axis == 1 and nbits != 3:  # two ranks, half the rows each: global sums -> the unsharded stop
+        h = shape[0] // 2
+        a, b = shard(W[:h]), shard(W[h:])
+        tot = aligned((20,), np.float64); tot[...] = a[3] + b[3]
+        ia = finish(a[0], a[1], a[2], tot, W.size)[3]
+        ib = finish(b[0], b[1], b[2], tot, W.size)[3]
+        assert int(ia[0]) == int(ib[0]) == int(ref[3][0])

@@ -165,3 +165,16 @@ def test_tensor_parallel_peer_exchange_matches_nccl():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29541", os.path.join(root, "tools", "tp_check.py")], capture_output=True, text=True, timeout=300)
     assert "AGREE 16 of 16" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_quantisation_equals_shards_of_the_unsharded_quantisation():
+    """every rank quantises its rows / groups with the early stop taken from all-reduced error sums
+    (hqq_b200_quantize_shard_begin / _finish) and gets exactly the shard models/tp.py cuts out of the unsharded quantisation."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29543", os.path.join(root, "tools", "tp_quant_check.py")], capture_output=True, text=True, timeout=300)
+    assert "SHARDED-QUANT ALL-IDENTICAL" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
