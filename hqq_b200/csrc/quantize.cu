@@ -209,63 +209,29 @@ __global__ void __launch_bounds__(kSolverThreads) solver_axis1_kernel(SolverArgs
     float ws[8];  // W_f * scale, the same rounding solver_elem applies every iteration
 #pragma unroll
     for (int j = 0; j < 8; ++j) ws[j] = __fmul_rn(w[j], st.s);
-    // (3) the float64 zero-point sum as an exact int32 sum.  While no level of the group is clamped and z >= 2.52, every term
-    //     t = fl(q - ws) lies within 0.5 + 2^-15 of z and is a multiple of 2^-22 (t >= 2), so r = t - z is exact (Sterbenz), a
-    //     multiple of 2^-22 below 1 in magnitude, and fl(r + 3.0) holds r * 2^22 in its mantissa: the lanes add integers, and
-    //     n z + I 2^-22 is the very float64 sum the general path accumulates (every partial sum there is exact as well).  The
-    //     same two conditions bound |W - W_r| by 0.51 / s, which replaces the per-element maximum of shortcut (1) when that is
-    //     below the threshold.  Saves the float->double conversion (1/8 rate), the DADD and both clamps per element.
-    float wsmin = ws[0], wsmax = ws[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) { wsmin = fminf(wsmin, ws[j]); wsmax = fmaxf(wsmax, ws[j]); }
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) {
-      wsmin = fminf(wsmin, __shfl_xor_sync(0xffffffffu, wsmin, o));
-      wsmax = fmaxf(wsmax, __shfl_xor_sync(0xffffffffu, wsmax, o));
-    }
-    const bool small_rs = __fmul_rn(0.51f, st.rs) < thr;
     float ew = 0.0f;  // warp-wide error sum of the last iteration executed
     int it = 0;
     while (it < a.iters) {
-      float errsum = 0.0f;
-      double zs;
-      const bool int_ok = !valid || (small_rs && st.z >= 2.52f && st.z < 250.0f && rint_magic(__fadd_rn(wsmin, st.z)) >= 0.0f &&
-                                     rint_magic(__fadd_rn(wsmax, st.z)) <= fmaxv);
-      if (__all_sync(0xffffffffu, int_ok)) {
-        int isum = 0;
+      float errsum = 0.0f, amax = 0.0f;
+      double zs = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float q = rint_magic(__fadd_rn(ws[j], st.z));  // in [0, maxv]: the clamp is the identity
-          const float wr = __fmul_rn(__fsub_rn(q, st.z), st.rs);
-          errsum += fabsf(__fsub_rn(w[j], wr));
-          const float r = __fsub_rn(__fsub_rn(q, ws[j]), st.z);
-          isum += (int)__float_as_uint(__fadd_rn(r, 3.0f)) - 0x40400000;
-        }
-#pragma unroll
-        for (int o = 1; o < L; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
-        zs = (double)st.z * (double)(8 * L) + (double)isum * (1.0 / 4194304.0);
-      } else {
-        float amax = 0.0f;
-        zs = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float q = rint_magic(__fadd_rn(ws[j], st.z));
-          q = fminf(fmaxf(q, 0.0f), fmaxv);
-          const float wr = __fmul_rn(__fsub_rn(q, st.z), st.rs);
-          const float ad = fabsf(__fsub_rn(w[j], wr));
-          errsum += ad;
-          amax = fmaxf(amax, ad);
-          zs += (double)__fsub_rn(q, ws[j]);
-        }
-        if (__any_sync(0xffffffffu, !(amax < thr))) {  // some |W - W_r| may survive the shrinkage: full formula for the warp
-          zs = 0.0;
-          float unused = 0.0f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
-        }
-#pragma unroll
-        for (int o = 1; o < L; o <<= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+      for (int j = 0; j < 8; ++j) {
+        float q = rint_magic(__fadd_rn(ws[j], st.z));
+        q = fminf(fmaxf(q, 0.0f), fmaxv);
+        const float wr = __fmul_rn(__fsub_rn(q, st.z), st.rs);
+        const float ad = fabsf(__fsub_rn(w[j], wr));
+        errsum += ad;
+        amax = fmaxf(amax, ad);
+        zs += (double)__fsub_rn(q, ws[j]);
       }
+      if (__any_sync(0xffffffffu, !(amax < thr))) {  // some |W - W_r| may survive the shrinkage: full formula for the warp
+        zs = 0.0;
+        float unused = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zs += (double)solver_elem(w[j], st, fmaxv, a.inv_beta, a.pm1, a.lp_is_one, unused);
+      }
+#pragma unroll
+      for (int o = 1; o < L; o <<= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
       const float znew = zero_mean(zs, 8 * L);  // torch.mean = sum / n, exactly as solver_axis1_kernel
       if (valid && l == 0) a.hist[(long long)(it + 1) * a.G + g] = znew;
       ew = valid ? errsum : 0.0f;
