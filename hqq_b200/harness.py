@@ -191,15 +191,13 @@ class DecodeModel:
             h = h + y
         h = F.rms_norm(h, (s.hidden,), self.final_norm, s.rms_eps)
         logits = torch.matmul(h, self.lm_head.t())
-        if self.tp > 1:  # vocabulary shards: (max, first index) per rank, the best one wins
+        if self.tp > 1:  # vocabulary shards: the global maximum, then the lowest global index that attains it (two small all-reduces)
             val, idx = torch.max(logits.float(), dim=-1)
-            vals = [torch.empty_like(val) for _ in range(self.tp)]
-            idxs = [torch.empty_like(idx) for _ in range(self.tp)]
-            torch.distributed.all_gather(vals, val, group=self.pg)
-            torch.distributed.all_gather(idxs, idx, group=self.pg)
-            vals, idxs = torch.stack(vals), torch.stack(idxs) + torch.arange(self.tp, device=idx.device).view(-1, 1) * self.vocab_shard
-            best = torch.argmax(vals, dim=0, keepdim=True)  # first rank on ties = lowest index
-            self.next_tok.copy_(torch.gather(idxs, 0, best).view(-1))
+            gmax = val.clone()
+            torch.distributed.all_reduce(gmax, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            cand = torch.where(val == gmax, idx + self.rank * self.vocab_shard, torch.full_like(idx, s.vocab))
+            torch.distributed.all_reduce(cand, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+            self.next_tok.copy_(cand)
         else:
             self.next_tok.copy_(torch.argmax(logits, dim=-1))
         self.pos.add_(1).remainder_(self.cache_len)
