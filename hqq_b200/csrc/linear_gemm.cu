@@ -45,6 +45,12 @@ struct Sched {
   int n_tok;     // token tiles of 256
   int i_split;   // first item that is a half tile
   int n_items;
+  // Few tiles (M <= 512 on most matrices): `ksplit` CTAs share a tile, each accumulating a contiguous run of k-blocks and writing
+  // its fp32 partial tile to the caller's workspace; splitk_reduce_kernel adds the partials in slice order (deterministic) and
+  // rounds.  Without it a [128 x K] tile is ONE serial stream per CTA with four stages in flight: ~960 cycles per 64-k block
+  // (first-touch DRAM latency), 32 CTAs busy out of 148 -- 32 us for 4096 x 4096 at any M <= 512 (profiles/r2_midm_options.log).
+  int ksplit;    // 1 = off; items are then (tile, slice), slice fastest
+  int n_row;     // row tiles
 };
 
 struct Args {
@@ -53,22 +59,34 @@ struct Args {
   const void* zero;
   const void* bias;
   void* y;
+  float* ws;     // ksplit > 1: [ksplit][n_row * n_tok][256 tokens][128 rows] fp32 partials
   int M, N, K;
   int step;  // packed rows = N / F
   int Gk;    // groups per row = K / GS
   Sched sched;
 };
 
-struct Item { int tile_n, m0, un; bool valid; };
+struct Item { int tile_n, m0, un, kb0, kb1, slice, tile; bool valid; };
 __host__ __device__ __forceinline__ Item decode_item(const Args& a, int j) {
   Item it;
+  const int num_kb = (a.K + kBlockK - 1) / kBlockK;
+  it.kb0 = 0; it.kb1 = num_kb; it.slice = 0;
   int base = j, half = -1;
-  if (j >= a.sched.i_split) { base = a.sched.i_split + ((j - a.sched.i_split) >> 1); half = (j - a.sched.i_split) & 1; }
+  if (a.sched.ksplit > 1) {
+    it.slice = j % a.sched.ksplit;
+    base = j / a.sched.ksplit;
+    const int quads = num_kb >> 2, per = (quads + a.sched.ksplit - 1) / a.sched.ksplit;
+    it.kb0 = it.slice * per * 4;
+    it.kb1 = ((it.slice + 1) * per < quads ? (it.slice + 1) * per : quads) * 4;
+  } else if (j >= a.sched.i_split) {
+    base = a.sched.i_split + ((j - a.sched.i_split) >> 1); half = (j - a.sched.i_split) & 1;
+  }
+  it.tile = base;
   it.tile_n = base / a.sched.n_tok;
   it.m0 = (base % a.sched.n_tok) * kUN;
   it.un = (a.M - it.m0 > 128) ? 256 : 128;
   if (half >= 0) { it.m0 += half * 128; it.un = 128; }
-  it.valid = it.m0 < a.M;
+  it.valid = it.m0 < a.M && it.kb0 < it.kb1;
   return it;
 }
 
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
         const Item im = decode_item(a, j);
         if (!im.valid) continue;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           constexpr uint32_t A_TX = DENSE ? S::A_STAGE : 0;  // dense: the weight tile rides the same barrier
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       tc_fence_after();
       const uint32_t idesc = make_idesc<T>(im.un);
       const uint32_t tmem_d = tmem_base + buf * kUN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = im.kb0; kb < im.kb1; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         if constexpr (!DENSE) mbar_wait(&full_a[s], ph);
@@ -347,9 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * S::B_STAGE));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
-            tc_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            tc_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((kb - im.kb0) | k) != 0);
           tc_commit(&empty[s]);                              // frees the stage when these MMAs have read it
-          if (kb == num_kb - 1) tc_commit(&acc_full[buf]);   // accumulator complete
+          if (kb == im.kb1 - 1) tc_commit(&acc_full[buf]);   // accumulator complete
         }
         __syncwarp();
       }
@@ -374,13 +392,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     const uint8_t* wptr = nullptr;
     const T* sptr[F];
     const T* zptr[F];
-    auto tile_ptrs = [&](int tile_n) {  // this thread's packed row / meta rows at k = 0 of a weight tile
-      const int prow0 = tile_n * PR;
+    auto tile_ptrs = [&](const Item& im) {  // this thread's packed row / meta rows at the first k-block of an item
+      const int prow0 = im.tile_n * PR;
       const bool row_ok = (prow0 + pr) < a.step;  // rows past the ragged edge re-read row 0 (always mapped); never stored
-      wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT;
+      wptr = a.Wq + (long long)(row_ok ? prow0 + pr : 0) * a.K + c * BPT + (long long)im.kb0 * kBlockK;
 #pragma unroll
       for (int f = 0; f < F; ++f) {
-        const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk;
+        const long long mrow = (long long)(row_ok ? f * a.step + prow0 + pr : 0) * a.Gk + (im.kb0 >> 2) * GPQ;
         sptr[f] = reinterpret_cast<const T*>(a.scale) + mrow;
         zptr[f] = reinterpret_cast<const T*>(a.zero) + mrow;
       }
@@ -405,12 +423,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
 #pragma unroll
       for (int f = 0; f < F; ++f) { sv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(sptr[f]); zv[f] = *reinterpret_cast<const Vec<T, GPQ>*>(zptr[f]); }
     };
-    const int num_quads = num_kb >> 2;  // K % 256 == 0 (checked by the router): every tile starts at ring stage 0
+    // K % 256 == 0 (checked by the router) and k-slices are whole quads: every item starts at ring stage 0
     int j = next_valid((int)blockIdx.x);
-    if (j < n_items) { tile_ptrs(decode_item(a, j).tile_n); load_quad(); }
+    if (j < n_items) { tile_ptrs(decode_item(a, j)); load_quad(); }
     uint32_t gq = 0;  // quads done so far (ring parity)
     while (j < n_items) {
       const int jn = next_valid(j + (int)gridDim.x);
+      const Item cur = decode_item(a, j);
+      const int num_quads = (cur.kb1 - cur.kb0) >> 2;
       for (int q = 0; q < num_quads; ++q, ++gq) {
         uint32_t wq[4][BPT / 4];
         typename P2::T2 s2[4][F], z2[4][F];
@@ -431,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           if (q + 4 < num_quads) HQQ_PREFETCH_L2(wptr + 3 * 4 * kBlockK + (c & 1) * 128);
           load_quad();
         } else if (jn < n_items) {
-          tile_ptrs(decode_item(a, jn).tile_n);
+          tile_ptrs(decode_item(a, jn));
           load_quad();
         }
         const uint32_t parity = (gq & 1u) ^ 1u;
@@ -491,13 +511,21 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       for (int col = 0; col < im.un; col += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kUN + (uint32_t)col, v);
+        if (a.sched.ksplit > 1) {
+          // fp32 partial of this k-slice: [slice][tile][token][tile row] -- 32 lanes write 32 consecutive rows (128 bytes)
+          float* wsp = a.ws + (((size_t)im.slice * (size_t)(a.sched.n_row * a.sched.n_tok) + (size_t)im.tile) * kUN + (size_t)col) * kTileRows + t;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int m = im.m0 + col + jj;
-          if (n_ok && m < a.M) {
-            T o = cvt_out<T>(__uint_as_float(v[jj]));
-            if (has_bias) o = __hadd(o, bn);  // out += bias: second rounding, as in the reference
-            y[(long long)m * a.N + n] = o;
+          for (int jj = 0; jj < 32; ++jj)
+            if (im.m0 + col + jj < a.M) wsp[(size_t)jj * kTileRows] = __uint_as_float(v[jj]);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int m = im.m0 + col + jj;
+            if (n_ok && m < a.M) {
+              T o = cvt_out<T>(__uint_as_float(v[jj]));
+              if (has_bias) o = __hadd(o, bn);  // out += bias: second rounding, as in the reference
+              y[(long long)m * a.N + n] = o;
+            }
           }
         }
       }
@@ -513,6 +541,26 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// Split-K second pass: y[m][n] = round(sum over slices, in slice order) (+ bias).  One thread per output, consecutive threads =
+// consecutive n = (mostly) consecutive tile rows: coalesced on both sides.
+template <typename T>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, T* __restrict__ y, const T* __restrict__ bias, int M, int N,
+                                                            int step, int PR, int S, int n_row, int n_tok) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  const int f = n / step, prg = n % step;
+  const int tile_n = prg / PR, t = f * PR + prg % PR;
+  const int tile = tile_n * n_tok + m / kUN, col = m % kUN;
+  const size_t slice_stride = (size_t)n_row * n_tok * kUN * kTileRows;
+  const float* p = ws + ((size_t)tile * kUN + col) * kTileRows + t;
+  float acc = 0.0f;
+  for (int sidx = 0; sidx < S; ++sidx) acc += p[(size_t)sidx * slice_stride];
+  T o = cvt_out<T>(acc);
+  if (bias) o = __hadd(o, bias[n]);
+  y[idx] = o;
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -555,10 +603,33 @@ static int sm_count() {
 }
 
 // see `Sched`: full tiles first, the last partial round as half tiles when that shortens it
-Sched make_sched(int64_t M, int64_t row_tiles, int P) {
+// HQQ_B200_GEMM_CTAS=<n> (test hook): the number of persistent CTAs the schedule is built for instead of the SM count, so that
+// small problems exercise tile-after-tile execution, both accumulators, the half-tile round and split-K (the emulator tests and
+// tests/test_linear_gpu.py set it; results never depend on it beyond the split-K summation order, which they pin)
+static int persistent_ctas() {
+  HQQ_ENV_KNOB(cta_cap, ([] { const char* e = getenv("HQQ_B200_GEMM_CTAS"); return e ? atoi(e) : 0; })());
+  return cta_cap > 0 ? cta_cap : sm_count();
+}
+
+// see `Sched`: few tiles -> k-slices; else full tiles first, the last partial round as half tiles when that shortens it
+Sched make_sched(int64_t M, int64_t K, int64_t row_tiles, int P, bool allow_splitk) {
   Sched s;
   s.n_tok = (int)cdiv(M, kUN);
+  s.n_row = (int)row_tiles;
+  s.ksplit = 1;
   const int64_t full = row_tiles * s.n_tok;
+  const int64_t quads = K / 256;
+  if (allow_splitk && full * 2 <= P && quads >= 2) {
+    int64_t S = P / full;
+    if (S > 8) S = 8;
+    if (S > quads) S = quads;
+    S = cdiv(quads, cdiv(quads, S));  // every slice gets cdiv(quads, S) quads: drop the slices that would stay empty
+    if (S >= 2) {
+      s.ksplit = (int)S;
+      s.i_split = s.n_items = (int)(full * S);
+      return s;
+    }
+  }
   const int64_t r = full % P;
   const int64_t r_split = (r > 0 && 2 * r <= P) ? r : 0;
   s.i_split = (int)(full - r_split);
@@ -566,8 +637,12 @@ Sched make_sched(int64_t M, int64_t row_tiles, int P) {
   return s;
 }
 
+static size_t splitk_ws_bytes(const Sched& s) {
+  return s.ksplit > 1 ? (size_t)s.ksplit * (size_t)s.n_row * s.n_tok * kUN * kTileRows * sizeof(float) : 0;
+}
+
 template <typename T, int NBITS, int GS>
-static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W = nullptr) {
+static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W = nullptr, void* ws = nullptr, size_t ws_bytes = 0) {
   CUtensorMap xmap256, xmap128, amap;
   const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc = encode_map(&xmap256, x, a.M, a.K, dt, sizeof(T), kUN);
@@ -581,12 +656,15 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
     amap = xmap128;  // unused
   }
   constexpr int PR = NBITS == 16 ? kTileRows : kTileRows / (NBITS == 16 ? 1 : 8 / NBITS);
-  // HQQ_B200_GEMM_CTAS=<n> (test hook): cap the persistent grid, so that small problems exercise tile-after-tile execution, both
-  // accumulators and the half-tile round (the emulator tests and tests/test_linear_gpu.py set it; results never depend on it)
-  HQQ_ENV_KNOB(cta_cap, ([] { const char* e = getenv("HQQ_B200_GEMM_CTAS"); return e ? atoi(e) : 0; })());
-  int P = sm_count();
-  if (cta_cap > 0 && cta_cap < P) P = cta_cap;
-  a.sched = make_sched(a.M, cdiv(a.step, PR), P);
+  const int P = persistent_ctas();
+  a.sched = make_sched(a.M, a.K, cdiv(a.step, PR), P, NBITS != 16);
+  a.ws = nullptr;
+  if (a.sched.ksplit > 1) {
+    const size_t need = splitk_ws_bytes(a.sched);
+    HQQ_REQUIRE(ws != nullptr && ws_bytes >= need && aligned(ws, 256), HQQ_E_WORKSPACE,
+                "hqq_b200_linear_fwd: this shape runs split-K and needs a 256-byte aligned workspace of %zu bytes (got %zu)", need, ws_bytes);
+    a.ws = reinterpret_cast<float*>(ws);
+  }
   const int grid = a.sched.n_items < P ? a.sched.n_items : P;
   auto k = linear_gemm_kernel<T, NBITS, GS>;
   int dev = 0;
@@ -599,22 +677,28 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
   }
   k<<<grid, kThreads, Smem::BYTES, st>>>(xmap256, xmap128, amap, a);
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
+  if (a.sched.ksplit > 1) {
+    const long long total = (long long)a.M * a.N;
+    splitk_reduce_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M, a.N,
+                                                                         a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
+    HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/splitk-reduce");
+  }
   return HQQ_OK;
 }
 
 template <typename T, int NBITS>
-static int by_gs(const void* x, Args& a, int gs, cudaStream_t st) {
-  if (gs == 64) return launch<T, NBITS, 64>(x, a, st);
-  return launch<T, NBITS, 128>(x, a, st);
+static int by_gs(const void* x, Args& a, int gs, cudaStream_t st, void* ws, size_t ws_bytes) {
+  if (gs == 64) return launch<T, NBITS, 64>(x, a, st, nullptr, ws, ws_bytes);
+  return launch<T, NBITS, 128>(x, a, st, nullptr, ws, ws_bytes);
 }
 
 template <typename T>
-static int by_bits(const void* x, Args& a, int gs, int nbits, cudaStream_t st) {
+static int by_bits(const void* x, Args& a, int gs, int nbits, cudaStream_t st, void* ws, size_t ws_bytes) {
   switch (nbits) {
-    case 8: return by_gs<T, 8>(x, a, gs, st);
-    case 4: return by_gs<T, 4>(x, a, gs, st);
-    case 2: return by_gs<T, 2>(x, a, gs, st);
-    case 1: return by_gs<T, 1>(x, a, gs, st);
+    case 8: return by_gs<T, 8>(x, a, gs, st, ws, ws_bytes);
+    case 4: return by_gs<T, 4>(x, a, gs, st, ws, ws_bytes);
+    case 2: return by_gs<T, 2>(x, a, gs, st, ws, ws_bytes);
+    case 1: return by_gs<T, 1>(x, a, gs, st, ws, ws_bytes);
   }
   return HQQ_E_UNSUPPORTED;
 }
@@ -632,7 +716,10 @@ bool gemm_route_ok(int64_t M, int64_t N, int64_t K, int gs, int nbits, int axis,
   return true;
 }
 
-size_t gemm_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int, int nbits, int) {
+  const int F = 8 / nbits, PR = gemm::kTileRows / F;
+  return gemm::splitk_ws_bytes(gemm::make_sched(M, K, cdiv(N / F, PR), gemm::persistent_ctas(), true));
+}
 
 // y[M, N] = x[M, K] @ W[N, K]^T (+ bias), W an ordinary fp16/bf16 matrix: the same persistent tcgen05 kernel with both operands on TMA
 bool dense_route_ok(int64_t M, int64_t N, int64_t K, int dtype) {
@@ -656,15 +743,14 @@ int linear_dense(const void* x, const void* W, const void* bias, void* y, int64_
 
 int linear_gemm(const void* x, const void* Wq, const void* scale, const void* zero, const void* bias, void* y, int64_t M, int64_t N,
                 int64_t K, int gs, int nbits, int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
-  (void)ws; (void)ws_bytes;
   HQQ_REQUIRE(aligned(x, 16) && aligned(Wq, 16), HQQ_E_INVALID, "hqq_b200_linear_fwd: x and W_q must be 16-byte aligned");
   gemm::Args a;
   a.Wq = (const uint8_t*)Wq; a.scale = scale; a.zero = zero; a.bias = bias; a.y = y;
   a.M = (int)M; a.N = (int)N; a.K = (int)K;
   a.step = (int)(N / (8 / nbits));
   a.Gk = (int)(K / gs);
-  if (dtype == HQQ_F16) return gemm::by_bits<__half>(x, a, gs, nbits, st);
-  return gemm::by_bits<__nv_bfloat16>(x, a, gs, nbits, st);
+  if (dtype == HQQ_F16) return gemm::by_bits<__half>(x, a, gs, nbits, st, ws, ws_bytes);
+  return gemm::by_bits<__nv_bfloat16>(x, a, gs, nbits, st, ws, ws_bytes);
 }
 
 }  // namespace hqq

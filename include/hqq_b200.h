@@ -135,9 +135,10 @@ int hqq_b200_quantize_shard_finish(const void* W, int src_dtype, int64_t N, int6
  *   nbits 8/4/2/1, group_size 64/128, K % 256 == 0 -- and 3 = everything else hqq_b200_dequantize accepts (3-bit, axis 0, other
  *   group sizes, ragged K): the dequantize kernel writes W_r into `workspace`, the dense tcgen05 GEMM multiplies.  Returns
  *   HQQ_E_UNSUPPORTED where none applies (fp32 compute).
- *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, 256-byte aligned scratch owned by the caller: 0 for routes 1 and 2
- *   (split-K partials of the small-M kernel meet in shared memory), N*K*sizeof(dtype) for route 3.  Contents on entry are
- *   irrelevant.                                                                                                        */
+ *   workspace: hqq_b200_linear_fwd_workspace_bytes() bytes, 256-byte aligned scratch owned by the caller: 0 for route 1
+ *   (split-K partials of the small-M kernel meet in shared memory); route 2: 0 unless the problem has so few output tiles
+ *   (roughly M <= 512 on a 4096-row matrix) that the kernel splits K over CTAs -- then the fp32 partial tiles, summed in slice
+ *   order by a second pass (deterministic); route 3: N*K*sizeof(dtype) for W_r.  Contents on entry are irrelevant.           */
 size_t hqq_b200_linear_fwd_workspace_bytes(int64_t M, int64_t N, int64_t K, int group_size,
                                            int nbits, int axis, int dtype);
 int hqq_b200_linear_fwd(const void* x, const void* W_q, const void* scale, const void* zero,

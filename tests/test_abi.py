@@ -67,6 +67,7 @@ def test_forward_routing_table(lib):
     assert r(4096, 4096, 4096, 64, 4, 1, HQQ_F16) == 2   # fused tcgen05 GEMM
     wsb = lib.hqq_b200_linear_fwd_workspace_bytes
     assert wsb(1, 4096, 4096, 64, 4, 1, HQQ_F16) == 0 and wsb(4096, 4096, 4096, 64, 4, 1, HQQ_F16) == 0
+    assert wsb(128, 4096, 4096, 64, 4, 1, HQQ_F16) % (32 * 256 * 128 * 4) == 0 and wsb(128, 4096, 4096, 64, 4, 1, HQQ_F16) > 0  # few tiles: split-K partials
     assert wsb(64, 4096, 4096, 64, 3, 1, HQQ_F16) == 4096 * 4096 * 2 and wsb(64, 4096, 4096, 64, 4, 0, HQQ_BF16) == 4096 * 4096 * 2
     assert r(64, 4096, 4096, 64, 4, 1, HQQ_F16) != 1     # beyond the small-M kernel
 

@@ -290,11 +290,11 @@ def test_emulated_tcgen05_gemm_matches_the_oracle(emu, tmp_path_factory):
     for k in refs:
         # the A operand is dequantised with the reference's two roundings and accumulated in fp32: far inside the fp16 tolerance
         assert rel(d[k[:-4]], d[k]) <= 1e-4, k
-        assert np.array_equal(d[k[:-4]], d[k[:-4] + "_again"]), k
-        assert int(d[k[:-4] + "_ws"][0]) == 0  # no default route needs scratch
+        assert np.array_equal(d[k[:-4]], d[k[:-4] + "_again"]), k  # also on a dirty split-K workspace: deterministic
+    assert sum(int(d[k[:-4] + "_ws"][0]) > 0 for k in refs) >= 1  # few tiles x long K: k-slices + second-pass reduction
 
 
-@pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_CTAS", "1"), ("HQQ_B200_GEMM_CTAS", "3"), ("HQQ_B200_GEMM_CTAS", "5")])
+@pytest.mark.parametrize("knob", [("HQQ_B200_GEMM_CTAS", "1"), ("HQQ_B200_GEMM_CTAS", "3"), ("HQQ_B200_GEMM_CTAS", "5"), ("HQQ_B200_GEMM_CTAS", "24")])
 def test_emulated_persistent_gemm_schedules_are_bit_identical(emu, tmp_path_factory, knob):
     """The persistent kernel with its grid capped to 1 / 3 / 5 CTAs: every CTA then walks several tiles (both TMEM accumulators,
     epilogue of tile i under the main loop of tile i + 1, rings running across tile boundaries, the half-tile round of the
@@ -302,7 +302,13 @@ def test_emulated_persistent_gemm_schedules_are_bit_identical(emu, tmp_path_fact
     and no barrier protocol that stalls."""
     ref, got = run_gemm_emu(tmp_path_factory), run_gemm_emu(tmp_path_factory, knob)
     for k in ref:
-        if not k.endswith("_ws"):
+        if k.endswith("_ws"):
+            continue
+        base = k[:-6] if k.endswith("_again") else (k[:-4] if k.endswith("_ref") else k)
+        split = (base + "_ws") in ref and (int(ref[base + "_ws"][0]) > 0 or int(got[base + "_ws"][0]) > 0)
+        if split and not k.endswith("_ref"):  # the number of k-slices follows the CTA count: fp32 summation order differs
+            assert rel(got[k], ref[k]) <= 1e-4, k
+        else:
             assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
 
 
@@ -310,11 +316,10 @@ def test_emulated_persistent_gemm_schedules_are_bit_identical(emu, tmp_path_fact
 def test_emulated_persistent_gemm_under_adversarial_timing(emu, tmp_path_factory, seed):
     """EMU_ASYNC: TMA copies, tensor-core operations and their commits land a random number of scheduler passes late and threads
     resume in random order; the capped grid keeps several tiles per CTA in flight.  Same bits as the in-order run."""
-    ref = run_gemm_emu(tmp_path_factory)
+    ref = run_gemm_emu(tmp_path_factory, ("HQQ_B200_GEMM_CTAS", "2"))
     got = run_gemm_emu(tmp_path_factory, ("HQQ_B200_GEMM_CTAS", "2"), async_seed=seed)
     for k in ref:
-        if not k.endswith("_ws"):
-            assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
+        assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
 
 
 @pytest.mark.parametrize("tp", [2, 8])
