@@ -234,14 +234,24 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
 // (ordered() is the usual monotone float -> uint32 map; fp16/bf16 values leave the low mantissa bits of the float zero, so the
 // shift that keeps the sign bit clear loses nothing).
 constexpr int kArgmaxCtas = 8;
+//
+// tp > 0 (hqq_b200_glue_argmax_tp): the key exchange happens in this launch.  Bits 32..43 of a key are the same for every fp16 /
+// bf16 value of one sign (they are below the 16-bit value's precision), so they can carry a 12-bit tag of the token step without
+// disturbing the order, as long as every rank uses the same tag in the same step.  CTA 0 stores its tagged key into slot
+// [parity][rank] of every peer's key area (one aligned 8-byte store each: value, index and tag arrive together), polls its own
+// slots [parity][0..tp) until all carry this step's tag, and writes the winner's index to out[0].  Two parities suffice: a rank
+// cannot finish step s+1 before every peer has sent its step s+1 key, which a peer does only after it has read step s.
+struct KeyPeers { unsigned long long* p[8]; };
 template <typename T>
 __global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argmax_kernel(const T* __restrict__ x, int n, long long* __restrict__ out,
-                                                                                            long long key_offset) {
+                                                                                            long long key_offset, KeyPeers peers, int tp, int tp_rank,
+                                                                                            const int* __restrict__ step_ctr) {
   namespace cg = cooperative_groups;
   __shared__ float bv[32];
   __shared__ int bi[32];
   __shared__ float cv[kArgmaxCtas];
   __shared__ int ci[kArgmaxCtas];
+  __shared__ unsigned long long xkey;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   pdl_launch_g();
@@ -281,7 +291,33 @@ __global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argm
     } else {
       const uint32_t u = __float_as_uint(best);
       const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-      out[0] = (long long)(((unsigned long long)(ord >> 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(key_offset + idx)));
+      const unsigned long long key = ((unsigned long long)(ord >> 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(key_offset + idx));
+      if (tp <= 0) out[0] = (long long)key;
+      else xkey = key;
+    }
+  }
+  if (tp > 0 && rank == 0) {  // uniform per CTA
+    __syncthreads();
+    if ((int)threadIdx.x < 32) {
+      const int seq = *reinterpret_cast<const volatile int*>(step_ctr);  // already bumped by this token's final norm: >= 1
+      const unsigned long long tag = (unsigned long long)((unsigned)seq & 0xFFFu) << 32, tmask = 0xFFFull << 32;
+      const int par = seq & 1, t = (int)threadIdx.x;
+      long long got = 0;  // keys are non-negative
+      if (t < tp) {
+        const unsigned long long mine = (xkey & ~tmask) | tag;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(peers.p[t] + par * tp + tp_rank), "l"(mine) : "memory");
+        const unsigned long long* slot = peers.p[tp_rank] + par * tp + t;
+        unsigned long long v;
+        unsigned spins = 0;  // a peer that never arrives (it died) ends in a launch failure, not in a GPU that spins for ever
+        do {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+          if (++spins == (1u << 27)) __trap();
+        } while ((v & tmask) != tag);
+        got = (long long)v;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) { const long long ov = __shfl_xor_sync(0xffffffffu, got, o); got = ov > got ? ov : got; }
+      if (t == 0) out[0] = (long long)(0xFFFFFFFFu - (uint32_t)((unsigned long long)got & 0xFFFFFFFFull));
     }
   }
 }
@@ -362,8 +398,8 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
 extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {
   HQQ_REQUIRE(logits && out && n > 0, HQQ_E_INVALID, "hqq_b200_glue_argmax: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out, -1LL);
-  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out, -1LL);
+  if (dtype == HQQ_F16) return launch_pdl("argmax", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out, -1LL, KeyPeers{}, 0, 0, (const int*)nullptr);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out, -1LL, KeyPeers{}, 0, 0, (const int*)nullptr);
   set_error("hqq_b200_glue_argmax: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }
@@ -371,8 +407,25 @@ extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int
 extern "C" int hqq_b200_glue_argmax_key(const void* logits, int n, int64_t index_offset, int64_t* out_key, int dtype, void* stream) {
   HQQ_REQUIRE(logits && out_key && n > 0 && index_offset >= 0 && index_offset + n <= 0xFFFFFFFFll, HQQ_E_INVALID, "hqq_b200_glue_argmax_key: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == HQQ_F16) return launch_pdl("argmax_key", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out_key, (long long)index_offset);
-  if (dtype == HQQ_BF16) return launch_pdl("argmax_key", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out_key, (long long)index_offset);
+  if (dtype == HQQ_F16) return launch_pdl("argmax_key", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out_key, (long long)index_offset, KeyPeers{}, 0, 0, (const int*)nullptr);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax_key", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out_key, (long long)index_offset, KeyPeers{}, 0, 0, (const int*)nullptr);
   set_error("hqq_b200_glue_argmax_key: dtype must be f16/bf16");
+  return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_argmax_tp(const void* logits, int n, int64_t index_offset, void* const* peer_keys, int tp, int rank, const int* step_ctr,
+                                       int64_t* out, int dtype, void* stream) {
+  HQQ_REQUIRE(logits && out && peer_keys && step_ctr && n > 0 && index_offset >= 0 && index_offset + n <= 0xFFFFFFFFll && tp >= 1 && tp <= 8 &&
+                  rank >= 0 && rank < tp,
+              HQQ_E_INVALID, "hqq_b200_glue_argmax_tp: bad arguments (n=%d tp=%d rank=%d)", n, tp, rank);
+  KeyPeers kp = {};
+  for (int i = 0; i < tp; ++i) {
+    HQQ_REQUIRE(peer_keys[i] && ((uintptr_t)peer_keys[i] & 7) == 0, HQQ_E_INVALID, "hqq_b200_glue_argmax_tp: key area %d must be 8-byte aligned", i);
+    kp.p[i] = (unsigned long long*)peer_keys[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == HQQ_F16) return launch_pdl("argmax_tp", argmax_kernel<__half>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __half*)logits, n, (long long*)out, (long long)index_offset, kp, tp, rank, step_ctr);
+  if (dtype == HQQ_BF16) return launch_pdl("argmax_tp", argmax_kernel<__nv_bfloat16>, dim3(kArgmaxCtas), dim3(1024), 0, st, (const __nv_bfloat16*)logits, n, (long long*)out, (long long)index_offset, kp, tp, rank, step_ctr);
+  set_error("hqq_b200_glue_argmax_tp: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }

@@ -204,13 +204,18 @@ class DecodeModel:
 
     def _head(self, lib, x, code, st):
         """Final projection + greedy pick inside the captured step: fp16 lm_head through the library GEMV (it is not an HQQ
-        layer), then our argmax kernel; with tp > 1 each rank covers its vocabulary shard and one 8-byte MAX all-reduce of
-        {value : index} keys picks the winner."""
+        layer), then our argmax kernel; with tp > 1 each rank covers its vocabulary shard and the MAX of the ranks' 8-byte
+        {value : index} keys picks the winner -- exchanged inside the argmax launch over peer-mapped memory ("p2p"), or by one
+        NCCL all-reduce ("nccl")."""
         from ._lib import check, ptr
         b = self._bufs
         torch.matmul(x, self.lm_head.t(), out=b["logits"])
         if self.tp == 1:
             check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), self.vocab_shard, ptr(self.next_tok), code, st))
+            return
+        if self.fused == 5 and self.tp_mode == "p2p":  # the keys meet in peer-mapped memory inside the argmax launch
+            check(lib.hqq_b200_glue_argmax_tp(ptr(b["logits"]), self.vocab_shard, self.rank * self.vocab_shard, self._tp_keys, self.tp, self.rank,
+                                              self._xstep.data_ptr(), ptr(self.next_tok), code, st))
             return
         check(lib.hqq_b200_glue_argmax_key(ptr(b["logits"]), self.vocab_shard, self.rank * self.vocab_shard, ptr(b["key"]), code, st))
         torch.distributed.all_reduce(b["key"], op=torch.distributed.ReduceOp.MAX, group=self.pg)
@@ -256,22 +261,24 @@ class DecodeModel:
         import ctypes
         s, tp, dev = self.shape, self.tp, self.device
         slot_bytes = 2 * tp * s.hidden * 4
+        key_bytes = 2 * tp * 8  # argmax keys of the vocabulary-sharded lm_head, uint64 [2 parities][tp] (hqq_b200_glue_argmax_tp)
         if tp > 1:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
-            buf = symm.empty(2 * slot_bytes, dtype=torch.uint8, device=dev)
+            buf = symm.empty(2 * slot_bytes + key_bytes, dtype=torch.uint8, device=dev)
             buf.fill_(0xFF)  # tag 0xFFFF is only reached after 65535 exchanges; by then every word has been overwritten
             hdl = symm.rendezvous(buf, self.pg if self.pg is not None else dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             self._xhdl = hdl
         else:
-            buf = torch.full((2 * slot_bytes,), 0xFF, dtype=torch.uint8, device=dev)
+            buf = torch.full((2 * slot_bytes + key_bytes,), 0xFF, dtype=torch.uint8, device=dev)
             ptrs = [buf.data_ptr()]
         self._xbuf = buf
         self._xstep = torch.zeros(1, dtype=torch.int32, device=dev)
         VP = ctypes.c_void_p * tp
         self._tp_keep = [VP(*[p + slot * slot_bytes for p in ptrs]) for slot in range(2)]
         self._tp_local = [ptrs[self.rank] + slot * slot_bytes for slot in range(2)]
+        self._tp_keys = VP(*[p + 2 * slot_bytes for p in ptrs])
         torch.cuda.synchronize(dev)
         if tp > 1:
             dist.barrier()

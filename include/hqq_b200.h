@@ -232,6 +232,13 @@ int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, voi
  * argmax)} of this rank's logits slice; the MAX of the keys over the ranks (one 8-byte all-reduce) names the global argmax, first
  * index on ties: token = 0xFFFFFFFF - (key & 0xFFFFFFFF). */
 int hqq_b200_glue_argmax_key(const void* logits, int n, int64_t index_offset, int64_t* out_key, int dtype, void* stream);
+/* The same pick with the key exchange inside the launch (tensor-parallel decode over peer-mapped memory, no collective library
+ * call in the step): peer_keys[r] is rank r's key area, uint64 [2][tp], initialised to 0xFF bytes; *step_ctr >= 1 is the token
+ * counter every rank advances in step (hqq_b200_glue_add_rmsnorm_tp bumps it).  Each rank stores its key, tagged with 12 bits of
+ * the counter in key bits that are equal for all 16-bit values of one sign, into slot [ctr & 1][rank] of every peer, waits for
+ * the tp keys of this step in its own area and writes the global argmax (first index on ties) to out[0]. */
+int hqq_b200_glue_argmax_tp(const void* logits, int n, int64_t index_offset, void* const* peer_keys, int tp, int rank,
+                            const int* step_ctr, int64_t* out, int dtype, void* stream);
 
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (used by bench.py for its gpu_launches claim).                                        */

@@ -38,6 +38,46 @@ def test_glue_kernels_match_torch_ops(dt):
         assert int(out) == min(hot), (n, int(out))
 
 
+def _argmax_key(value: float, index: int, tag: int) -> int:
+    """The 64-bit key hqq_b200_glue_argmax_tp exchanges (include/hqq_b200.h): ordered(value) >> 1 in the high word with the 12-bit
+    tag in bits 32..43, 0xFFFFFFFF - index in the low word."""
+    import struct
+    u = struct.unpack("<I", struct.pack("<f", value))[0]
+    ord_ = (~u & 0xFFFFFFFF) if (u & 0x80000000) else (u | 0x80000000)
+    hi = ((ord_ >> 1) & ~0xFFF) | (tag & 0xFFF)
+    return (hi << 32) | (0xFFFFFFFF - index)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_argmax_with_key_exchange_in_the_launch(dt):
+    """hqq_b200_glue_argmax_tp on ONE GPU standing in for rank 0 of 2: both key areas are the same buffer and rank 1's key of the
+    step is planted there beforehand.  The winner is the larger value, the lower index on equal values, whatever the sign; the
+    key of an older step (another tag) in the slot is not taken for this step's."""
+    import ctypes
+    lib = load()
+    st, code = stream_ptr(DEV), DTYPE_CODE[dt]
+    torch.manual_seed(5)
+    n, tp = 16032, 2
+    VP = ctypes.c_void_p * tp
+    out = torch.zeros(1, dtype=torch.long, device=DEV)
+    for step, (local_top, peer_val, peer_idx) in enumerate(((3.0, 2.5, n + 7), (3.0, 3.5, n + 7), (3.0, 3.0, n + 900), (-2.0, -1.5, 2 * n - 1),
+                                                            (-1.0, -1.5, n), (0.0, -0.5, n + 1)), start=1):
+        lg = (torch.full((1, n), -4.0, device=DEV) - torch.rand(1, n, device=DEV)).to(dt)
+        lg[0, 4321] = local_top
+        lg[0, 9000] = local_top  # tie inside the shard: first index
+        keys = torch.full((2 * tp,), -1, dtype=torch.long, device=DEV)  # 0xFF bytes, as the harness initialises the area
+        ctr = torch.tensor([step], dtype=torch.int32, device=DEV)
+        par = step & 1
+        keys[par * tp + 1] = _argmax_key(peer_val, peer_idx, step)
+        keys[(1 - par) * tp + 1] = _argmax_key(100.0, 5, step + 1)  # the other parity holds a key of another step: never read
+        peers = VP(keys.data_ptr(), keys.data_ptr())
+        check(lib.hqq_b200_glue_argmax_tp(ptr(lg), n, 0, peers, tp, 0, ctr.data_ptr(), ptr(out), code, st))
+        torch.cuda.synchronize()
+        want = peer_idx if peer_val > local_top else 4321
+        assert int(out) == want, (step, int(out), want)
+        assert int(keys[par * tp + 0]) == _argmax_key(local_top, 4321, step)  # what rank 0 published
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 def test_rope_attention_kernel(dt):
     lib = load()
