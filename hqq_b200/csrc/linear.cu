@@ -28,8 +28,16 @@ static bool dequant_ok(int64_t N, int64_t K, int gs, int nbits, int axis) {
 
 static size_t dense_ws_bytes(int64_t N, int64_t K, int dtype) { return (size_t)((N * K * (int64_t)dtype_size(dtype) + 255) & ~(int64_t)255); }
 
+// HQQ_B200_SMALL_M_MAX=<m> (measurement hook): the largest M the single-matrix entry point hands to the small-M kernel when the
+// tcgen05 route would take the shape too (default 32, the small kernel's own limit)
+static int small_m_max() {
+  HQQ_ENV_KNOB(m, ([] { const char* e = getenv("HQQ_B200_SMALL_M_MAX"); return e ? atoi(e) : 0; })());
+  return m > 0 ? m : 32;
+}
+
 extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {
-  if (small_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 1;
+  const bool small = small_route_ok(M, N, K, group_size, nbits, axis, dtype);
+  if (small && (M <= small_m_max() || !gemm_route_ok(M, N, K, group_size, nbits, axis, dtype))) return 1;
   if (gemm_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 2;
   if (dequant_ok(N, K, group_size, nbits, axis) && dense_route_ok(M, N, K, dtype)) return 3;  // dequantize kernel -> dense tcgen05 GEMM
   return 0;

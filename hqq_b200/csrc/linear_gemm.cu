@@ -543,12 +543,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   }
 }
 
-// Split-K second pass: y[m][n] = round(sum over slices, in slice order) (+ bias).  One thread per output, consecutive threads =
-// consecutive n = (mostly) consecutive tile rows: coalesced on both sides.
-template <typename T>
+// Split-K second pass: y[m][n] = round(sum over slices, in slice order) (+ bias).  A thread owns V consecutive outputs (V = 4 when
+// step, N and y allow 8-byte stores, else 1): they are consecutive rows of one tile column in the workspace, so both sides are
+// coalesced vector accesses.  All slices are loaded before the first add -- the loads are independent, the adds keep the order.
+template <typename T, int V>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, T* __restrict__ y, const T* __restrict__ bias, int M, int N,
                                                             int step, int PR, int S, int n_row, int n_tok) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (idx >= (long long)M * N) return;
   const int m = (int)(idx / N), n = (int)(idx % N);
   const int f = n / step, prg = n % step;
@@ -556,11 +557,35 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   const int tile = tile_n * n_tok + m / kUN, col = m % kUN;
   const size_t slice_stride = (size_t)n_row * n_tok * kUN * kTileRows;
   const float* p = ws + ((size_t)tile * kUN + col) * kTileRows + t;
-  float acc = 0.0f;
-  for (int sidx = 0; sidx < S; ++sidx) acc += p[(size_t)sidx * slice_stride];
-  T o = cvt_out<T>(acc);
-  if (bias) o = __hadd(o, bias[n]);
-  y[idx] = o;
+  float part[8][V];
+#pragma unroll
+  for (int sidx = 0; sidx < 8; ++sidx) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) part[sidx][v] = 0.0f;
+    if (sidx < S) {
+      if constexpr (V == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(p + (size_t)sidx * slice_stride);
+        part[sidx][0] = q.x; part[sidx][1] = q.y; part[sidx][2] = q.z; part[sidx][3] = q.w;
+      } else {
+        part[sidx][0] = p[(size_t)sidx * slice_stride];
+      }
+    }
+  }
+  T o[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int sidx = 0; sidx < 8; ++sidx)
+      if (sidx < S) acc += part[sidx][v];
+    o[v] = cvt_out<T>(acc);
+    if (bias) o[v] = __hadd(o[v], bias[n + v]);
+  }
+  if constexpr (V == 4) {
+    *reinterpret_cast<uint2*>(y + idx) = *reinterpret_cast<const uint2*>(o);
+  } else {
+    y[idx] = o[0];
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -611,6 +636,12 @@ static int persistent_ctas() {
   return cta_cap > 0 ? cta_cap : sm_count();
 }
 
+// HQQ_B200_GEMM_KSPLIT=<n> (test / measurement hook): the largest number of k-slices the schedule may use (1 = never split)
+static int ksplit_cap() {
+  HQQ_ENV_KNOB(cap, ([] { const char* e = getenv("HQQ_B200_GEMM_KSPLIT"); return e ? atoi(e) : 0; })());
+  return cap > 0 ? (cap > 8 ? 8 : cap) : 8;
+}
+
 // see `Sched`: few tiles -> k-slices; else full tiles first, the last partial round as half tiles when that shortens it
 Sched make_sched(int64_t M, int64_t K, int64_t row_tiles, int P, bool allow_splitk) {
   Sched s;
@@ -621,7 +652,7 @@ Sched make_sched(int64_t M, int64_t K, int64_t row_tiles, int P, bool allow_spli
   const int64_t quads = K / 256;
   if (allow_splitk && full * 2 <= P && quads >= 2) {
     int64_t S = P / full;
-    if (S > 8) S = 8;
+    if (S > ksplit_cap()) S = ksplit_cap();
     if (S > quads) S = quads;
     S = cdiv(quads, cdiv(quads, S));  // every slice gets cdiv(quads, S) quads: drop the slices that would stay empty
     if (S >= 2) {
@@ -679,8 +710,12 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   if (a.sched.ksplit > 1) {
     const long long total = (long long)a.M * a.N;
-    splitk_reduce_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M, a.N,
-                                                                         a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
+    if (a.step % 4 == 0 && PR % 4 == 0 && aligned(a.y, 8))
+      splitk_reduce_kernel<T, 4><<<(unsigned)cdiv(total / 4, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M,
+                                                                                  a.N, a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
+    else
+      splitk_reduce_kernel<T, 1><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M, a.N,
+                                                                              a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
     HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/splitk-reduce");
   }
   return HQQ_OK;
