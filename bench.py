@@ -652,7 +652,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    pin_openmp_env()
+    # The CPU legs pin their OpenMP team (reproducible reference arm).  Never in a multi-rank GPU run: with OMP_PLACES set, libgomp
+    # binds every process's initial thread to the FIRST place, i.e. all ranks' host threads to core 0, and a loop with one host sync
+    # per step (e2e) then time-slices the ranks on one core -- measured: e2e 89 tok/s at N = 4 against 774 in the device loop.
+    if args.impl == "reference" or (world == 1 and args.gpus <= 1):
+        pin_openmp_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

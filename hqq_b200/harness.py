@@ -15,6 +15,7 @@ all-reduce of the [1, hidden] activation, the only exchange step on the path (SU
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -213,7 +214,8 @@ class DecodeModel:
         if self.tp == 1:
             check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), self.vocab_shard, ptr(self.next_tok), code, st))
             return
-        if self.fused == 5 and self.tp_mode == "p2p":  # the keys meet in peer-mapped memory inside the argmax launch
+        if self.fused == 5 and self.tp_mode == "p2p" and os.environ.get("HQQ_B200_HEAD_EXCHANGE", "p2p") != "nccl":  # (env: diagnosis only)
+            # the keys meet in peer-mapped memory inside the argmax launch
             check(lib.hqq_b200_glue_argmax_tp(ptr(b["logits"]), self.vocab_shard, self.rank * self.vocab_shard, self._tp_keys, self.tp, self.rank,
                                               self._xstep.data_ptr(), ptr(self.next_tok), code, st))
             return

@@ -4,6 +4,7 @@ emit path are assembled by the real code.  (The numbers are fake; this guards th
 logic: steps of 1/32 token, pinned team, stability verdict."""
 import argparse
 import json
+import os
 import types
 
 import pytest
@@ -141,3 +142,23 @@ def test_host_topology_and_the_reference_step(monkeypatch):
     assert r.n == 27 and info["steps_timed"] == 25 and v > 0 and len(info["tokens_per_s_min_median_max"]) == 3
     lo, med, hi = info["tokens_per_s_min_median_max"]
     assert lo <= med <= hi and isinstance(info["stable"], bool) and "1/32" in info["sample"]
+
+
+def test_openmp_pinning_stays_out_of_multi_rank_gpu_runs(monkeypatch):
+    """OMP_PLACES / OMP_PROC_BIND belong to the CPU legs: in a torchrun GPU run they would bind every rank's host thread to core 0
+    (libgomp binds the initial thread to the first place) and the per-step host sync of the e2e loop would time-slice the ranks."""
+    import sys
+    seen = {}
+    monkeypatch.setenv("OMP_PLACES", "x")      # so that monkeypatch restores both variables to their state before this test
+    monkeypatch.setenv("OMP_PROC_BIND", "x")
+    monkeypatch.setattr(bench, "run_gpu", lambda args, rank, world, lr: seen.update(gpu=(world, os.environ.get("OMP_PLACES"))))
+    monkeypatch.setattr(bench, "run_reference", lambda args, rank, world: seen.update(ref=(world, os.environ.get("OMP_PLACES"))))
+    for env_world, argv, key, want in (("2", ["bench.py", "--gpus", "2"], "gpu", None), ("1", ["bench.py"], "gpu", "cores"),
+                                       ("2", ["bench.py", "--impl", "reference", "--gpus", "2"], "ref", "cores")):
+        monkeypatch.delenv("OMP_PLACES", raising=False)
+        monkeypatch.delenv("OMP_PROC_BIND", raising=False)
+        monkeypatch.setenv("WORLD_SIZE", env_world)
+        monkeypatch.setenv("RANK", "0")
+        monkeypatch.setattr(sys, "argv", argv)
+        bench.main()
+        assert seen[key] == (int(env_world), want), (argv, seen)
