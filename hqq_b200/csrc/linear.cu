@@ -28,16 +28,20 @@ static bool dequant_ok(int64_t N, int64_t K, int gs, int nbits, int axis) {
 
 static size_t dense_ws_bytes(int64_t N, int64_t K, int dtype) { return (size_t)((N * K * (int64_t)dtype_size(dtype) + 255) & ~(int64_t)255); }
 
-// HQQ_B200_SMALL_M_MAX=<m> (measurement hook): the largest M the single-matrix entry point hands to the small-M kernel when the
-// tcgen05 route would take the shape too (default 32, the small kernel's own limit)
-static int small_m_max() {
+// Where the single-matrix entry point hands over from the small-M kernel (mma.sync, streams x per tile) to the tcgen05 kernel when
+// both take the shape.  Measured on the B200 (round 2, tools/prof_route_boundary.py, profiles/r2_route_boundary.log, CUDA-graph
+// timed, 4-bit gs 64): up to M = 16 the small kernel wins everywhere (14336x4096: 22 vs 29 us); at M = 17..32 it still wins or
+// ties on matrices up to 4096x4096 (11-12.5 vs 12.5 us) and loses on larger ones (14336x4096: 34-38 vs 28.5 us, 4096x14336: 33-35
+// vs 26, 28672x4096: 63-72 vs 51).  HQQ_B200_SMALL_M_MAX=<m> (measurement hook) replaces the rule by "small kernel up to M = m".
+static bool prefer_small(int64_t M, int64_t N, int64_t K) {
   HQQ_ENV_KNOB(m, ([] { const char* e = getenv("HQQ_B200_SMALL_M_MAX"); return e ? atoi(e) : 0; })());
-  return m > 0 ? m : 32;
+  if (m > 0) return M <= m;
+  return M <= 16 || N * K < (int64_t(1) << 25);
 }
 
 extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {
   const bool small = small_route_ok(M, N, K, group_size, nbits, axis, dtype);
-  if (small && (M <= small_m_max() || !gemm_route_ok(M, N, K, group_size, nbits, axis, dtype))) return 1;
+  if (small && (prefer_small(M, N, K) || !gemm_route_ok(M, N, K, group_size, nbits, axis, dtype))) return 1;
   if (gemm_route_ok(M, N, K, group_size, nbits, axis, dtype)) return 2;
   if (dequant_ok(N, K, group_size, nbits, axis) && dense_route_ok(M, N, K, dtype)) return 3;  // dequantize kernel -> dense tcgen05 GEMM
   return 0;

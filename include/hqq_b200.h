@@ -131,7 +131,8 @@ int hqq_b200_quantize_shard_finish(const void* W, int src_dtype, int64_t N, int6
  * i.e. y = x @ dequantize(W_q).T + bias, as ONE fused unpack->dequant->MMA kernel.
  *   hqq/core/quantize.py:880-898 ; semantic template hqq/kernels/hqq_aten_torch.cpp:79-107
  *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
- *   Routes (hqq_b200_linear_fwd_route): 1 = small-M weight-streaming kernel (M <= 32), 2 = fused tcgen05 GEMM -- both axis 1,
+ *   Routes (hqq_b200_linear_fwd_route): 1 = small-M weight-streaming kernel (M <= 16; M <= 32 on matrices below 2^25 weights),
+ *   2 = fused tcgen05 GEMM -- both axis 1,
  *   nbits 8/4/2/1, group_size 64/128, K % 256 == 0 -- and 3 = everything else hqq_b200_dequantize accepts (3-bit, axis 0, other
  *   group sizes, ragged K): the dequantize kernel writes W_r into `workspace`, the dense tcgen05 GEMM multiplies.  Returns
  *   HQQ_E_UNSUPPORTED where none applies (fp32 compute).

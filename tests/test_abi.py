@@ -57,7 +57,11 @@ def test_forward_routing_table(lib):
     from hqq_b200._lib import HQQ_BF16, HQQ_F16, HQQ_F32
     r = lib.hqq_b200_linear_fwd_route
     assert r(1, 4096, 4096, 64, 4, 1, HQQ_F16) == 1      # decode: weight-streaming kernel
-    assert r(32, 14336, 4096, 64, 4, 1, HQQ_BF16) == 1
+    assert r(16, 14336, 4096, 64, 4, 1, HQQ_BF16) == 1   # up to 16 tokens the weight-streaming kernel wins on every matrix
+    assert r(32, 4096, 4096, 64, 4, 1, HQQ_BF16) == 1    # 17..32 tokens: still on matrices up to 4096 x 4096 ...
+    assert r(32, 14336, 4096, 64, 4, 1, HQQ_BF16) == 2   # ... larger ones go to the tcgen05 kernel (measured boundary, linear.cu)
+    assert r(17, 4096, 14336, 64, 4, 1, HQQ_F16) == 2
+    assert r(32, 14336, 4096, 64, 4, 1, HQQ_F32) == 0
     assert r(1, 4096, 4096, 64, 4, 0, HQQ_F16) == 3      # axis 0: dequantize kernel + dense tcgen05 GEMM
     assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0      # float32 compute: no tensor-core route
     assert r(1, 4096, 4096, 64, 3, 1, HQQ_F16) == 3      # 3-bit (ten fields per int32, slabs cut rows): route 3

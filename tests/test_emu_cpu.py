@@ -356,8 +356,12 @@ def test_emulated_forward_random_shapes(emu, oracle):
         route = emu.hqq_b200_linear_fwd_route(i64(M), i64(N), i64(K), gs, nbits, 1, F16)
         assert route in (1, 2)
         routes.add(route)
+        emu.hqq_b200_linear_fwd_workspace_bytes.restype = ctypes.c_size_t
+        nws = int(emu.hqq_b200_linear_fwd_workspace_bytes(i64(M), i64(N), i64(K), gs, nbits, 1, F16))  # > 0: few tiles, split-K partials
+        ws = R.aligned((max(nws, 1),), np.uint8)
+        ws[:] = 0xA5  # contents on entry are irrelevant
         rc = emu.hqq_b200_linear_fwd(R.P(xd), R.P(L["Wq"]), R.P(L["scale"]), R.P(L["zero"]), R.P(L["bias"]), R.P(y), i64(M), i64(N), i64(K), gs, nbits, 1,
-                                     F16, None, ctypes.c_size_t(0), None)
+                                     F16, R.P(ws) if nws else None, ctypes.c_size_t(nws), None)
         assert rc == 0, emu.hqq_b200_last_error()
         ref = oracle.linear_forward(x.astype(np.float32), L["Wq_host"], L["meta"], None if not wb else L["bias_host"].astype(np.float32), "float16")
         assert rel(y, ref) <= 2e-3, (nbits, gs, N, K, M, wb, route)
