@@ -497,8 +497,14 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1 and B == 1 and not args.no_token_check:
         agree, token_check = tokens_agree(model, torch)
         if not agree:
-            raise RuntimeError("bench.py: the fused NVLink exchange and the NCCL all-reduce decode different tokens -- refusing to time a "
-                               f"wrong model: {json.dumps(token_check)}")
+            # never time a model whose exchange is in doubt: NCCL all-reduces between the kernels are the correctness reference
+            if rank == 0:
+                print(f"bench.py: the fused NVLink exchange and the NCCL all-reduce disagree beyond rounding ({json.dumps(token_check)}); "
+                      "timing the NCCL mode instead", file=sys.stderr, flush=True)
+            token_check["fell_back_to"] = "nccl"
+            model.tp_mode = "nccl"
+            model.graph = None
+            model.capture(warmup=3)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
