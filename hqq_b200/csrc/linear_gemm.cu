@@ -90,6 +90,15 @@ __host__ __device__ __forceinline__ Item decode_item(const Args& a, int j) {
   return it;
 }
 
+// programmatic dependent launch: the split-K second pass is a dependent of the GEMM grid
+#ifdef HQQ_EMU
+__device__ __forceinline__ void pdl_wait_primary() {}
+__device__ __forceinline__ void pdl_release_dependents() {}
+#else
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 #ifdef HQQ_EMU
 // CPU emulation (tests/emu): the same entry points, backed by a functional model of mbarrier / TMA / tcgen05 / TMEM
@@ -320,6 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // split-K: the second pass is a programmatic dependent -- let it become resident now (it blocks in griddepcontrol.wait until
+  // this grid has completed and flushed), so that its launch latency hides under our main loop
+  if (a.sched.ksplit > 1 && threadIdx.x == 0) pdl_release_dependents();
 
   if (warp == 0) {
     // ================= TMA producer: activation tiles =================
@@ -550,6 +562,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, T* __restrict__ y, const T* __restrict__ bias, int M, int N,
                                                             int step, int PR, int S, int n_row, int n_tok) {
   const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  pdl_wait_primary();  // launched as a programmatic dependent of the GEMM: resident early, reads only after that grid has completed
   if (idx >= (long long)M * N) return;
   const int m = (int)(idx / N), n = (int)(idx % N);
   const int f = n / step, prg = n % step;
@@ -710,12 +723,21 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   if (a.sched.ksplit > 1) {
     const long long total = (long long)a.M * a.N;
-    if (a.step % 4 == 0 && PR % 4 == 0 && aligned(a.y, 8))
-      splitk_reduce_kernel<T, 4><<<(unsigned)cdiv(total / 4, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M,
-                                                                                  a.N, a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
-    else
-      splitk_reduce_kernel<T, 1><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(a.ws, reinterpret_cast<T*>(a.y), reinterpret_cast<const T*>(a.bias), a.M, a.N,
-                                                                              a.step, PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
+    const bool vec = a.step % 4 == 0 && PR % 4 == 0 && aligned(a.y, 8);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cdiv(vec ? total / 4 : total, 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    T* yt = reinterpret_cast<T*>(a.y);
+    const T* bt = reinterpret_cast<const T*>(a.bias);
+    const float* wsc = a.ws;
+    if (vec) cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<T, 4>, wsc, yt, bt, a.M, a.N, a.step, (int)PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
+    else cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<T, 1>, wsc, yt, bt, a.M, a.N, a.step, (int)PR, a.sched.ksplit, a.sched.n_row, a.sched.n_tok);
     HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/splitk-reduce");
   }
   return HQQ_OK;
