@@ -118,3 +118,82 @@ def test_batched_decode_step_equals_independent_sequences(monkeypatch):
     assert len({tuple(r.tolist()) for r in together}) > 1  # the sequences really differ
     with pytest.raises(ValueError):
         harness.DecodeModel(shape, dtype=torch.float64, device="cpu", cache_len=16, fused=False, batch=0)
+
+
+class _TwoModeModel:
+    """Stand-in for harness.DecodeModel in bench.tokens_agree: a vocabulary of 16 sharded over 2 ranks; the "nccl" mode's logits are
+    the "p2p" mode's plus `pert` (what a different summation order does)."""
+
+    def __init__(self, rank, pert):
+        self.rank, self.vocab_shard, self.device = rank, 8, torch.device("cpu")
+        self.tp_mode, self.graph = "p2p", object()
+        self.tok = torch.zeros(1, dtype=torch.long)
+        self.next_tok = torch.zeros(1, dtype=torch.long)
+        self._bufs = {"logits": torch.zeros(1, 8, dtype=torch.float16)}
+        g = torch.Generator().manual_seed(3)
+        self.table = (torch.randn(64, 16, generator=g) * 2).half().float()
+        self.table[5, 3] = self.table[5, 11] = 9.0   # a dead heat between a token of rank 0's shard and one of rank 1's
+        self.table[5, 11] -= 2 ** -7                 # ... that "p2p" decides for token 3 by one fp16 step
+        self.pert, self.captures, self.i = pert, 0, 0
+
+    def capture(self, warmup=2):
+        self.graph = object()
+        self.captures += 1
+
+    def reset_state(self, token=1):
+        self.tok.fill_(token)
+        self.i = 0
+
+    def decode(self, feed_back=True):
+        row = 5 if self.i == 4 else (int(self.tok) * 7 + self.i) % 64
+        g = (self.table[row] + (self.pert if self.tp_mode == "nccl" else 0.0)).half().float()
+        self._bufs["logits"].copy_(g[self.rank * 8:(self.rank + 1) * 8].view(1, 8))
+        self.next_tok.fill_(int(torch.argmax(g)))
+        self.i += 1
+        if feed_back:
+            self.tok.copy_(self.next_tok)
+
+
+def _agree_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    torch.cuda.synchronize = lambda *a, **k: None  # the stand-in lives on the CPU
+    res = {}
+    zero = torch.zeros(16)
+    tie = torch.zeros(16); tie[11] = 2 ** -6       # last-bits difference: flips the dead heat at step 4, nothing else
+    wrong = torch.zeros(16); wrong[2] = 30.0       # a broken exchange: one rank's contribution is off by a lot
+    for name, pert in (("same", zero), ("tie", tie), ("wrong", wrong)):
+        m = _TwoModeModel(rank, pert)
+        agree, detail = bench.tokens_agree(m, torch, n_tokens=8)
+        res[name] = (agree, detail, m.tp_mode, m.captures)
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_p2p_vs_nccl_check_accepts_rounding_ties_and_nothing_else():
+    """bench.tokens_agree on two gloo ranks with a stand-in model: identical modes agree; a pick that differs because two logits of
+    different vocabulary shards are one fp16 step apart is accepted and reported; a gross logit difference is not.  The model is
+    left in the mode it came with."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_agree_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    agree, d, mode, captures = res["same"]
+    assert agree and d["identical"] and d["max_logit_diff"] == 0.0 and mode == "p2p" and captures == 2 and "differing_picks" not in d
+    agree, d, mode, _ = res["tie"]
+    assert agree and not d["identical"] and mode == "p2p"
+    assert [p["step"] for p in d["differing_picks"]] == [4] and d["differing_picks"][0]["near_tie"]
+    assert 0 < d["differing_picks"][0]["margin"] <= 2 * d["differing_picks"][0]["max_logit_diff"] <= 2 ** -5
+    agree, d, mode, _ = res["wrong"]
+    assert not agree and d["max_logit_diff"] >= 29.0 and mode == "p2p"
