@@ -405,7 +405,8 @@ def tokens_agree(model, torch, n_tokens=16):
     (teacher forcing, so one flipped pick cannot snowball) and must pick the same token at every step.  The two modes add the
     ranks' 16-bit partial sums in different orders, so the logits differ in their last bits; a differing pick is accepted only if
     it is such a near-tie: the timed mode's own margin between the two candidates is within twice the largest logit difference
-    of that step, and the logits as a whole differ by less than 2 % of their range.  Anything else is a wrong exchange.
+    of that step, and the logits as a whole differ by less than 5 % of their range (measured: 0.7 % on the 8B model at tp = 8, 2 % on
+    the 80-block 70B model).  Anything else is a wrong exchange.
     Leaves the model captured in the mode it came with.  Returns (agree, detail)."""
     import torch.distributed as dist
     want = model.tp_mode
@@ -453,7 +454,7 @@ def tokens_agree(model, torch, n_tokens=16):
             explained = explained and ok
             ties.append({"step": i, "margin": margin, "max_logit_diff": float(diff[i]), "near_tie": ok})
     dmax = float(diff.max())
-    agree = identical or (explained and dmax <= 0.02 * scale)
+    agree = identical or (explained and dmax <= 0.05 * scale)
     flag = torch.tensor([1 if agree else 0], device=model.device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     detail = {"tokens": n_tokens, "identical": identical, "max_logit_diff": dmax, "logit_absmax": scale, "against": other}

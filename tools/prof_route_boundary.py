@@ -38,7 +38,10 @@ def graph_us(fn):
     return e0.elapsed_time(e1) / (5 * REP) * 1e3
 
 
-for N, K in ((1024, 4096), (4096, 4096), (14336, 4096), (4096, 14336), (28672, 4096)):
+SHAPES = ((1024, 4096), (4096, 4096), (14336, 4096), (4096, 14336), (28672, 4096))
+if len(sys.argv) > 1 and sys.argv[1] == "70b-tp8":  # per-rank matrices of the Llama-3-70B shape at tp = 8 (bs = 32 leg of configs[4])
+    SHAPES = ((1280, 8192), (8192, 1024), (3584, 8192), (7168, 8192), (8192, 3584))
+for N, K in SHAPES:
     layer = HQQLinear.from_weights((torch.randn(N, K, device="cuda") * 0.02).half(), None, BaseQuantizeConfig(nbits=4, group_size=64, axis=1),
                                    compute_dtype=torch.float16, device="cuda")
     m = layer.meta
