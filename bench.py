@@ -652,8 +652,8 @@ def main():
     ap.add_argument("--no-token-check", action="store_true", help="N>1: skip the p2p-vs-nccl token agreement check before timing")
     ap.add_argument("--extras-deadline", type=float, default=240.0, help="seconds the objects added after the measurement (GEMM sweep, "
                     "quantizer, CPU baselines) may take before the line is printed without the unfinished ones")
-    ap.add_argument("--batch", type=int, default=1, help="sequences decoded in lock-step (BASELINE configs[4]: 32); > 1 uses the fused small-M "
-                    "kernel between framework glue ops and NCCL all-reduce")
+    ap.add_argument("--batch", type=int, default=1, help="sequences decoded in lock-step (BASELINE configs[4]: 32); > 1 runs the small-M / tcgen05 "
+                    "kernels between the batched glue kernels, NCCL all-reduce for the tensor-parallel partials")
     ap.add_argument("--model", default="8b", choices=["8b", "70b"], help="70b = BASELINE configs[4] (use with --gpus 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

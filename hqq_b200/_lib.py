@@ -51,7 +51,10 @@ SIGNATURES = {
     "hqq_b200_decode_linear_fwd_desc": (c_int, [c_void_p, c_void_p]),
     "hqq_b200_glue_add_rmsnorm_tp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
+    "hqq_b200_glue_add_rmsnorm_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "hqq_b200_glue_silu_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hqq_b200_glue_rope_attn_decode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hqq_b200_glue_rope_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hqq_b200_glue_argmax": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),

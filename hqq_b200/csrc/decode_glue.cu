@@ -27,11 +27,17 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;
 }
 
-// h += delta (optional); y = rmsnorm(h) * w         (one CTA; H <= 8 * blockDim * 4)
+// h += delta (optional); y = rmsnorm(h) * w         (one CTA per row of [rows, H]; H <= 8 * blockDim)
 template <typename T>
 __global__ void __launch_bounds__(1024) add_rmsnorm_kernel(T* __restrict__ h, const T* __restrict__ delta, const T* __restrict__ w,
                                                            T* __restrict__ y, int H, float eps) {
   __shared__ float red[32];
+  {
+    const long long row = (long long)blockIdx.x * H;  // batched decode: one sequence per CTA
+    h += row;
+    y += row;
+    if (delta) delta += row;
+  }
   pdl_launch_g();
   pdl_wait_g();
   float v[8];
@@ -120,6 +126,12 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
   float* ps = sm + 2 * hd;
   float* red = sm + max(2 * hd + L, NW * hd);
   const int h = blockIdx.x, kvh = h / (n_q / n_kv), d = threadIdx.x;
+  {
+    const long long b = blockIdx.y;  // batched decode: sequence b of the lock-step batch (all at the same position)
+    q_in += b * n_q * hd; out += b * n_q * hd;
+    k_in += b * n_kv * hd; v_in += b * n_kv * hd;
+    k_cache += b * n_kv * L * hd; v_cache += b * n_kv * L * hd;
+  }
   const int pos = (int)pos_p[0];
   pdl_launch_g();
   {
@@ -340,14 +352,20 @@ static int launch_pdl(const char* name, K kernel, dim3 grid, dim3 block, size_t 
 
 using namespace hqq;
 
-extern "C" int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y, int H, float eps, int dtype, void* stream) {
-  HQQ_REQUIRE(h && weight && y && H > 0 && H <= 8 * 1024, HQQ_E_INVALID, "hqq_b200_glue_add_rmsnorm: bad arguments (H=%d)", H);
+extern "C" int hqq_b200_glue_add_rmsnorm_rows(void* h, const void* delta, const void* weight, void* y, int rows, int H, float eps, int dtype,
+                                              void* stream) {
+  HQQ_REQUIRE(h && weight && y && H > 0 && H <= 8 * 1024 && rows > 0 && rows <= 65535, HQQ_E_INVALID,
+              "hqq_b200_glue_add_rmsnorm: bad arguments (rows=%d H=%d)", rows, H);
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = H > 2048 ? 1024 : 256;  // at most 8 elements per thread (the kernels keep them in registers)
-  if (dtype == HQQ_F16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__half>, dim3(1), dim3(threads), 0, st, (__half*)h, (const __half*)delta, (const __half*)weight, (__half*)y, H, eps);
-  if (dtype == HQQ_BF16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__nv_bfloat16>, dim3(1), dim3(threads), 0, st, (__nv_bfloat16*)h, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, (__nv_bfloat16*)y, H, eps);
+  if (dtype == HQQ_F16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__half>, dim3(rows), dim3(threads), 0, st, (__half*)h, (const __half*)delta, (const __half*)weight, (__half*)y, H, eps);
+  if (dtype == HQQ_BF16) return launch_pdl("add_rmsnorm", add_rmsnorm_kernel<__nv_bfloat16>, dim3(rows), dim3(threads), 0, st, (__nv_bfloat16*)h, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, (__nv_bfloat16*)y, H, eps);
   set_error("hqq_b200_glue_add_rmsnorm: dtype must be f16/bf16");
   return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y, int H, float eps, int dtype, void* stream) {
+  return hqq_b200_glue_add_rmsnorm_rows(h, delta, weight, y, 1, H, eps, dtype, stream);
 }
 
 extern "C" int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, int x_index, int x_per_step, int tp, const void* weight,
@@ -372,10 +390,11 @@ extern "C" int hqq_b200_glue_silu_mul(const void* gate, const void* up, void* y,
   return HQQ_E_INVALID;
 }
 
-extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v, const void* cos_table, const void* sin_table,
+extern "C" int hqq_b200_glue_rope_attn_decode_batch(const void* q, const void* k, const void* v, const void* cos_table, const void* sin_table,
                                               void* k_cache, void* v_cache, const int64_t* pos, void* out, int n_q_heads, int n_kv_heads,
-                                              int cache_len, int head_dim, int dtype, void* stream) {
+                                              int cache_len, int head_dim, int batch, int dtype, void* stream) {
   HQQ_REQUIRE(q && k && v && cos_table && sin_table && k_cache && v_cache && pos && out, HQQ_E_INVALID, "hqq_b200_glue_rope_attn_decode: null pointer");
+  HQQ_REQUIRE(batch > 0 && batch <= 65535, HQQ_E_INVALID, "hqq_b200_glue_rope_attn_decode: batch %d", batch);
   HQQ_REQUIRE(head_dim == 128 && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && cache_len > 0 && cache_len <= 8192, HQQ_E_UNSUPPORTED,
               "hqq_b200_glue_rope_attn_decode: needs head_dim 128, cache_len <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
@@ -383,16 +402,23 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
   const size_t smem = (size_t)(body + 32) * sizeof(float);
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (dtype == HQQ_F16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads), dim3(kAttnThreads), smem, st, (const __half*)q, (const __half*)k,
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads, batch), dim3(kAttnThreads), smem, st, (const __half*)q, (const __half*)k,
                       (const __half*)v, (const __half*)cos_table, (const __half*)sin_table, (__half*)k_cache, (__half*)v_cache, (const long long*)pos,
                       (__half*)out, n_q_heads, n_kv_heads, cache_len, head_dim, scale);
   if (dtype == HQQ_BF16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads), dim3(kAttnThreads), smem, st, (const __nv_bfloat16*)q,
+    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads, batch), dim3(kAttnThreads), smem, st, (const __nv_bfloat16*)q,
                       (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
                       (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, (const long long*)pos, (__nv_bfloat16*)out, n_q_heads, n_kv_heads, cache_len,
                       head_dim, scale);
   set_error("hqq_b200_glue_rope_attn_decode: dtype must be f16/bf16");
   return HQQ_E_INVALID;
+}
+
+extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v, const void* cos_table, const void* sin_table,
+                                              void* k_cache, void* v_cache, const int64_t* pos, void* out, int n_q_heads, int n_kv_heads,
+                                              int cache_len, int head_dim, int dtype, void* stream) {
+  return hqq_b200_glue_rope_attn_decode_batch(q, k, v, cos_table, sin_table, k_cache, v_cache, pos, out, n_q_heads, n_kv_heads, cache_len, head_dim, 1,
+                                              dtype, stream);
 }
 
 extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {

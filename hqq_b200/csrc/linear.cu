@@ -31,12 +31,13 @@ static size_t dense_ws_bytes(int64_t N, int64_t K, int dtype) { return (size_t)(
 // Where the single-matrix entry point hands over from the small-M kernel (mma.sync, streams x per tile) to the tcgen05 kernel when
 // both take the shape.  Measured on the B200 (round 2, tools/prof_route_boundary.py, profiles/r2_route_boundary.log, CUDA-graph
 // timed, 4-bit gs 64): up to M = 16 the small kernel wins everywhere (14336x4096: 22 vs 29 us); at M = 17..32 it still wins or
-// ties on matrices up to 4096x4096 (11-12.5 vs 12.5 us) and loses on larger ones (14336x4096: 34-38 vs 28.5 us, 4096x14336: 33-35
-// vs 26, 28672x4096: 63-72 vs 51).  HQQ_B200_SMALL_M_MAX=<m> (measurement hook) replaces the rule by "small kernel up to M = m".
+// ties on matrices up to 4096x4096 = 2^24 weights (11-12.5 vs 12.5 us; 1280x8192: 11.5 vs 11.9; 8192x1024: 11.8 vs 10.5) and loses
+// on larger ones (3584x8192: 20-21 vs 17.4 us, 8192x3584: 20-22.5 vs 17-18, 14336x4096: 34-38 vs 28.5, 4096x14336: 33-35 vs 26,
+// 28672x4096: 63-72 vs 51).  HQQ_B200_SMALL_M_MAX=<m> (measurement hook) replaces the rule by "small kernel up to M = m".
 static bool prefer_small(int64_t M, int64_t N, int64_t K) {
   HQQ_ENV_KNOB(m, ([] { const char* e = getenv("HQQ_B200_SMALL_M_MAX"); return e ? atoi(e) : 0; })());
   if (m > 0) return M <= m;
-  return M <= 16 || N * K < (int64_t(1) << 25);
+  return M <= 16 || N * K <= (int64_t(1) << 24);
 }
 
 extern "C" int hqq_b200_linear_fwd_route(int64_t M, int64_t N, int64_t K, int group_size, int nbits, int axis, int dtype) {

@@ -63,13 +63,13 @@ class DecodeModel:
                  n_layers: int | None = None, fused=5, tp_mode: str | None = None, batch: int = 1, shard_from_full: bool = False):
         self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
         # batch > 1 (BASELINE configs[4], bs = 32): `batch` sequences decode in lock-step at the same position; the linears then
-        # run the fused small-M kernel (M = batch <= 32) between framework glue ops -- the one-token glue kernels and the fused
-        # NVLink exchange are M = 1 only, so tensor-parallel partials are summed by NCCL
+        # run the small-M kernel (M = batch <= 32; the tcgen05 kernel from 17 sequences on large matrices) between the batched glue
+        # kernels -- the one-token kernels and their NVLink exchange are M = 1 only, so tensor-parallel partials are summed by NCCL
         self.batch = int(batch)
         if self.batch < 1:
             raise ValueError("batch must be >= 1")
-        if self.batch > 1:
-            fused = False
+        if self.batch > 1 and fused:
+            fused = True  # the 8-launch path with the batched glue kernels; the one-token kernels (fused=5) and their exchange are M = 1 only
         self.fused = fused
         import os
         # "p2p": the row-parallel partials meet through tagged words over NVLink peer memory inside the kernels (default);
@@ -211,6 +211,17 @@ class DecodeModel:
         from ._lib import check, ptr
         b = self._bufs
         torch.matmul(x, self.lm_head.t(), out=b["logits"])
+        if self.batch > 1:  # a row per sequence: framework ops (with tp > 1: the global maximum, then the lowest index that attains it)
+            if self.tp == 1:
+                self.next_tok.copy_(torch.argmax(b["logits"], dim=-1))
+                return
+            val, idx = torch.max(b["logits"].float(), dim=-1)
+            gmax = val.clone()
+            torch.distributed.all_reduce(gmax, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            cand = torch.where(val == gmax, idx + self.rank * self.vocab_shard, torch.full_like(idx, self.shape.vocab))
+            torch.distributed.all_reduce(cand, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+            self.next_tok.copy_(cand)
+            return
         if self.tp == 1:
             check(lib.hqq_b200_glue_argmax(ptr(b["logits"]), self.vocab_shard, ptr(self.next_tok), code, st))
             return
@@ -224,6 +235,18 @@ class DecodeModel:
         torch.bitwise_and(b["key"], 0xFFFFFFFF, out=b["key"])
         self.next_tok.copy_(0xFFFFFFFF - b["key"])
 
+    def _lin(self, x, layers, outs):
+        """Matrices that share the activation x [B, K]: ONE launch of the small-M kernel when the router gives it all of them,
+        else one routed call per matrix (from 17 rows on, matrices above 2^24 weights take the tcgen05 kernel, csrc/linear.cu)."""
+        if ops.linear_fwd_multi(x, layers, outs) is not None:
+            return
+        for l, y in zip(layers, outs):
+            m = l.meta
+            store_bits = {"8bit_u8": 8, "4bit_u8": 4, "3bit_32": 3, "2bit_u8": 2, "1bit_u8": 1}[m["packing"]]
+            if ops.linear_fwd(x, l.W_q, m["scale"], m["zero"], l.bias, int(m["shape"][0]), int(m["shape"][1]), m["group_size"], store_bits, m["axis"],
+                              out=y) is None:
+                raise RuntimeError("hqq_b200: no fused forward for this layer; use fused=False")
+
     def step_fused(self):
         """Same token step with the package's glue kernels (8 launches per block): add+RMSNorm, fused q/k/v, RoPE+cache+
         attention, o, add+RMSNorm, fused gate/up, SiLU*mul, down.  With tensor parallelism every rank runs the same launches
@@ -235,24 +258,26 @@ class DecodeModel:
         hd, hq, hkv = s.head_dim, s.n_heads // self.tp, s.n_kv_heads // self.tp
         inter = s.inter // self.tp
         b = self._bufs
-        torch.index_select(self.embed, 0, self.tok, out=b["h"])
+        B = self.batch
+        torch.index_select(self.embed, 0, self.tok, out=b["h"])  # [B, hidden]
         delta = None
+        norm = lambda d, w: check(lib.hqq_b200_glue_add_rmsnorm_rows(ptr(b["h"]), ptr(d), ptr(w), ptr(b["x"]), B, s.hidden, s.rms_eps, code, st))
         for blk in self.blocks:
-            check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(blk["norm1"]), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
-            ops.linear_fwd_multi(b["x"], (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]])
-            check(lib.hqq_b200_glue_rope_attn_decode(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
-                                                     ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, code, st))
-            ops.linear_fwd_multi(b["a"], (blk["o"],), [b["o"]])
+            norm(delta, blk["norm1"])
+            self._lin(b["x"], (blk["q"], blk["k"], blk["v"]), [b["q"], b["k"], b["v"]])
+            check(lib.hqq_b200_glue_rope_attn_decode_batch(ptr(b["q"]), ptr(b["k"]), ptr(b["v"]), ptr(self.cos), ptr(self.sin), ptr(blk["k_cache"]),
+                                                           ptr(blk["v_cache"]), ptr(self.pos), ptr(b["a"]), hq, hkv, self.cache_len, hd, B, code, st))
+            self._lin(b["a"], (blk["o"],), [b["o"]])
             if self.tp > 1:
                 torch.distributed.all_reduce(b["o"], group=self.pg)
-            check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(b["o"]), ptr(blk["norm2"]), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
-            ops.linear_fwd_multi(b["x"], (blk["gate"], blk["up"]), [b["gate"], b["up"]])
-            check(lib.hqq_b200_glue_silu_mul(ptr(b["gate"]), ptr(b["up"]), ptr(b["act"]), inter, code, st))
-            ops.linear_fwd_multi(b["act"], (blk["down"],), [b["down"]])
+            norm(b["o"], blk["norm2"])
+            self._lin(b["x"], (blk["gate"], blk["up"]), [b["gate"], b["up"]])
+            check(lib.hqq_b200_glue_silu_mul(ptr(b["gate"]), ptr(b["up"]), ptr(b["act"]), B * inter, code, st))
+            self._lin(b["act"], (blk["down"],), [b["down"]])
             if self.tp > 1:
                 torch.distributed.all_reduce(b["down"], group=self.pg)
             delta = b["down"]
-        check(lib.hqq_b200_glue_add_rmsnorm(ptr(b["h"]), ptr(delta), ptr(self.final_norm), ptr(b["x"]), s.hidden, s.rms_eps, code, st))
+        norm(delta, self.final_norm)
         self._head(lib, b["x"], code, st)
         self.pos.add_(1).remainder_(self.cache_len)
 
@@ -347,7 +372,7 @@ class DecodeModel:
 
     def _alloc_bufs(self):
         s, dev, dt = self.shape, self.device, self.dtype
-        z = lambda n: torch.zeros(1, n, device=dev, dtype=dt)
+        z = lambda n: torch.zeros(self.batch, n, device=dev, dtype=dt)
         tp = self.tp
         self._bufs = {"h": z(s.hidden), "h2": z(s.hidden), "x": z(s.hidden), "q": z(s.n_heads // tp * s.head_dim), "k": z(s.n_kv_heads // tp * s.head_dim),
                       "v": z(s.n_kv_heads // tp * s.head_dim), "a": z(s.n_heads // tp * s.head_dim), "o": z(s.hidden),

@@ -131,7 +131,7 @@ int hqq_b200_quantize_shard_finish(const void* W, int src_dtype, int64_t N, int6
  * i.e. y = x @ dequantize(W_q).T + bias, as ONE fused unpack->dequant->MMA kernel.
  *   hqq/core/quantize.py:880-898 ; semantic template hqq/kernels/hqq_aten_torch.cpp:79-107
  *   x [M,K], y [M,N], bias [N] or NULL, scale/zero [N*K/gs], all of `dtype` (f16/bf16)
- *   Routes (hqq_b200_linear_fwd_route): 1 = small-M weight-streaming kernel (M <= 16; M <= 32 on matrices below 2^25 weights),
+ *   Routes (hqq_b200_linear_fwd_route): 1 = small-M weight-streaming kernel (M <= 16; M <= 32 on matrices of up to 2^24 weights),
  *   2 = fused tcgen05 GEMM -- both axis 1,
  *   nbits 8/4/2/1, group_size 64/128, K % 256 == 0 -- and 3 = everything else hqq_b200_dequantize accepts (3-bit, axis 0, other
  *   group sizes, ragged K): the dequantize kernel writes W_r into `workspace`, the dense tcgen05 GEMM multiplies.  Returns
@@ -216,6 +216,9 @@ int hqq_b200_glue_add_rmsnorm_tp(void* h, const void* red_data, int* step_ctr, i
 /* h += delta (delta may be NULL);  y = rmsnorm(h) * weight          (one token, H <= 8192) */
 int hqq_b200_glue_add_rmsnorm(void* h, const void* delta, const void* weight, void* y,
                               int H, float eps, int dtype, void* stream);
+/* the same on `rows` sequences decoding in lock-step: h, delta, y are [rows, H] row-major, one CTA per row */
+int hqq_b200_glue_add_rmsnorm_rows(void* h, const void* delta, const void* weight, void* y,
+                                   int rows, int H, float eps, int dtype, void* stream);
 /* y = silu(gate) * up */
 int hqq_b200_glue_silu_mul(const void* gate, const void* up, void* y, int n, int dtype, void* stream);
 /* RoPE(q,k at *pos) + KV-cache append + one-token GQA attention over cache[0..*pos];
@@ -227,6 +230,13 @@ int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, const void* v,
                                    void* k_cache, void* v_cache, const int64_t* pos, void* out,
                                    int n_q_heads, int n_kv_heads, int cache_len, int head_dim,
                                    int dtype, void* stream);
+/* the same for `batch` sequences at the SAME position *pos: q / out [batch, n_q_heads*head_dim], k / v [batch, n_kv_heads*head_dim],
+ * caches [batch, n_kv_heads, cache_len, head_dim]; grid = (n_q_heads, batch) */
+int hqq_b200_glue_rope_attn_decode_batch(const void* q, const void* k, const void* v,
+                                         const void* cos_table, const void* sin_table,
+                                         void* k_cache, void* v_cache, const int64_t* pos, void* out,
+                                         int n_q_heads, int n_kv_heads, int cache_len, int head_dim,
+                                         int batch, int dtype, void* stream);
 /* out[0] = argmax(logits[0..n)) (first index on ties) */
 int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream);
 /* Vocabulary-sharded lm_head (tensor parallel decode): out_key[0] = a signed 64-bit key {ordered(max) : 0xFFFFFFFF - (index_offset +

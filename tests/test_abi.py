@@ -61,6 +61,7 @@ def test_forward_routing_table(lib):
     assert r(32, 4096, 4096, 64, 4, 1, HQQ_BF16) == 1    # 17..32 tokens: still on matrices up to 4096 x 4096 ...
     assert r(32, 14336, 4096, 64, 4, 1, HQQ_BF16) == 2   # ... larger ones go to the tcgen05 kernel (measured boundary, linear.cu)
     assert r(17, 4096, 14336, 64, 4, 1, HQQ_F16) == 2
+    assert r(32, 3584, 8192, 64, 4, 1, HQQ_F16) == 2 and r(32, 1280, 8192, 64, 4, 1, HQQ_F16) == 1   # the boundary: 2^24 weights
     assert r(32, 14336, 4096, 64, 4, 1, HQQ_F32) == 0
     assert r(1, 4096, 4096, 64, 4, 0, HQQ_F16) == 3      # axis 0: dequantize kernel + dense tcgen05 GEMM
     assert r(1, 4096, 4096, 64, 4, 1, HQQ_F32) == 0      # float32 compute: no tensor-core route

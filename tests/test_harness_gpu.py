@@ -195,6 +195,64 @@ def test_decode_graph_fused_equals_framework_ops():
     assert t8[:4] == tref[:4]
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_batched_glue_kernels_equal_the_one_sequence_kernels_row_by_row(dt):
+    """hqq_b200_glue_add_rmsnorm_rows / hqq_b200_glue_rope_attn_decode_batch (lock-step batch, one CTA per sequence / per head and
+    sequence) produce, row by row, exactly what the one-sequence entry points produce."""
+    lib = load()
+    st, code = stream_ptr(DEV), DTYPE_CODE[dt]
+    torch.manual_seed(11)
+    B, H = 5, 4096
+    h = torch.randn(B, H, device=DEV).to(dt); d = torch.randn(B, H, device=DEV).to(dt); w = torch.rand(H, device=DEV).to(dt)
+    for delta in (d, None):
+        hb, yb = h.clone(), torch.empty_like(h)
+        check(lib.hqq_b200_glue_add_rmsnorm_rows(ptr(hb), ptr(delta), ptr(w), ptr(yb), B, H, 1e-5, code, st))
+        for r in range(B):
+            h1, y1 = h[r:r + 1].clone(), torch.empty(1, H, device=DEV, dtype=dt)
+            check(lib.hqq_b200_glue_add_rmsnorm(ptr(h1), ptr(None if delta is None else delta[r:r + 1].contiguous()), ptr(w), ptr(y1), H, 1e-5, code, st))
+            assert torch.equal(hb[r:r + 1], h1) and torch.equal(yb[r:r + 1], y1), r
+    hq, hkv, hd, L = 8, 2, 128, 96
+    m = harness.DecodeModel(harness.LlamaShape(hidden=hq * hd, inter=1024, n_layers=0, n_heads=hq, n_kv_heads=hkv, vocab=256), dtype=dt, device=DEV,
+                            cache_len=L)
+    kc = torch.randn(B, hkv, L, hd, device=DEV).to(dt); vc = torch.randn(B, hkv, L, hd, device=DEV).to(dt)
+    for pos in (0, 5, 64, 95):
+        q = torch.randn(B, hq * hd, device=DEV).to(dt); k = torch.randn(B, hkv * hd, device=DEV).to(dt); v = torch.randn(B, hkv * hd, device=DEV).to(dt)
+        p = torch.tensor([pos], device=DEV)
+        kb, vb, ob = kc.clone(), vc.clone(), torch.empty(B, hq * hd, device=DEV, dtype=dt)
+        check(lib.hqq_b200_glue_rope_attn_decode_batch(ptr(q), ptr(k), ptr(v), ptr(m.cos), ptr(m.sin), ptr(kb), ptr(vb), ptr(p), ptr(ob), hq, hkv, L, hd, B,
+                                                       code, st))
+        for r in range(B):
+            k1, v1, o1 = kc[r].clone(), vc[r].clone(), torch.empty(1, hq * hd, device=DEV, dtype=dt)
+            check(lib.hqq_b200_glue_rope_attn_decode(ptr(q[r:r + 1].contiguous()), ptr(k[r:r + 1].contiguous()), ptr(v[r:r + 1].contiguous()), ptr(m.cos),
+                                                     ptr(m.sin), ptr(k1), ptr(v1), ptr(p), ptr(o1), hq, hkv, L, hd, code, st))
+            assert torch.equal(kb[r], k1) and torch.equal(vb[r], v1) and torch.equal(ob[r:r + 1], o1), (pos, r)
+
+
+@pytest.mark.parametrize("batch,shape", [(4, harness.LlamaShape(hidden=1024, inter=2048, n_layers=2, n_heads=8, n_kv_heads=2, vocab=2048)),
+                                         (32, harness.LlamaShape(hidden=4096, inter=14336, n_layers=1, n_heads=32, n_kv_heads=8, vocab=4096))])
+def test_batched_decode_graph_fused_equals_framework_ops(batch, shape):
+    """Lock-step batch: the captured step on the batched glue kernels (add+RMSNorm rows, RoPE+attention per sequence, SiLU*mul; the
+    linears through `_lin`: small-M kernel, or the tcgen05 kernel for 17+ sequences on matrices above 2^24 weights -- the second
+    case has such matrices) against the same step on framework ops, every sequence starting from its own token."""
+    toks = []
+    for f in (True, False):
+        m = harness.DecodeModel(shape, dtype=torch.float16, device=DEV, cache_len=32, fused=f, seed=3, batch=batch)
+        assert m.fused is f
+        m.capture()
+        m.reset_state(1)
+        m.tok.copy_(torch.arange(3, 3 + batch, device=DEV))
+        t = []
+        for _ in range(8):
+            m.decode()
+            t.append(m.next_tok.clone())
+        toks.append(torch.stack(t))  # [steps, batch]
+        del m
+    a, b = toks
+    assert torch.equal(a[:2], b[:2]), (a[:2], b[:2])                 # the first tokens of every sequence agree ...
+    assert (a == b).float().mean().item() >= 0.9, (a, b)             # ... later ones up to fp16 near-ties (different summation orders)
+    assert len(set(a[0].tolist())) > 1                               # the sequences are really different
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (the fused NVLink exchange is exercised by tools/tp_check.py under gpurun --gpus 2)")
 def test_tensor_parallel_peer_exchange_matches_nccl():
     """TP=2: the all-reduce fused into the row-parallel kernels over peer memory produces the same tokens as NCCL all-reduce."""
