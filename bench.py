@@ -287,19 +287,24 @@ def kernel_roofline(model, torch, peaks, reps=4):
         tot_ms += ms
     achieved = tot_bytes / tot_ms / 1e6
     # dram bytes per launch (average over the four launch groups) from the committed `ncu --set full` capture of the shipped kernel
+    # -- it was taken on the unsharded Llama-3-8B matrices: for any other launch shapes (tensor-parallel shards, the 70B model)
+    # there is no capture and `traffic` is null rather than a number that belongs to other launches
     traffic, traffic_src = None, None
     for name in ("r2_decode1_traffic.json", "r1_decode1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
-                traffic, traffic_src = json.load(fh)["traffic_bytes_per_launch_avg"], "profiles/" + name
+                cap = json.load(fh)
+            if abs(cap["algorithmic_bytes_per_launch_avg"] / (tot_bytes / len(groups)) - 1.0) < 0.01:
+                traffic, traffic_src = cap["traffic_bytes_per_launch_avg"], "profiles/" + name
             break
-        except (OSError, KeyError, ValueError):
+        except (OSError, KeyError, ValueError, ZeroDivisionError):
             continue
     return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": traffic, "algorithmic_bytes_per_launch": tot_bytes / len(groups),
             "kernel": "hqq::linear_decode1_kernel<half,4,64,...,MR=1> (scale/zero on the cp.async ring; 4 launches/block, 128/step)",
             "peak_source": peaks["source"], "per_launch_group": per, "linear_us_per_step": round(tot_ms * 1e3 * len(model.blocks), 1),
-            "note": f"event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: {traffic_src} (ncu dram bytes)"}
+            "note": "event-timed graph replay of back-to-back launches over all layers (cold weights); traffic: "
+                    + (f"{traffic_src} (ncu dram bytes, same launch shapes)" if traffic_src else "no ncu capture for these launch shapes")}
 
 
 def quantizer_roofline(torch, peaks, dev, reps=3):
