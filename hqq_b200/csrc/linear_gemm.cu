@@ -329,14 +329,19 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // split-K: the second pass is a programmatic dependent -- let it become resident now (it blocks in griddepcontrol.wait until
-  // this grid has completed and flushed), so that its launch latency hides under our main loop
-  if (a.sched.ksplit > 1 && threadIdx.x == 0) pdl_release_dependents();
+  // Programmatic dependent launch, both sides.  Our dependents (the split-K second pass; the next forward of a chain of layers) may
+  // become resident as our CTAs retire -- they block in griddepcontrol.wait until this grid has completed and flushed, so only
+  // their launch latency and prologue move under our tail.  As a dependent ourselves, the one thing we read that a PDL-aware
+  // predecessor may still be writing is the activation x (and, dense mode, W written by the dequantize kernel): the TMA producer
+  // waits before its first load, and nothing is written (y, split-K partials) before an accumulator fed by those loads is full.
+  // Packed weights, scale, zero and bias are never produced by a kernel that releases its dependents early.
+  if (threadIdx.x == 0) pdl_release_dependents();
 
   if (warp == 0) {
     // ================= TMA producer: activation tiles =================
     if (lane == 0) {
       uint32_t it = 0;  // k-blocks issued so far (ring position)
+      pdl_wait_primary();
       for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
         const Item im = decode_item(a, j);
         if (!im.valid) continue;
@@ -649,6 +654,12 @@ static int persistent_ctas() {
   return cta_cap > 0 ? cta_cap : sm_count();
 }
 
+// HQQ_B200_PDL=0 (test hook, shared with the small-M kernels): launch without the programmatic-dependency attribute
+static bool pdl_on() {
+  HQQ_ENV_KNOB(on, ([] { const char* e = getenv("HQQ_B200_PDL"); return (e && e[0] == '0') ? 0 : 1; })());
+  return on == 1;
+}
+
 // HQQ_B200_GEMM_KSPLIT=<n> (test / measurement hook): the largest number of k-slices the schedule may use (1 = never split)
 static int ksplit_cap() {
   HQQ_ENV_KNOB(cap, ([] { const char* e = getenv("HQQ_B200_GEMM_KSPLIT"); return e ? atoi(e) : 0; })());
@@ -719,7 +730,19 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
     HQQ_REQUIRE(e == cudaSuccess, HQQ_E_CUDA, "hqq_b200_linear_fwd: cannot reserve %d bytes of shared memory: %s", Smem::BYTES, cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  k<<<grid, kThreads, Smem::BYTES, st>>>(xmap256, xmap128, amap, a);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Smem::BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_on() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, xmap256, xmap128, amap, a);
+  }
   HQQ_LAUNCH_CHECK("hqq_b200_linear_fwd/tcgen05");
   if (a.sched.ksplit > 1) {
     const long long total = (long long)a.M * a.N;
@@ -732,7 +755,7 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_on() ? 1 : 0;
     T* yt = reinterpret_cast<T*>(a.y);
     const T* bt = reinterpret_cast<const T*>(a.bias);
     const float* wsc = a.ws;
