@@ -194,13 +194,11 @@ RUNNER = os.path.join(HERE, "emu", "run_small.py")
 _RUNS = {}
 
 
-def run_small(tmp_path_factory, variant=None):
-    key = variant or "default"
+def run_small(tmp_path_factory):
+    key = "default"
     if key not in _RUNS:
         out = str(tmp_path_factory.mktemp("emu_small") / f"{key}.npz")
         env = {k: v for k, v in os.environ.items() if not k.startswith("HQQ_B200_")}
-        if variant:
-            env["HQQ_B200_D1_VARIANT"] = str(variant)
         r = subprocess.run([sys.executable, RUNNER, out], env=env, capture_output=True, text=True, timeout=600)
         if r.returncode != 0:
             if "emulator build unavailable" in r.stderr or "g++" in r.stderr and "not found" in r.stderr:
