@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const T* __restrict__ g, 
 // BEFORE griddepcontrol.wait, under the tail of the q/k/v kernel (pos itself is only written by the non-PDL kernel that ends
 // a step, a full barrier); (2) both position loops keep 8-16 independent loads in flight per thread.
 constexpr int kAttnThreads = 256;
-template <typename T>
+template <typename T, bool BATCH>
 __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T* __restrict__ q_in, const T* __restrict__ k_in, const T* __restrict__ v_in,
                                                                         const T* __restrict__ cos_t, const T* __restrict__ sin_t,
                                                                         T* __restrict__ k_cache, T* __restrict__ v_cache, const long long* __restrict__ pos_p,
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
   float* ps = sm + 2 * hd;
   float* red = sm + max(2 * hd + L, NW * hd);
   const int h = blockIdx.x, kvh = h / (n_q / n_kv), d = threadIdx.x;
-  {
-    const long long b = blockIdx.y;  // batched decode: sequence b of the lock-step batch (all at the same position)
-    q_in += b * n_q * hd; out += b * n_q * hd;
+  if constexpr (BATCH) {  // sequence blockIdx.y of the lock-step batch (all at the same position); the one-sequence
+    const long long b = blockIdx.y;  // instantiation is the kernel as it was (its position loops lost 1 us per layer at 200
+    q_in += b * n_q * hd; out += b * n_q * hd;  // cached positions when the offsets were applied unconditionally)
     k_in += b * n_kv * hd; v_in += b * n_kv * hd;
     k_cache += b * n_kv * L * hd; v_cache += b * n_kv * L * hd;
   }
@@ -401,15 +401,16 @@ extern "C" int hqq_b200_glue_rope_attn_decode_batch(const void* q, const void* k
   const int body = 2 * head_dim + cache_len > 8 * head_dim ? 2 * head_dim + cache_len : 8 * head_dim;
   const size_t smem = (size_t)(body + 32) * sizeof(float);
   const float scale = 1.0f / sqrtf((float)head_dim);
-  if (dtype == HQQ_F16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__half>, dim3(n_q_heads, batch), dim3(kAttnThreads), smem, st, (const __half*)q, (const __half*)k,
-                      (const __half*)v, (const __half*)cos_table, (const __half*)sin_table, (__half*)k_cache, (__half*)v_cache, (const long long*)pos,
-                      (__half*)out, n_q_heads, n_kv_heads, cache_len, head_dim, scale);
+  auto go = [&](auto kernel, auto tag) {
+    using T = decltype(tag);
+    return launch_pdl("rope_attn_decode", kernel, dim3(n_q_heads, batch), dim3(kAttnThreads), smem, st, (const T*)q, (const T*)k, (const T*)v,
+                      (const T*)cos_table, (const T*)sin_table, (T*)k_cache, (T*)v_cache, (const long long*)pos, (T*)out, n_q_heads, n_kv_heads,
+                      cache_len, head_dim, scale);
+  };
+  if (dtype == HQQ_F16) return batch > 1 ? go(rope_attn_decode_kernel<__half, true>, __half()) : go(rope_attn_decode_kernel<__half, false>, __half());
   if (dtype == HQQ_BF16)
-    return launch_pdl("rope_attn_decode", rope_attn_decode_kernel<__nv_bfloat16>, dim3(n_q_heads, batch), dim3(kAttnThreads), smem, st, (const __nv_bfloat16*)q,
-                      (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
-                      (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, (const long long*)pos, (__nv_bfloat16*)out, n_q_heads, n_kv_heads, cache_len,
-                      head_dim, scale);
+    return batch > 1 ? go(rope_attn_decode_kernel<__nv_bfloat16, true>, __nv_bfloat16())
+                     : go(rope_attn_decode_kernel<__nv_bfloat16, false>, __nv_bfloat16());
   set_error("hqq_b200_glue_rope_attn_decode: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }
