@@ -63,7 +63,6 @@ struct Args {
   int M, N, K;
   int step;  // packed rows = N / F
   int Gk;    // groups per row = K / GS
-  int k2;    // 1: the MMAs of a tile alternate between the two TMEM accumulators (even / odd 16-k steps), summed by the epilogue
   Sched sched;
 };
 
@@ -367,12 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
       const Item im = decode_item(a, j);
       if (!im.valid) continue;
-      // k2: consecutive tcgen05.mma on ONE accumulator tile serialise on the accumulate chain (bare stream: 889 cycles per 64-k
-      // stage; alternating two accumulators: 681, tools/ummabench.cu "ss k2", profiles/r2_ummabench_k2.log).  Then a tile owns both
-      // TMEM buffers -- even 16-k steps accumulate into the first, odd ones into the second, the epilogue adds them -- and its
-      // drain is no longer hidden under the next tile's main loop.
-      const uint32_t k2 = (uint32_t)a.k2;
-      const uint32_t buf = k2 ? 0u : (q & 1), use = k2 ? q : (q >> 1);
+      const uint32_t buf = q & 1, use = q >> 1;
       mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // the epilogue has drained this accumulator (passes at once the first time)
       tc_fence_after();
       const uint32_t idesc = make_idesc<T>(im.un);
@@ -388,8 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
           const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * S::B_STAGE));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)  // UMMA_K = 16: advance 32 bytes inside the 128-byte swizzle row
-            tc_mma_f16(tmem_d + (k2 ? (uint32_t)(k & 1) * kUN : 0u), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                       ((kb - im.kb0) | (k2 ? (k >> 1) : k)) != 0);
+            tc_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((kb - im.kb0) | k) != 0);
           tc_commit(&empty[s]);                              // frees the stage when these MMAs have read it
           if (kb == im.kb1 - 1) tc_commit(&acc_full[buf]);   // accumulator complete
         }
@@ -523,8 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
     for (int j = blockIdx.x; j < n_items; j += gridDim.x) {
       const Item im = decode_item(a, j);
       if (!im.valid) continue;
-      const uint32_t k2 = (uint32_t)a.k2;
-      const uint32_t buf = k2 ? 0u : (q & 1), use = k2 ? q : (q >> 1);
+      const uint32_t buf = q & 1, use = q >> 1;
       const int prow0 = im.tile_n * PR;
       const bool n_ok = (prow0 + tp) < a.step;
       const int n = tf * a.step + prow0 + tp;
@@ -536,12 +528,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_gemm_kernel(const __grid_c
       for (int col = 0; col < im.un; col += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kUN + (uint32_t)col, v);
-        if (k2) {  // the odd 16-k steps' partial sums
-          uint32_t v2[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kUN + (uint32_t)col, v2);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
-        }
         if (a.sched.ksplit > 1) {
           // fp32 partial of this k-slice: [slice][tile][token][tile row] -- 32 lanes write 32 consecutive rows (128 bytes)
           float* wsp = a.ws + (((size_t)im.slice * (size_t)(a.sched.n_row * a.sched.n_tok) + (size_t)im.tile) * kUN + (size_t)col) * kTileRows + t;
@@ -674,12 +660,6 @@ static bool pdl_on() {
   return on == 1;
 }
 
-// HQQ_B200_GEMM_K2=0 (measurement hook): one accumulator per tile (double-buffered across tiles) instead of two alternating ones
-static int k2_on() {
-  HQQ_ENV_KNOB(on, ([] { const char* e = getenv("HQQ_B200_GEMM_K2"); return (e && e[0] == '0') ? 0 : 1; })());
-  return on;
-}
-
 // HQQ_B200_GEMM_KSPLIT=<n> (test / measurement hook): the largest number of k-slices the schedule may use (1 = never split)
 static int ksplit_cap() {
   HQQ_ENV_KNOB(cap, ([] { const char* e = getenv("HQQ_B200_GEMM_KSPLIT"); return e ? atoi(e) : 0; })());
@@ -733,7 +713,6 @@ static int launch(const void* x, Args& a, cudaStream_t st, const void* dense_W =
   constexpr int PR = NBITS == 16 ? kTileRows : kTileRows / (NBITS == 16 ? 1 : 8 / NBITS);
   const int P = persistent_ctas();
   a.sched = make_sched(a.M, a.K, cdiv(a.step, PR), P, NBITS != 16);
-  a.k2 = k2_on();
   a.ws = nullptr;
   if (a.sched.ksplit > 1) {
     const size_t need = splitk_ws_bytes(a.sched);
