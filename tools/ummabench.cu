@@ -131,7 +131,7 @@ constexpr int B_STAGE = UN * 128;
 constexpr int SMEM_BYTES = kStages * (A_STAGE + B_STAGE) + 1024 + 256;
 constexpr int kThreads = 64 + 256;
 
-enum { F_TS = 1, F_TMA = 2, F_ST = 4 };
+enum { F_TS = 1, F_TMA = 2, F_ST = 4, F_K2 = 8, F_N128 = 16 };  // F_K2: two K-interleaved accumulators; F_N128: two N = 128 accumulators
 
 __global__ void __launch_bounds__(kThreads, 1) bench_kernel(int flags, int iters, const uint8_t* __restrict__ gsrc, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
@@ -188,10 +188,25 @@ __global__ void __launch_bounds__(kThreads, 1) bench_kernel(int flags, int iters
       if (lane == 0) {
         const uint64_t adesc = make_desc_sw128(smem_u32(sA + s * A_STAGE));
         const uint64_t bdesc = make_desc_sw128(smem_u32(sB + s * B_STAGE));
+        if (flags & F_K2) {
+          // does the accumulate chain on ONE TMEM tile bound the stream?  even k -> accumulator 0, odd k -> accumulator 1 (256 columns each)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (ts) mma_ts(tmem_base, tmem_a0 + s * 32 + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          else mma_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_base + (uint32_t)(k & 1) * 256, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (k >> 1)) != 0);
+        } else if (flags & F_N128) {
+          // the same work as eight N = 128 instructions on two independent accumulators (token halves of the B tile)
+          const uint32_t idesc128 = make_idesc_f16(128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc128, (kb | k) != 0);
+            mma_ss(tmem_base + 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(1024 + k * 2), idesc128, (kb | k) != 0);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (ts) mma_ts(tmem_base, tmem_a0 + s * 32 + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else mma_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
         }
         tc_commit(&empty[s]);
         if (kb == iters - 1) tc_commit(done);
@@ -344,7 +359,8 @@ int main() {
   CK(cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int iters = 4096;  // stages per CTA: 4 MMAs of 128 x 256 x 16 each
   struct { const char* name; int flags; } modes[] = {{"ss", 0}, {"ss+tma", F_TMA}, {"ss+tma+st", F_TMA | F_ST}, {"ss+st", F_ST},
-                                                      {"ts", F_TS}, {"ts+tma", F_TS | F_TMA}, {"ts+tma+st", F_TS | F_TMA | F_ST}, {"ts+st", F_TS | F_ST}};
+                                                      {"ts", F_TS}, {"ts+tma", F_TS | F_TMA}, {"ts+tma+st", F_TS | F_TMA | F_ST}, {"ts+st", F_TS | F_ST},
+                                                      {"ss k2", F_K2}, {"ss k2+st", F_K2 | F_ST}, {"ss n128x2", F_N128}, {"ss n128x2+st", F_N128 | F_ST}};
   for (auto& m : modes) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaEvent_t e0, e1;
