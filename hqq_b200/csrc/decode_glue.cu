@@ -2,14 +2,31 @@
 // between the fused linears of a Llama-style block at batch 1, written so a decode step is 8 launches per block
 // instead of ~25 framework kernels.  fp16/bf16, one token.  All kernels are PDL-aware (griddepcontrol) so their
 // launch latency overlaps the tail of the previous kernel inside a CUDA graph.
+#ifndef HQQ_EMU
 #include <cooperative_groups.h>
+#endif
 
 #include "common.cuh"
 
 namespace hqq {
 
+#ifdef HQQ_EMU
+// CPU emulation (tests/emu): kernels and blocks run one after another, so the dependency instructions, the L2 prefetch and the
+// system-scope accesses are plain code; the cluster argmax (DSMEM) is not emulated
+__device__ __forceinline__ void pdl_wait_g() {}
+__device__ __forceinline__ void pdl_launch_g() {}
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void pdl_wait_g() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_g() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
@@ -78,7 +95,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_tp_kernel(T* __restrict__ h,
     float d = 0.f;
     for (int r = 0; r < tp; ++r) {
       uint32_t wv;
-      do { asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(wv) : "l"(part + (size_t)r * H + i) : "memory"); } while ((wv >> 16) != tag);
+      do { wv = ld_sys_u32(part + (size_t)r * H + i); } while ((wv >> 16) != tag);
       const unsigned short hb = (unsigned short)(wv & 0xFFFFu);
       d += to_f32<T>(*reinterpret_cast<const T*>(&hb));
     }
@@ -140,8 +157,8 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
     const char* vb = reinterpret_cast<const char*>(v_cache + (long long)kvh * L * hd);
     const int lines = (int)(((long long)pos * hd * (int)sizeof(T)) >> 7);
     for (int i = d; i < lines; i += kAttnThreads) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + ((long long)i << 7)));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + ((long long)i << 7)));
+      prefetch_l2(kb + ((long long)i << 7));
+      prefetch_l2(vb + ((long long)i << 7));
     }
   }
   pdl_wait_g();
@@ -239,6 +256,7 @@ __global__ void __launch_bounds__(kAttnThreads) rope_attn_decode_kernel(const T*
   }
 }
 
+#ifndef HQQ_EMU
 // argmax over n logits -> int64 index (first index on ties).  One thread-block cluster of 8 CTAs: each scans an
 // interleaved eighth of the row, the eight candidates meet in CTA 0's shared memory over DSMEM (no workspace, one launch).
 // key_offset >= 0 (vocabulary-sharded lm_head under tensor parallelism): out[0] = (ordered(max) >> 1) << 32 | (0xFFFFFFFF -
@@ -334,6 +352,8 @@ __global__ void __cluster_dims__(kArgmaxCtas, 1, 1) __launch_bounds__(1024) argm
   }
 }
 
+#endif  // !HQQ_EMU
+
 template <typename K, typename... Args>
 static int launch_pdl(const char* name, K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -422,6 +442,7 @@ extern "C" int hqq_b200_glue_rope_attn_decode(const void* q, const void* k, cons
                                               dtype, stream);
 }
 
+#ifndef HQQ_EMU
 extern "C" int hqq_b200_glue_argmax(const void* logits, int n, int64_t* out, int dtype, void* stream) {
   HQQ_REQUIRE(logits && out && n > 0, HQQ_E_INVALID, "hqq_b200_glue_argmax: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -456,3 +477,4 @@ extern "C" int hqq_b200_glue_argmax_tp(const void* logits, int n, int64_t index_
   set_error("hqq_b200_glue_argmax_tp: dtype must be f16/bf16");
   return HQQ_E_INVALID;
 }
+#endif  // !HQQ_EMU

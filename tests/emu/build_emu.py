@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY: build `libhqq_b200_emu.so` -- the *simple* kernels of hqq_b200/csrc (quantizer, bit-packing, 3-bit
-one-token forward) compiled by g++ against tests/emu/include/cuda_runtime.h and executed on the CPU by cooperative fibers.
+"""TEST INFRASTRUCTURE ONLY: build `libhqq_b200_emu.so` -- the kernels of hqq_b200/csrc (quantizer, bit-packing, small-M / one-token
+forward, tcgen05 GEMM, the decode glue kernels except the cluster argmax) compiled by g++ against tests/emu/include/cuda_runtime.h and
+executed on the CPU by cooperative fibers.
 
 The .cu sources are used as they are, except for two textual rewrites CUDA syntax forces on a C++ compiler:
   kernel<<<grid, block, smem, stream>>>(args)   ->  EMU_LAUNCH((kernel), grid, block, smem, stream)(args)
@@ -15,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "hqq_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libhqq_b200_emu.so")
-SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear_small.cu", "linear_gemm.cu", "linear.cu"]
+SOURCES = ["api.cu", "quantize.cu", "bitpack.cu", "linear_small.cu", "linear_gemm.cu", "linear.cu", "decode_glue.cu"]
 CUDA_INC = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 
 EXTRA = ''

@@ -495,3 +495,123 @@ def test_emulated_sharded_quantise_hooks_reproduce_the_one_call_path(emu, nbits,
         ia = finish(a[0], a[1], a[2], tot, W.size)[3]
         ib = finish(b[0], b[1], b[2], tot, W.size)[3]
         assert int(ia[0]) == int(ib[0]) == int(ref[3][0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Decode glue kernels (csrc/decode_glue.cu, harness): the same source on the emulator against numpy restatements of the framework
+# ops they replace.  (The cluster argmax is not emulated: DSMEM.)
+def _f16(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float16)
+
+
+def _rms_ref(h, delta, w, eps):
+    """h = fl16(h + delta); y = fl16(fl16(h * rsqrt(mean(h^2) + eps)) * w), all in fp16 like `h = h + o; F.rms_norm(h, w)`"""
+    x = h.astype(np.float32) if delta is None else (h.astype(np.float32) + delta.astype(np.float32)).astype(np.float16).astype(np.float32)
+    inv = 1.0 / np.sqrt((x.astype(np.float64) ** 2).mean(axis=-1, keepdims=True) + eps)
+    y = ((x * inv).astype(np.float16).astype(np.float32) * w.astype(np.float32)).astype(np.float16)
+    return x.astype(np.float16), y
+
+
+def test_emulated_add_rmsnorm_rows_and_silu_mul(emu):
+    rng = np.random.default_rng(21)
+    for rows, H in ((1, 4096), (5, 1024), (3, 8192), (2, 200)):
+        h = aligned((rows, H), np.float16); d = aligned((rows, H), np.float16); w = aligned((H,), np.float16); y = aligned((rows, H), np.float16)
+        h[...] = _f16(rng.standard_normal((rows, H))); d[...] = _f16(rng.standard_normal((rows, H))); w[...] = _f16(rng.random(H) + 0.5)
+        for delta in (d, None):
+            hh = aligned((rows, H), np.float16); hh[...] = h
+            rc = emu.hqq_b200_glue_add_rmsnorm_rows(P(hh), P(delta), P(w), P(y), rows, H, ctypes.c_float(1e-5), F16, None)
+            assert rc == 0, emu.hqq_b200_last_error()
+            h_ref, y_ref = _rms_ref(h, delta, w, 1e-5)
+            assert np.array_equal(hh, h_ref), (rows, H)                       # the residual stream: exactly fl16(h + delta)
+            assert np.abs(y.astype(np.float32) - y_ref.astype(np.float32)).max() <= 2 ** -8 * np.abs(y_ref.astype(np.float32)).max()
+            if rows > 1:                                                      # a row does not depend on its batch-mates
+                h1 = aligned((1, H), np.float16); h1[...] = h[1:2]; y1 = aligned((1, H), np.float16)
+                d1 = None
+                if delta is not None:
+                    d1 = aligned((1, H), np.float16); d1[...] = d[1:2]
+                assert emu.hqq_b200_glue_add_rmsnorm(P(h1), P(d1), P(w), P(y1), H, ctypes.c_float(1e-5), F16, None) == 0
+                assert np.array_equal(y1[0], y[1]) and np.array_equal(h1[0], hh[1])
+    n = 3 * 1792 + 5
+    g = aligned((n,), np.float16); u = aligned((n,), np.float16); o = aligned((n,), np.float16)
+    g[...] = _f16(rng.standard_normal(n) * 3); u[...] = _f16(rng.standard_normal(n))
+    assert emu.hqq_b200_glue_silu_mul(P(g), P(u), P(o), n, F16, None) == 0
+    gf = g.astype(np.float32)
+    ref = ((gf / (1.0 + np.exp(-gf))).astype(np.float16).astype(np.float32) * u.astype(np.float32)).astype(np.float16)
+    assert np.abs(o.astype(np.float32) - ref.astype(np.float32)).max() <= 2 ** -9 * max(1.0, np.abs(ref.astype(np.float32)).max())
+
+
+def _rope(x, cos, sin):
+    """x*cos + rotate_half(x)*sin with every product and the sum rounded to fp16 (the framework ops' rounding)"""
+    half = x.shape[-1] // 2
+    rot = np.concatenate([-x[..., half:], x[..., :half]], axis=-1)
+    a = (x.astype(np.float32) * cos.astype(np.float32)).astype(np.float16).astype(np.float32)
+    b = (rot.astype(np.float32) * sin.astype(np.float32)).astype(np.float16).astype(np.float32)
+    return (a + b).astype(np.float16)
+
+
+def test_emulated_rope_attention_one_sequence_and_lock_step_batch(emu):
+    """RoPE + KV-cache append + one-token GQA attention: cache rows written exactly, output against softmax(q k^T / sqrt(d)) v in
+    float64; the lock-step batch entry point equals the one-sequence one sequence by sequence."""
+    rng = np.random.default_rng(22)
+    hq, hkv, hd, L, B = 4, 2, 128, 96, 3
+    inv = 1.0 / (500000.0 ** (np.arange(0, hd, 2, dtype=np.float64) / hd))
+    fr = np.outer(np.arange(L, dtype=np.float64), inv)
+    cos = aligned((L, hd), np.float16); sin = aligned((L, hd), np.float16)
+    cos[...] = _f16(np.concatenate([np.cos(fr), np.cos(fr)], -1)); sin[...] = _f16(np.concatenate([np.sin(fr), np.sin(fr)], -1))
+    kc0 = _f16(rng.standard_normal((B, hkv, L, hd))); vc0 = _f16(rng.standard_normal((B, hkv, L, hd)))
+    for pos in (0, 1, 37, 64, 95):
+        q = aligned((B, hq * hd), np.float16); k = aligned((B, hkv * hd), np.float16); v = aligned((B, hkv * hd), np.float16)
+        q[...] = _f16(rng.standard_normal(q.shape)); k[...] = _f16(rng.standard_normal(k.shape)); v[...] = _f16(rng.standard_normal(v.shape))
+        kc = aligned(kc0.shape, np.float16); vc = aligned(vc0.shape, np.float16); out = aligned((B, hq * hd), np.float16)
+        kc[...] = kc0; vc[...] = vc0
+        p = aligned((1,), np.int64); p[0] = pos
+        rc = emu.hqq_b200_glue_rope_attn_decode_batch(P(q), P(k), P(v), P(cos), P(sin), P(kc), P(vc), P(p), P(out), hq, hkv, L, hd, B, F16, None)
+        assert rc == 0, emu.hqq_b200_last_error()
+        for b in range(B):
+            qr = _rope(q[b].reshape(hq, hd), cos[pos], sin[pos]); kr = _rope(k[b].reshape(hkv, hd), cos[pos], sin[pos])
+            kref, vref = kc0[b].copy(), vc0[b].copy()
+            kref[:, pos] = kr; vref[:, pos] = v[b].reshape(hkv, hd)
+            assert np.array_equal(kc[b], kref) and np.array_equal(vc[b], vref), (pos, b)
+            for h in range(hq):
+                g = h // (hq // hkv)
+                s = (kref[g, :pos + 1].astype(np.float64) @ qr[h].astype(np.float64)) / np.sqrt(hd)
+                w = np.exp(s - s.max()); w /= w.sum()
+                ref = w @ vref[g, :pos + 1].astype(np.float64)
+                got = out[b, h * hd:(h + 1) * hd].astype(np.float64)
+                assert np.abs(got - ref).max() <= 4e-3 * max(1.0, np.abs(ref).max()), (pos, b, h)
+            # the one-sequence entry point on sequence b alone: bit-identical
+            q1 = aligned((1, hq * hd), np.float16); k1 = aligned((1, hkv * hd), np.float16); v1 = aligned((1, hkv * hd), np.float16)
+            q1[...] = q[b:b + 1]; k1[...] = k[b:b + 1]; v1[...] = v[b:b + 1]
+            kc1 = aligned(kc0[b].shape, np.float16); vc1 = aligned(vc0[b].shape, np.float16); o1 = aligned((1, hq * hd), np.float16)
+            kc1[...] = kc0[b]; vc1[...] = vc0[b]
+            assert emu.hqq_b200_glue_rope_attn_decode(P(q1), P(k1), P(v1), P(cos), P(sin), P(kc1), P(vc1), P(p), P(o1), hq, hkv, L, hd, F16, None) == 0
+            assert np.array_equal(o1[0], out[b]) and np.array_equal(kc1, kc[b]) and np.array_equal(vc1, vc[b]), (pos, b)
+
+
+def test_emulated_add_rmsnorm_of_tagged_tensor_parallel_partials(emu):
+    """hqq_b200_glue_add_rmsnorm_tp: the residual delta is the fp32 sum of `tp` tagged partial vectors {tag16 : value16} in this
+    rank's exchange buffer (rounded once), the step counter is bumped; words of another exchange (other parity) are not touched."""
+    rng = np.random.default_rng(23)
+    H, tp, nb = 1024, 4, 3
+    for step, x_index in ((0, 3), (5, 3), (6, 3)):
+        ex = step * nb + x_index
+        parts = _f16(rng.standard_normal((tp, H)))
+        buf = aligned((2, tp, H), np.uint32)
+        buf[...] = 0xFFFFFFFF
+        buf[ex & 1] = (np.uint32(ex & 0xFFFF) << np.uint32(16)) | parts.view(np.uint16).astype(np.uint32)
+        h = aligned((1, H), np.float16); w = aligned((H,), np.float16); y = aligned((1, H), np.float16)
+        h0 = _f16(rng.standard_normal((1, H))); h[...] = h0; w[...] = _f16(rng.random(H) + 0.5)
+        ctr = aligned((1,), np.int32); ctr[0] = step
+        rc = emu.hqq_b200_glue_add_rmsnorm_tp(P(h), P(buf), P(ctr), x_index, nb, tp, P(w), P(y), H, ctypes.c_float(1e-5), F16, None)
+        assert rc == 0, emu.hqq_b200_last_error()
+        delta = parts.astype(np.float32).sum(axis=0, dtype=np.float32).astype(np.float16)   # fp32 sum in rank order, one rounding
+        # (rank order matters in fp32: replay it exactly)
+        acc = np.zeros(H, dtype=np.float32)
+        for r in range(tp):
+            acc = (acc + parts[r].astype(np.float32)).astype(np.float32)
+        delta = acc.astype(np.float16)
+        h_ref, y_ref = _rms_ref(h0, delta.reshape(1, H), w, 1e-5)
+        assert np.array_equal(h, h_ref)
+        assert np.abs(y.astype(np.float32) - y_ref.astype(np.float32)).max() <= 2 ** -8 * np.abs(y_ref.astype(np.float32)).max()
+        assert int(ctr[0]) == step + 1
+        assert np.all(buf[(ex & 1) ^ 1] == 0xFFFFFFFF)
